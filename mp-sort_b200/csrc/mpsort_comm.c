@@ -1,0 +1,421 @@
+/*
+ * mpsort_comm.c -- the communicator of mpsort-b200: what replaces MPI_Comm and the
+ * MPI calls of the reference (inventory: SURVEY.md 2.2, call sites C1-C14).
+ *
+ * Three transports behind one struct:
+ *   SELF   one rank, no collective at all (single-GPU path)
+ *   NCCL   one process per GPU; ncclAllReduce / ncclAllGather for counts, grouped
+ *          ncclSend/ncclRecv over NVLink for the record exchange
+ *          (replaces MPI_Alltoallv and MPI_Alltoallv_sparse, mp-mpiu.c:69-236)
+ *   LOCAL  ranks are host threads of one process; records move with
+ *          cudaMemcpyAsync (peer or same-device copies), counts through host memory
+ */
+#include <stdarg.h>
+#include <string.h>
+#include <unistd.h>
+
+#include "mpsort_internal.h"
+
+__thread const char * mps_caller_file = "?";
+__thread int mps_caller_line = 0;
+
+void mps_fatal(struct mpsort_comm * c, const char * file, int line, const char * fmt, ...)
+{
+    va_list va;
+    fprintf(stderr, "MPSort: ");
+    va_start(va, fmt);
+    vfprintf(stderr, fmt, va);
+    va_end(va);
+    fprintf(stderr, " [%s:%d, rank %d]. Caller site: %s:%d\n",
+            file, line, c ? c->rank : -1, mps_caller_file, mps_caller_line);
+    fflush(stderr);
+    if (c && c->kind == MPS_T_NCCL && c->nccl) {
+        /* the moral equivalent of MPI_Abort(comm, -1): do not leave peers spinning */
+        ncclCommAbort(c->nccl);
+    }
+    abort();
+}
+
+/* ------------------------------------------------------------------------- */
+/* allocator hook (reference mp-mpiu.c:9-59) for host allocations             */
+
+static void * default_malloc(const char * name, size_t size, const char * file, const int line, void * ud)
+{ (void) name; (void) file; (void) line; (void) ud; return malloc(size); }
+static void default_free(void * ptr, const char * file, const int line, void * ud)
+{ (void) file; (void) line; (void) ud; free(ptr); }
+
+static struct {
+    mpiu_malloc_func malloc_func;
+    mpiu_free_func free_func;
+    void * userdata;
+} g_mem = { default_malloc, default_free, NULL };
+
+void mpiu_set_malloc(mpiu_malloc_func m, mpiu_free_func f, void * userdata)
+{
+    g_mem.malloc_func = m ? m : default_malloc;
+    g_mem.free_func = f ? f : default_free;
+    g_mem.userdata = userdata;
+}
+
+void * mps_host_malloc(const char * name, size_t size, const char * file, int line)
+{
+    return g_mem.malloc_func(name, size, file, line, g_mem.userdata);
+}
+void mps_host_free(void * ptr, const char * file, int line)
+{
+    g_mem.free_func(ptr, file, line, g_mem.userdata);
+}
+
+void MPIU_Set_verbose_malloc(mpsort_comm_t comm)
+{
+    if (comm) comm->verbose_malloc = 1;
+}
+
+/* ------------------------------------------------------------------------- */
+/* arena                                                                      */
+
+static const char * slot_names[MPS_NSLOTS] = {
+    "din", "dout", "keywords", "keys_b", "keys_a", "idx_a", "idx_b", "sortedkeys",
+    "hist", "lookback", "sendbuf", "recvbuf", "splitters", "stage", "stage2", "misc"
+};
+
+void * mps_arena_get(struct mpsort_comm * c, int slot, size_t bytes)
+{
+    if (bytes == 0) bytes = 256;
+    if (c->slot[slot].cap >= bytes) return c->slot[slot].ptr;
+    if (c->slot[slot].ptr) {
+        /* buffers may still be in use by work queued on the stream */
+        CUDA_OK(c, cudaStreamSynchronize(c->stream));
+        CUDA_OK(c, cudaFree(c->slot[slot].ptr));
+        if (c->verbose_malloc)
+            fprintf(stderr, "MPIU_Free: T%04d %16p : device arena '%s'\n", c->rank, c->slot[slot].ptr, slot_names[slot]);
+        c->slot[slot].ptr = NULL;
+        c->slot[slot].cap = 0;
+    }
+    /* round up to 2 MiB so that slowly growing inputs do not reallocate every call */
+    size_t cap = (bytes + ((size_t) 2 << 20) - 1) & ~(((size_t) 2 << 20) - 1);
+    void * p = NULL;
+    cudaError_t e = cudaMalloc(&p, cap);
+    if (e != cudaSuccess) {
+        mps_fatal(c, __FILE__, __LINE__, "cannot allocate %zu bytes of device memory for '%s' (%s)",
+                  cap, slot_names[slot], cudaGetErrorString(e));
+    }
+    if (c->verbose_malloc)
+        fprintf(stderr, "MPIU_Malloc: T%04d %16p : device arena '%s' size = %zu\n", c->rank, p, slot_names[slot], cap);
+    c->slot[slot].ptr = p;
+    c->slot[slot].cap = cap;
+    return p;
+}
+
+void * mps_host_stage(struct mpsort_comm * c, size_t bytes)
+{
+    if (c->h_stage_cap >= bytes) return c->h_stage;
+    if (c->h_stage) {
+        CUDA_OK(c, cudaStreamSynchronize(c->stream));   /* async copies may still read it */
+        CUDA_OK(c, cudaFreeHost(c->h_stage));
+    }
+    size_t cap = bytes < 65536 ? 65536 : bytes;
+    CUDA_OK(c, cudaMallocHost(&c->h_stage, cap));
+    c->h_stage_cap = cap;
+    return c->h_stage;
+}
+
+/* ------------------------------------------------------------------------- */
+/* construction                                                               */
+
+static struct mpsort_comm * comm_alloc(int kind, int rank, int size, int device)
+{
+    struct mpsort_comm * c = (struct mpsort_comm *) calloc(1, sizeof(*c));
+    if (!c) { fprintf(stderr, "MPSort: out of host memory\n"); abort(); }
+    c->kind = kind; c->rank = rank; c->size = size; c->device = device;
+    if (size > MPS_MAX_RANKS) mps_fatal(c, __FILE__, __LINE__, "communicator size %d exceeds the supported maximum %d", size, MPS_MAX_RANKS);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        mps_fatal(c, __FILE__, __LINE__,
+                  "no CUDA device available (%s): mpsort-b200 has no CPU fallback",
+                  cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= ndev) mps_fatal(c, __FILE__, __LINE__, "device %d out of range (have %d)", device, ndev);
+    CUDA_OK(c, cudaSetDevice(device));
+    CUDA_OK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    return c;
+}
+
+int mpsort_comm_get_unique_id(void * id)
+{
+    ncclUniqueId uid;
+    if (sizeof(uid) > MPSORT_UNIQUE_ID_BYTES) return -1;
+    ncclResult_t r = ncclGetUniqueId(&uid);
+    if (r != ncclSuccess) {
+        fprintf(stderr, "MPSort: ncclGetUniqueId failed: %s\n", ncclGetErrorString(r));
+        return (int) r;
+    }
+    memset(id, 0, MPSORT_UNIQUE_ID_BYTES);
+    memcpy(id, &uid, sizeof(uid));
+    return 0;
+}
+
+mpsort_comm_t mpsort_comm_init_rank(int rank, int size, const void * unique_id, int device)
+{
+    if (size <= 1) return mpsort_comm_self(device);
+    struct mpsort_comm * c = comm_alloc(MPS_T_NCCL, rank, size, device);
+    ncclUniqueId uid;
+    memcpy(&uid, unique_id, sizeof(uid));
+    NCCL_OK(c, ncclCommInitRank(&c->nccl, size, uid, rank));
+    return c;
+}
+
+mpsort_comm_t mpsort_comm_self(int device)
+{
+    return comm_alloc(MPS_T_SELF, 0, 1, device);
+}
+
+int mpsort_comm_init_local_group(int size, const int * devices, mpsort_comm_t * comms)
+{
+    int i, j;
+    if (size < 1 || size > MPS_MAX_RANKS) return -1;
+    if (size == 1) { comms[0] = mpsort_comm_self(devices[0]); return 0; }
+    struct mps_local_group * g = (struct mps_local_group *) calloc(1, sizeof(*g));
+    if (!g) return -2;
+    g->size = size;
+    g->refcount = size;
+    pthread_barrier_init(&g->barrier, NULL, (unsigned) size);
+    pthread_mutex_init(&g->lock, NULL);
+    for (i = 0; i < size; i++) {
+        comms[i] = comm_alloc(MPS_T_LOCAL, i, size, devices[i]);
+        comms[i]->grp = g;
+    }
+    /* kernels of one rank read buffers of the others: enable peer access between
+     * distinct devices (same-device ranks need nothing) */
+    for (i = 0; i < size; i++) {
+        for (j = 0; j < size; j++) {
+            if (devices[i] == devices[j]) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, devices[i], devices[j]);
+            if (!can) continue;
+            cudaSetDevice(devices[i]);
+            cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        }
+    }
+    return 0;
+}
+
+void mpsort_comm_destroy(mpsort_comm_t c)
+{
+    int s;
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (s = 0; s < MPS_NSLOTS; s++) if (c->slot[s].ptr) cudaFree(c->slot[s].ptr);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->kind == MPS_T_NCCL && c->nccl) ncclCommDestroy(c->nccl);
+    if (c->kind == MPS_T_LOCAL && c->grp) {
+        int last;
+        pthread_mutex_lock(&c->grp->lock);
+        last = (--c->grp->refcount == 0);
+        pthread_mutex_unlock(&c->grp->lock);
+        if (last) {
+            pthread_barrier_destroy(&c->grp->barrier);
+            pthread_mutex_destroy(&c->grp->lock);
+            free(c->grp);
+        }
+    }
+    if (c->timers.created) { int i; for (i = 0; i < MPS_MAX_TIMERS; i++) cudaEventDestroy(c->timers.ev[i]); }
+    cudaStreamDestroy(c->stream);
+    free(c);
+}
+
+int mpsort_comm_rank(mpsort_comm_t c) { return c->rank; }
+int mpsort_comm_size(mpsort_comm_t c) { return c->size; }
+int mpsort_comm_device(mpsort_comm_t c) { return c->device; }
+void * mpsort_comm_stream(mpsort_comm_t c) { return (void *) c->stream; }
+
+/* ------------------------------------------------------------------------- */
+/* small host collectives                                                     */
+
+static void local_barrier(struct mpsort_comm * c)
+{
+    pthread_barrier_wait(&c->grp->barrier);
+}
+
+void mpsort_comm_allgatherv_host(mpsort_comm_t c, const void * send, size_t nbytes,
+                                 void * recv, const size_t * recvcounts)
+{
+    int j;
+    size_t total = 0, myoff = 0;
+    for (j = 0; j < c->size; j++) {
+        if (j == c->rank) myoff = total;
+        total += recvcounts[j];
+    }
+    if (recvcounts[c->rank] != nbytes) mps_fatal(c, __FILE__, __LINE__, "allgatherv: inconsistent counts");
+    if (c->kind == MPS_T_SELF) {
+        if (nbytes) memmove(recv, send, nbytes);
+        return;
+    }
+    if (c->kind == MPS_T_LOCAL) {
+        c->grp->slot[c->rank] = send;
+        local_barrier(c);
+        size_t off = 0;
+        for (j = 0; j < c->size; j++) {
+            if (recvcounts[j]) memcpy((char *) recv + off, c->grp->slot[j], recvcounts[j]);
+            off += recvcounts[j];
+        }
+        local_barrier(c);
+        return;
+    }
+    /* NCCL: stage through device memory; every rank broadcasts its piece (grouped) */
+    CUDA_OK(c, cudaSetDevice(c->device));
+    if (total == 0) return;
+    char * h = (char *) mps_host_stage(c, total);
+    char * d = (char *) mps_arena_get(c, MPS_S_STAGE, total);
+    if (nbytes) {
+        memcpy(h + myoff, send, nbytes);
+        CUDA_OK(c, cudaMemcpyAsync(d + myoff, h + myoff, nbytes, cudaMemcpyHostToDevice, c->stream));
+    }
+    NCCL_OK(c, ncclGroupStart());
+    size_t off = 0;
+    for (j = 0; j < c->size; j++) {
+        if (recvcounts[j])
+            NCCL_OK(c, ncclBroadcast(d + off, d + off, recvcounts[j], ncclUint8, j, c->nccl, c->stream));
+        off += recvcounts[j];
+    }
+    NCCL_OK(c, ncclGroupEnd());
+    CUDA_OK(c, cudaMemcpyAsync(h, d, total, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    memcpy(recv, h, total);
+}
+
+void mpsort_comm_allgather_host(mpsort_comm_t c, const void * send, void * recv, size_t nbytes)
+{
+    int j;
+    if (c->kind == MPS_T_NCCL) {
+        /* equal pieces: one ncclAllGather (replaces the MPI_Allgathers of
+         * mpsort-mpi.c:633-640 and mp-mpiu.c:415-416) */
+        CUDA_OK(c, cudaSetDevice(c->device));
+        const size_t total = nbytes * (size_t) c->size;
+        if (total == 0) return;
+        char * h = (char *) mps_host_stage(c, total);
+        char * d = (char *) mps_arena_get(c, MPS_S_STAGE, total);
+        memcpy(h + nbytes * c->rank, send, nbytes);
+        CUDA_OK(c, cudaMemcpyAsync(d + nbytes * c->rank, h + nbytes * c->rank, nbytes, cudaMemcpyHostToDevice, c->stream));
+        NCCL_OK(c, ncclAllGather(d + nbytes * c->rank, d, nbytes, ncclUint8, c->nccl, c->stream));
+        CUDA_OK(c, cudaMemcpyAsync(h, d, total, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(c, cudaStreamSynchronize(c->stream));
+        memcpy(recv, h, total);
+        return;
+    }
+    size_t counts[MPS_MAX_RANKS];
+    for (j = 0; j < c->size; j++) counts[j] = nbytes;
+    mpsort_comm_allgatherv_host(c, send, nbytes, recv, counts);
+}
+
+void mpsort_comm_barrier(mpsort_comm_t c)
+{
+    if (c->kind == MPS_T_SELF) return;
+    if (c->kind == MPS_T_LOCAL) { local_barrier(c); return; }
+    char token = 1, all[MPS_MAX_RANKS];
+    mpsort_comm_allgather_host(c, &token, all, 1);
+}
+
+/* ------------------------------------------------------------------------- */
+/* device collectives                                                         */
+
+/* in-place sum of count u64 on the device, stream ordered.
+ * Replaces the two MPI_Allreduce per bisection round (mpsort-mpi.c:391-394). */
+void mps_comm_allreduce_u64_dev(struct mpsort_comm * c, uint64_t * dptr, size_t count)
+{
+    if (c->kind == MPS_T_SELF || count == 0) return;
+    if (c->kind == MPS_T_NCCL) {
+        NCCL_OK(c, ncclAllReduce(dptr, dptr, count, ncclUint64, ncclSum, c->nccl, c->stream));
+        return;
+    }
+    /* LOCAL: every rank's kernel sums all ranks' buffers into a private scratch */
+    const uint64_t * srcs[MPS_MAX_RANKS];
+    int j;
+    uint64_t * tmp = (uint64_t *) mps_arena_get(c, MPS_S_STAGE2, count * sizeof(uint64_t));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    c->grp->slot[c->rank] = dptr;
+    local_barrier(c);
+    for (j = 0; j < c->size; j++) srcs[j] = (const uint64_t *) c->grp->slot[j];
+    KERN_OK(c, mpsk_sum_u64(tmp, srcs, c->size, count, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    local_barrier(c);   /* everyone has read every dptr: now it may be overwritten */
+    CUDA_OK(c, cudaMemcpyAsync(dptr, tmp, count * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
+}
+
+/*
+ * The record exchange. Rank j's sorted records [cut[j][k], cut[j][k+1]) go to rank k
+ * and land at item offset sum_{j'<j} count[j'][k] of k's receive buffer, i.e. the
+ * receive buffer is laid out in source-rank order exactly like the reference's
+ * RecvDispl (mpsort-mpi.c:490-503).
+ *
+ * dense == 0 (AUTO / REQUIRE_SPARSE): zero-length pairs are skipped, the behaviour
+ *   of MPI_Alltoallv_sparse (mp-mpiu.c:184-214). Safe with NCCL because both sides
+ *   of every pair hold the same count matrix.
+ * dense != 0 (DISABLE_SPARSE): every pair is posted, like MPI_Alltoallv (mp-mpiu.c:140).
+ */
+void mps_comm_alltoallv_dev(struct mpsort_comm * c, const void * sendbuf, void * recvbuf,
+        const int64_t * cut, size_t elsize, int dense, uint64_t * bytes_remote)
+{
+    const int p = c->size, me = c->rank;
+    int j, k;
+    uint64_t remote = 0;
+#define CUT(j, k) cut[(size_t) (j) * (p + 1) + (k)]
+    /* my receive displacement for source j */
+    int64_t rdispl[MPS_MAX_RANKS + 1];
+    rdispl[0] = 0;
+    for (j = 0; j < p; j++) rdispl[j + 1] = rdispl[j] + (CUT(j, me + 1) - CUT(j, me));
+
+    if (c->kind == MPS_T_SELF) {
+        const int64_t cnt = CUT(0, 1) - CUT(0, 0);
+        if (cnt > 0 && sendbuf != recvbuf)
+            CUDA_OK(c, cudaMemcpyAsync(recvbuf, sendbuf, (size_t) cnt * elsize, cudaMemcpyDeviceToDevice, c->stream));
+        if (bytes_remote) *bytes_remote = 0;
+        return;
+    }
+    if (c->kind == MPS_T_NCCL) {
+        NCCL_OK(c, ncclGroupStart());
+        for (k = 0; k < p; k++) {
+            if (k == me) continue;
+            const int64_t scnt = CUT(me, k + 1) - CUT(me, k);
+            const int64_t rcnt = CUT(k, me + 1) - CUT(k, me);
+            if (scnt > 0 || dense) {
+                NCCL_OK(c, ncclSend((const char *) sendbuf + (size_t) CUT(me, k) * elsize,
+                                    (size_t) scnt * elsize, ncclUint8, k, c->nccl, c->stream));
+                remote += (uint64_t) scnt * elsize;
+            }
+            if (rcnt > 0 || dense) {
+                NCCL_OK(c, ncclRecv((char *) recvbuf + (size_t) rdispl[k] * elsize,
+                                    (size_t) rcnt * elsize, ncclUint8, k, c->nccl, c->stream));
+            }
+        }
+        NCCL_OK(c, ncclGroupEnd());
+        {
+            const int64_t cnt = CUT(me, me + 1) - CUT(me, me);
+            if (cnt > 0)
+                CUDA_OK(c, cudaMemcpyAsync((char *) recvbuf + (size_t) rdispl[me] * elsize,
+                                           (const char *) sendbuf + (size_t) CUT(me, me) * elsize,
+                                           (size_t) cnt * elsize, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        if (bytes_remote) *bytes_remote = remote;
+        return;
+    }
+    /* LOCAL: pull from every source's send buffer */
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));   /* my sendbuf is complete */
+    c->grp->slot2[me] = sendbuf;
+    local_barrier(c);
+    for (j = 0; j < p; j++) {
+        const int64_t cnt = CUT(j, me + 1) - CUT(j, me);
+        if (cnt <= 0) continue;
+        const char * src = (const char *) c->grp->slot2[j] + (size_t) CUT(j, me) * elsize;
+        CUDA_OK(c, cudaMemcpyAsync((char *) recvbuf + (size_t) rdispl[j] * elsize, src,
+                                   (size_t) cnt * elsize, cudaMemcpyDefault, c->stream));
+        if (j != me) remote += (uint64_t) cnt * elsize;
+    }
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    local_barrier(c);   /* sources may reuse their send buffers */
+    if (bytes_remote) *bytes_remote = remote;   /* bytes pulled, equals bytes pushed in total */
+#undef CUT
+}

@@ -1,0 +1,635 @@
+/*
+ * mpsort_host.c -- C host orchestration of the B200 distributed histogram sort.
+ *
+ * Mirrors, phase by phase, mpsort_mpi_newarray_impl and mpsort_mpi_histogram_sort
+ * of the reference (mpsort-mpi.c:161-331, :333-604); every device step is a
+ * hand-written sm_100a kernel from mpsort_kernels.cu, every collective goes
+ * through mpsort_comm.c (NCCL over NVLink in production).
+ *
+ *   reference phase (timer name)      here
+ *   -------------------------------   -------------------------------------------
+ *   FirstSort   radix_sort :369       local_sort(): extract+hist, onesweep passes
+ *   PmaxPmin    :375, :606-661        one host allgather of {n, outn, kmin, kmax}
+ *   findP       :383-441              byte-wise descent: count kernel + allreduce
+ *                                     + select kernel per level, no host round trip
+ *   LayDistr    :450-456              one host allgather of local CLT/CLE rows
+ *   LaySolve    :460-464, :663-727    mpsort_solve_layout() on every rank
+ *   Exchange    :571-592              payload gather (pack) + grouped send/recv
+ *   SecondSort  radix_sort :597       local_sort() of the received runs + gather
+ */
+#include <stdarg.h>
+#include <string.h>
+
+#include "mpsort_internal.h"
+
+void mpsort_cumulative_counts(int p, const int64_t * outnmemb, int64_t * C);
+int mpsort_key_range(int p, uint32_t nw, const int64_t * nmemb,
+        const uint64_t * kmin, const uint64_t * kmax,
+        uint64_t * Pmin, uint64_t * Pmax, uint64_t * prefix);
+
+/* ------------------------------------------------------------------------- */
+/* options (reference mpsort-mpi.c:17, :731-767)                              */
+
+static int _mpsort_mpi_options = 0;
+
+static void _mpsort_mpi_parse_env(void)
+{
+    static int parsed = 0;
+    if (parsed) return;
+    parsed = 1;
+    if (getenv("MPSORT_DISABLE_SPARSE_ALLTOALLV"))
+        _mpsort_mpi_options |= MPSORT_DISABLE_SPARSE_ALLTOALLV;
+    if (getenv("MPSORT_DISABLE_GATHER_SORT"))
+        _mpsort_mpi_options |= MPSORT_DISABLE_GATHER_SORT;
+    /* the reference looks up "MPSORT_REQUIRE_GATHER_SORT " with a trailing space
+     * (mpsort-mpi.c:741) and so never sees it; we honour the documented name */
+    if (getenv("MPSORT_REQUIRE_GATHER_SORT"))
+        _mpsort_mpi_options |= MPSORT_REQUIRE_GATHER_SORT;
+    if (getenv("MPSORT_REQUIRE_SPARSE_ALLTOALLV"))
+        _mpsort_mpi_options |= MPSORT_REQUIRE_SPARSE_ALLTOALLV;
+    if (getenv("MPSORT_VERIFY_CHECKSUM"))
+        _mpsort_mpi_options |= MPSORT_VERIFY_CHECKSUM;
+}
+
+void mpsort_mpi_set_options(int options)
+{
+    _mpsort_mpi_parse_env();
+    _mpsort_mpi_options |= options;
+}
+
+int mpsort_mpi_has_options(int options)
+{
+    _mpsort_mpi_parse_env();
+    return _mpsort_mpi_options & options;
+}
+
+void mpsort_mpi_unset_options(int options)
+{
+    _mpsort_mpi_parse_env();
+    _mpsort_mpi_options &= ~options;
+}
+
+/* ------------------------------------------------------------------------- */
+/* timers (reference mpsort-mpi.c:105-127): CUDA events on the comm's stream  */
+
+
+static struct {
+    char name[MPS_MAX_TIMERS][20];
+    double seconds[MPS_MAX_TIMERS];
+    int n;
+} g_last_run;
+static pthread_mutex_t g_last_run_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static void timer_reset(struct mpsort_comm * c)
+{
+    int i;
+    struct mps_timers * T = &c->timers;
+    if (!T->created) {
+        for (i = 0; i < MPS_MAX_TIMERS; i++) CUDA_OK(c, cudaEventCreate(&T->ev[i]));
+        T->created = 1;
+    }
+    T->n = 0;
+}
+
+static void timer_mark(struct mpsort_comm * c, const char * name)
+{
+    struct mps_timers * T = &c->timers;
+    if (T->n >= MPS_MAX_TIMERS) return;
+    CUDA_OK(c, cudaEventRecord(T->ev[T->n], c->stream));
+    snprintf(T->name[T->n], sizeof(T->name[0]), "%s", name);
+    T->n++;
+}
+
+/* called after the stream was synchronised; rank 0 publishes (the reference
+ * broadcasts the leader's timers, mpsort-mpi.c:306-313) */
+static void timer_publish(struct mpsort_comm * c)
+{
+    int i;
+    struct mps_timers * T = &c->timers;
+    if (c->rank != 0 || T->n < 1) return;
+    pthread_mutex_lock(&g_last_run_lock);
+    g_last_run.n = 0;
+    for (i = 1; i < T->n; i++) {
+        float ms = 0;
+        if (0 == strcmp(T->name[i], "END")) break;
+        if (cudaEventElapsedTime(&ms, T->ev[i - 1], T->ev[i]) != cudaSuccess) ms = 0;
+        snprintf(g_last_run.name[g_last_run.n], sizeof(g_last_run.name[0]), "%s", T->name[i]);
+        g_last_run.seconds[g_last_run.n] = ms * 1e-3;
+        g_last_run.n++;
+    }
+    pthread_mutex_unlock(&g_last_run_lock);
+}
+
+void mpsort_mpi_report_last_run(void)
+{
+    int i;
+    pthread_mutex_lock(&g_last_run_lock);
+    for (i = 0; i < g_last_run.n; i++) printf("%s: %g\n", g_last_run.name[i], g_last_run.seconds[i]);
+    pthread_mutex_unlock(&g_last_run_lock);
+}
+
+int mpsort_mpi_get_last_run(const char ** names, double * seconds, int max)
+{
+    int i;
+    pthread_mutex_lock(&g_last_run_lock);
+    for (i = 0; i < g_last_run.n && i < max; i++) {
+        if (names) names[i] = g_last_run.name[i];
+        if (seconds) seconds[i] = g_last_run.seconds[i];
+    }
+    i = g_last_run.n;
+    pthread_mutex_unlock(&g_last_run_lock);
+    return i;
+}
+
+void mpsort_comm_last_stats(mpsort_comm_t c, struct mpsort_last_stats * st, int64_t * sendcounts, int max)
+{
+    int i;
+    if (st) *st = c->stats;
+    if (sendcounts) for (i = 0; i < c->size && i < max; i++) sendcounts[i] = c->sendcounts[i];
+}
+
+/* ------------------------------------------------------------------------- */
+/* local sort: replaces radix_sort (radixsort.c:35-44)                        */
+
+struct sorted_view {
+    const uint64_t * skeys;   /* sorted packed key words, word w at skeys + w*stride */
+    size_t stride;
+    const uint32_t * idx;     /* idx[i] = original position of the i-th smallest record */
+    uint32_t nw;
+    uint32_t npasses;
+};
+
+static uint32_t key_words(const struct mpsort_radix_desc * d)
+{
+    return (uint32_t) (((size_t) d->width * d->nwords + 7) / 8);
+}
+
+/*
+ * Stable LSD radix sort of the n records at device pointer `dbase` by their
+ * descriptor key. Produces the permutation and (when want_keys) the sorted packed
+ * keys. Multi-word keys are sorted one 64-bit word at a time from the least
+ * significant word: each word costs 8 (key,idx) passes, and the next word is
+ * brought into the current order with one 8-byte gather.
+ * Digits that are constant over the whole array are skipped (their pass would be
+ * the identity permutation): small ids, 4-byte keys and post-exchange key ranges
+ * all profit.
+ */
+static void local_sort(struct mpsort_comm * c, const void * dbase, size_t n, size_t elsize,
+        const struct mpsort_radix_desc * desc, int want_keys, struct sorted_view * out)
+{
+    const uint32_t nw = key_words(desc);
+    uint32_t g, d;
+    memset(out, 0, sizeof(*out));
+    out->nw = nw;
+    out->stride = n;
+    if (n == 0) return;
+    if (n > MPSK_MAX_ITEMS)
+        mps_fatal(c, __FILE__, __LINE__, "%zu local items exceed the supported maximum %zu per rank", n, (size_t) MPSK_MAX_ITEMS);
+
+    uint64_t * kw = (uint64_t *) mps_arena_get(c, MPS_S_KW, (size_t) nw * n * sizeof(uint64_t));
+    uint64_t * kb = (uint64_t *) mps_arena_get(c, MPS_S_KB, n * sizeof(uint64_t));
+    uint64_t * ka = nw > 1 ? (uint64_t *) mps_arena_get(c, MPS_S_KA, n * sizeof(uint64_t)) : kw;
+    uint32_t * ia = (uint32_t *) mps_arena_get(c, MPS_S_IA, n * sizeof(uint32_t));
+    uint32_t * ib = (uint32_t *) mps_arena_get(c, MPS_S_IB, n * sizeof(uint32_t));
+    const size_t nhist = (size_t) nw * 8;
+    uint32_t * hist = (uint32_t *) mps_arena_get(c, MPS_S_HIST, nhist * 256 * sizeof(uint32_t) * 2);
+    uint32_t * bins = hist + nhist * 256;
+    void * scratch = mps_arena_get(c, MPS_S_SCRATCH, mpsk_onesweep_scratch_bytes(n));
+
+    CUDA_OK(c, cudaMemsetAsync(hist, 0, nhist * 256 * sizeof(uint32_t), c->stream));
+    for (g = 0; g < nw; g++) {
+        KERN_OK(c, mpsk_extract_keys(dbase, n, elsize, desc->offset, desc->width, desc->nwords,
+                                     desc->is_signed, g, kw + (size_t) g * n, hist + (size_t) g * 8 * 256, c->stream));
+    }
+    KERN_OK(c, mpsk_scan_histograms(hist, bins, (int) nhist, c->stream));
+
+    /* which digits are constant? (one small D2H per sort) */
+    uint32_t * hhist = (uint32_t *) mps_host_stage(c, nhist * 256 * sizeof(uint32_t));
+    CUDA_OK(c, cudaMemcpyAsync(hhist, hist, nhist * 256 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    unsigned char skip[MPS_MAX_KEY_WORDS * 8];
+    uint32_t todo = 0;
+    for (g = 0; g < nhist; g++) {
+        uint32_t b;
+        skip[g] = 0;
+        for (b = 0; b < 256; b++) {
+            if (hhist[(size_t) g * 256 + b] == (uint32_t) n) { skip[g] = 1; break; }
+        }
+        if (!skip[g]) todo++;
+    }
+    if (todo == 0) { skip[0] = 0; todo = 1; }  /* all keys equal: one pass yields the identity idx */
+
+    const uint32_t * cur_idx = NULL;     /* NULL = identity */
+    const uint64_t * cur_keys = NULL;    /* sorted keys of the word in progress */
+    uint32_t npasses = 0;
+    for (g = 0; g < nw; g++) {
+        int any = 0;
+        for (d = 0; d < 8; d++) if (!skip[g * 8 + d]) any = 1;
+        if (!any) continue;
+        /* keys of word g in the current order */
+        const uint64_t * kin;
+        uint64_t * kout;
+        if (cur_idx == NULL) {
+            kin = kw + (size_t) g * n;
+        } else {
+            KERN_OK(c, mpsk_gather_u64(kw + (size_t) g * n, cur_idx, ka == kw ? kb : ka, n, c->stream));
+            kin = (ka == kw ? kb : ka);
+        }
+        for (d = 0; d < 8; d++) {
+            if (skip[g * 8 + d]) continue;
+            /* ping-pong: never write into the original-order words of a multi-word key */
+            if (nw == 1) kout = (kin == kw) ? kb : kw;
+            else kout = (kin == ka) ? kb : ka;
+            uint32_t * vout = (cur_idx == ia) ? ib : ia;
+            KERN_OK(c, mpsk_onesweep_pass(kin, cur_idx, kout, vout, n, (int) (8 * d),
+                                          bins + (size_t) (g * 8 + d) * 256, scratch, c->stream));
+            kin = kout;
+            cur_idx = vout;
+            npasses++;
+        }
+        cur_keys = kin;
+    }
+    out->idx = cur_idx;
+    out->npasses = npasses;
+    if (want_keys) {
+        if (nw == 1) {
+            out->skeys = cur_keys;
+        } else {
+            uint64_t * sk = (uint64_t *) mps_arena_get(c, MPS_S_SK, (size_t) nw * n * sizeof(uint64_t));
+            for (g = 0; g < nw; g++)
+                KERN_OK(c, mpsk_gather_u64(kw + (size_t) g * n, cur_idx, sk + (size_t) g * n, n, c->stream));
+            out->skeys = sk;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* helpers                                                                    */
+
+static int is_device_pointer(struct mpsort_comm * c, const void * p)
+{
+    struct cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    (void) c;
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static uint64_t device_checksum(struct mpsort_comm * c, const void * d, size_t nbytes)
+{
+    uint64_t * dsum = (uint64_t *) mps_arena_get(c, MPS_S_MISC, 256);
+    uint64_t h = 0, all[MPS_MAX_RANKS];
+    int j;
+    CUDA_OK(c, cudaMemsetAsync(dsum, 0, sizeof(uint64_t), c->stream));
+    KERN_OK(c, mpsk_checksum(d, nbytes, dsum, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(&h, dsum, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    mpsort_comm_allgather_host(c, &h, all, sizeof(h));
+    h = 0;
+    for (j = 0; j < c->size; j++) h += all[j];
+    return h;
+}
+
+/* ------------------------------------------------------------------------- */
+/* the distributed histogram sort on device buffers                          */
+
+struct rank_info {
+    int64_t nmemb, outnmemb;
+    uint64_t kmin[MPS_MAX_KEY_WORDS], kmax[MPS_MAX_KEY_WORDS];
+};
+
+/* gather everything on one leader, sort there, scatter by outnmemb
+ * (reference: MPIU_Gather / MPIU_Scatter around the leaders' sort,
+ *  mpsort-mpi.c:276-304; leader = rank with most data, lowest on ties, mp-mpiu.c:465) */
+static void gather_sort(struct mpsort_comm * c, const void * dbase, void * dout, size_t elsize,
+        const struct mpsort_radix_desc * desc, const int64_t * nmemb, const int64_t * outnmemb)
+{
+    const int p = c->size;
+    int j, k, leader = 0;
+    int64_t total = 0;
+    for (j = 0; j < p; j++) {
+        total += nmemb[j];
+        if (nmemb[j] > nmemb[leader]) leader = j;
+    }
+    int64_t * cut = (int64_t *) malloc(sizeof(int64_t) * (size_t) p * (p + 1));
+    /* 1: everyone -> leader */
+    for (j = 0; j < p; j++) for (k = 0; k <= p; k++) cut[(size_t) j * (p + 1) + k] = (k <= leader) ? 0 : nmemb[j];
+    char * all = (char *) mps_arena_get(c, MPS_S_RECV, (size_t) (c->rank == leader ? total : 0) * elsize);
+    uint64_t remote = 0, r2 = 0;
+    mps_comm_alltoallv_dev(c, dbase, all, cut, elsize, 0, &remote);
+    for (k = 0; k < p; k++) c->sendcounts[k] = (k == leader) ? nmemb[c->rank] : 0;
+    timer_mark(c, "Gather");
+    /* 2: leader sorts */
+    char * sorted = (char *) mps_arena_get(c, MPS_S_SEND, (size_t) (c->rank == leader ? total : 0) * elsize);
+    if (c->rank == leader) {
+        struct sorted_view v;
+        local_sort(c, all, (size_t) total, elsize, desc, 0, &v);
+        KERN_OK(c, mpsk_gather_records(all, v.idx, sorted, (size_t) total, elsize, c->stream));
+        c->stats.first_sort_passes = v.npasses;
+    }
+    timer_mark(c, "FirstSort");
+    /* 3: leader -> everyone by outnmemb */
+    for (j = 0; j < p; j++) {
+        int64_t acc = 0;
+        for (k = 0; k <= p; k++) {
+            cut[(size_t) j * (p + 1) + k] = (j == leader) ? acc : 0;
+            if (k < p) acc += outnmemb[k];
+        }
+    }
+    mps_comm_alltoallv_dev(c, sorted, dout, cut, elsize, 0, &r2);
+    timer_mark(c, "Scatter");
+    c->stats.bytes_sent_remote = remote + r2;
+    c->stats.used_gather = 1;
+    free(cut);
+}
+
+static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
+        void * dout, size_t outn, size_t elsize, const struct mpsort_radix_desc * desc)
+{
+    const int p = c->size;
+    const uint32_t nw = key_words(desc);
+    int j, b, w;
+    struct sorted_view v1;
+
+    /* ---- sizes first: needed for the gather decision and the abort on mismatch.
+     * (MPIU_Segmenter_collect_sizes x2, mp-mpiu.c:394-425) */
+    struct rank_info mine, * info = (struct rank_info *) malloc(sizeof(struct rank_info) * (size_t) p);
+    memset(&mine, 0, sizeof(mine));
+    mine.nmemb = (int64_t) n;
+    mine.outnmemb = (int64_t) outn;
+    int64_t nmemb[MPS_MAX_RANKS], outnmemb[MPS_MAX_RANKS], C[MPS_MAX_RANKS + 1];
+    int64_t total = 0, totalout = 0;
+    if (p > 1) {
+        int64_t sz[2] = { (int64_t) n, (int64_t) outn }, allsz[2 * MPS_MAX_RANKS];
+        mpsort_comm_allgather_host(c, sz, allsz, sizeof(sz));
+        for (j = 0; j < p; j++) { nmemb[j] = allsz[2 * j]; outnmemb[j] = allsz[2 * j + 1]; }
+    } else {
+        nmemb[0] = (int64_t) n; outnmemb[0] = (int64_t) outn;
+    }
+    for (j = 0; j < p; j++) { total += nmemb[j]; totalout += outnmemb[j]; }
+    if (total != totalout) {
+        /* mpsort-mpi.c:225-232 */
+        if (c->rank == 0)
+            fprintf(stderr, "Input and output size mismatch: %td (in) != %td (out)"
+                            "Caller site: %s:%d\n", (ptrdiff_t) total, (ptrdiff_t) totalout,
+                            mps_caller_file, mps_caller_line);
+        mps_fatal(c, __FILE__, __LINE__, "total number of items in the output does not match the input");
+    }
+    mpsort_cumulative_counts(p, outnmemb, C);
+
+    timer_mark(c, "START");
+
+    /* ---- small-input path (mpsort-mpi.c:234-256): the reference merges tiny ranks
+     * into segments sorted by one leader; on GPUs the whole job is latency bound
+     * below a few thousand records, so everything goes to one leader. */
+    if (p > 1) {
+        int use_gather = 0;
+        if (mpsort_mpi_has_options(MPSORT_REQUIRE_GATHER_SORT)) {
+            use_gather = 1;
+            if (c->rank == 0)
+                fprintf(stderr, "MPSort: gathering all data to a single rank for sorting due to MPSORT_REQUIRE_GATHER_SORT. "
+                                "Total number of items is %ld. Caller site: %s:%d\n",
+                                (long) total, mps_caller_file, mps_caller_line);
+        } else if (mpsort_mpi_has_options(MPSORT_DISABLE_GATHER_SORT)) {
+            use_gather = 0;
+            if (c->rank == 0)
+                fprintf(stderr, "MPSort: disable gathering data into larger chunks due to MPSORT_DISABLE_GATHER_SORT. "
+                                "Caller site: %s:%d\n", mps_caller_file, mps_caller_line);
+        } else {
+            /* the reference's own cap: no more than 4 MiB in a segment (:235-238) */
+            use_gather = (total <= 65536) && ((size_t) total * elsize <= ((size_t) 4 << 20));
+        }
+        if (use_gather) {
+            gather_sort(c, dbase, dout, elsize, desc, nmemb, outnmemb);
+            timer_mark(c, "END");
+            free(info);
+            return;
+        }
+    }
+
+    /* ---- FirstSort */
+    local_sort(c, dbase, n, elsize, desc, p > 1, &v1);
+    c->stats.first_sort_passes = v1.npasses;
+    c->stats.key_words = nw;
+
+    if (p == 1) {
+        /* one rank: the exchange is a self copy and the second sort the identity
+         * (SURVEY.md appendix B.6): gather straight into the output */
+        if (dout != dbase) {
+            KERN_OK(c, mpsk_gather_records(dbase, v1.idx, dout, n, elsize, c->stream));
+        } else {
+            void * tmp = mps_arena_get(c, MPS_S_SEND, n * elsize);
+            KERN_OK(c, mpsk_gather_records(dbase, v1.idx, tmp, n, elsize, c->stream));
+            if (n) CUDA_OK(c, cudaMemcpyAsync(dout, tmp, n * elsize, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        c->sendcounts[0] = (int64_t) n;
+        timer_mark(c, "FirstSort");
+        timer_mark(c, "END");
+        free(info);
+        return;
+    }
+    timer_mark(c, "FirstSort");
+
+    /* ---- PmaxPmin (mpsort-mpi.c:606-661): ends of the locally sorted keys */
+    if (n > 0) {
+        uint64_t * h = (uint64_t *) mps_host_stage(c, 2 * MPS_MAX_KEY_WORDS * sizeof(uint64_t));
+        for (w = 0; w < (int) nw; w++) {
+            CUDA_OK(c, cudaMemcpyAsync(h + w, v1.skeys + (size_t) w * v1.stride, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_OK(c, cudaMemcpyAsync(h + MPS_MAX_KEY_WORDS + w, v1.skeys + (size_t) w * v1.stride + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        }
+        CUDA_OK(c, cudaStreamSynchronize(c->stream));
+        for (w = 0; w < (int) nw; w++) { mine.kmin[w] = h[w]; mine.kmax[w] = h[MPS_MAX_KEY_WORDS + w]; }
+    }
+    mpsort_comm_allgather_host(c, &mine, info, sizeof(mine));
+    uint64_t kmin[MPS_MAX_RANKS * MPS_MAX_KEY_WORDS], kmax[MPS_MAX_RANKS * MPS_MAX_KEY_WORDS];
+    uint64_t Pmin[MPS_MAX_KEY_WORDS], Pmax[MPS_MAX_KEY_WORDS], prefix0[MPS_MAX_KEY_WORDS];
+    for (j = 0; j < p; j++) for (w = 0; w < (int) nw; w++) {
+        kmin[(size_t) j * nw + w] = info[j].kmin[w];
+        kmax[(size_t) j * nw + w] = info[j].kmax[w];
+    }
+    const int level0 = mpsort_key_range(p, nw, nmemb, kmin, kmax, Pmin, Pmax, prefix0);
+    timer_mark(c, "PmaxPmin");
+
+    /* ---- findP: byte-wise descent to the key at global rank C[b]-1 for every
+     * boundary b. Any exact selection gives the reference's result because a
+     * splitter is only accepted when CLT < C <= CLE (internal-parallel.h:234-247),
+     * i.e. when it IS that key. */
+    const int ns = p - 1;
+    const int nlevels = 8 * (int) nw;
+    /* layout of the splitter slot: prefix[ns][nw] | target[ns] | counts[ns][256] | final[2*ns] */
+    const size_t sp_words = (size_t) ns * nw + ns + (size_t) ns * 256 + 2 * (size_t) ns;
+    uint64_t * d_sp = (uint64_t *) mps_arena_get(c, MPS_S_SPLIT, sp_words * sizeof(uint64_t));
+    uint64_t * d_prefix = d_sp;
+    uint64_t * d_target = d_prefix + (size_t) ns * nw;
+    uint64_t * d_counts = d_target + ns;
+    uint64_t * d_final = d_counts + (size_t) ns * 256;
+    {
+        uint64_t * h = (uint64_t *) mps_host_stage(c, ((size_t) ns * nw + ns) * sizeof(uint64_t));
+        for (b = 0; b < ns; b++) {
+            for (w = 0; w < (int) nw; w++) h[(size_t) b * nw + w] = prefix0[w];
+            h[(size_t) ns * nw + b] = (uint64_t) C[b + 1];
+        }
+        CUDA_OK(c, cudaMemcpyAsync(d_prefix, h, ((size_t) ns * nw + ns) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    }
+    int level, round = 0;
+    for (level = level0; level < nlevels; level++) {
+        KERN_OK(c, mpsk_splitter_count(v1.skeys, v1.stride, n, nw, d_prefix, ns, level, d_counts, c->stream));
+        mps_comm_allreduce_u64_dev(c, d_counts, (size_t) ns * 256);
+        KERN_OK(c, mpsk_splitter_select(d_counts, d_target, d_prefix, nw, ns, level, c->stream));
+        round++;
+        if (round <= 10) {
+            char name[20];
+            snprintf(name, sizeof(name), "bisect%04d", round);
+            timer_mark(c, name);
+        }
+    }
+    c->stats.splitter_rounds = (uint32_t) round;
+    KERN_OK(c, mpsk_splitter_final(v1.skeys, v1.stride, n, nw, d_prefix, ns, d_final, c->stream));
+    timer_mark(c, "findP");
+
+    /* ---- LayDistr: all-gather the local rows (replaces the 8-byte Alltoalls :450-456) */
+    int64_t * rows = (int64_t *) malloc(sizeof(int64_t) * 2 * (size_t) ns * p);
+    {
+        int64_t * h = (int64_t *) mps_host_stage(c, 2 * (size_t) ns * sizeof(int64_t));
+        CUDA_OK(c, cudaMemcpyAsync(h, d_final, 2 * (size_t) ns * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(c, cudaStreamSynchronize(c->stream));
+        int64_t myrow[2 * MPS_MAX_RANKS];
+        memcpy(myrow, h, 2 * (size_t) ns * sizeof(int64_t));
+        mpsort_comm_allgather_host(c, myrow, rows, 2 * (size_t) ns * sizeof(int64_t));
+    }
+    timer_mark(c, "LayDistr");
+
+    /* ---- LaySolve */
+    int64_t * clt = (int64_t *) malloc(sizeof(int64_t) * (size_t) ns * p);
+    int64_t * cle = (int64_t *) malloc(sizeof(int64_t) * (size_t) ns * p);
+    int64_t * cut = (int64_t *) malloc(sizeof(int64_t) * (size_t) p * (p + 1));
+    for (j = 0; j < p; j++) for (b = 0; b < ns; b++) {
+        clt[(size_t) j * ns + b] = rows[(size_t) j * 2 * ns + b];
+        cle[(size_t) j * ns + b] = rows[(size_t) j * 2 * ns + ns + b];
+    }
+    {
+        const int rc = mpsort_solve_layout(p, C, clt, cle, nmemb, cut);
+        if (rc != 0) mps_fatal(c, __FILE__, __LINE__, "serious bug: layout solver failed with code %d", rc);
+    }
+    /* consistency checks of mpsort-mpi.c:490-510 */
+    {
+        int64_t totrecv = 0;
+        for (j = 0; j < p; j++) totrecv += cut[(size_t) j * (p + 1) + c->rank + 1] - cut[(size_t) j * (p + 1) + c->rank];
+        if (totrecv != (int64_t) outn)
+            mps_fatal(c, __FILE__, __LINE__, "totrecv = %td, mismatch with %td", (ptrdiff_t) totrecv, (ptrdiff_t) outn);
+    }
+    for (j = 0; j < p; j++) c->sendcounts[j] = cut[(size_t) c->rank * (p + 1) + j + 1] - cut[(size_t) c->rank * (p + 1) + j];
+    timer_mark(c, "LaySolve");
+
+    /* ---- Exchange: pack (payload gather into destination-contiguous order; the
+     * destinations are contiguous slices of the sorted order, SendDispl[i] == myC[i]
+     * :483-501) then grouped send/recv */
+    void * sendbuf = mps_arena_get(c, MPS_S_SEND, n * elsize);
+    void * recvbuf = mps_arena_get(c, MPS_S_RECV, outn * elsize);
+    KERN_OK(c, mpsk_gather_records(dbase, v1.idx, sendbuf, n, elsize, c->stream));
+    timer_mark(c, "Pack");
+    const int dense = mpsort_mpi_has_options(MPSORT_DISABLE_SPARSE_ALLTOALLV)
+                      && !mpsort_mpi_has_options(MPSORT_REQUIRE_SPARSE_ALLTOALLV);
+    c->stats.dense_exchange = (uint32_t) dense;
+    mps_comm_alltoallv_dev(c, sendbuf, recvbuf, cut, elsize, dense, &c->stats.bytes_sent_remote);
+    timer_mark(c, "Exchange");
+
+    /* ---- SecondSort: the received buffer is p sorted runs in source-rank order;
+     * a stable sort of it restores global order with ties by (source rank, index) */
+    {
+        struct sorted_view v2;
+        local_sort(c, recvbuf, outn, elsize, desc, 0, &v2);
+        KERN_OK(c, mpsk_gather_records(recvbuf, v2.idx, dout, outn, elsize, c->stream));
+        c->stats.second_sort_passes = v2.npasses;
+    }
+    timer_mark(c, "SecondSort");
+    timer_mark(c, "END");
+
+    free(rows); free(clt); free(cle); free(cut); free(info);
+}
+
+/* ------------------------------------------------------------------------- */
+/* public entry points                                                        */
+
+static void validate(struct mpsort_comm * c, size_t elsize, const struct mpsort_radix_desc * d)
+{
+    if (!c) { fprintf(stderr, "MPSort: NULL communicator. Caller site: %s:%d\n", mps_caller_file, mps_caller_line); abort(); }
+    if (!d) mps_fatal(c, __FILE__, __LINE__, "NULL radix descriptor");
+    if (!(d->width == 1 || d->width == 2 || d->width == 4 || d->width == 8))
+        mps_fatal(c, __FILE__, __LINE__, "radix word width %u is not 1, 2, 4 or 8", d->width);
+    if (d->nwords < 1) mps_fatal(c, __FILE__, __LINE__, "radix descriptor has no words");
+    if (d->offset + (size_t) d->width * d->nwords > elsize)
+        mps_fatal(c, __FILE__, __LINE__, "radix key [%zu, %zu) does not fit in a %zu byte element",
+                  d->offset, d->offset + (size_t) d->width * d->nwords, elsize);
+    if (key_words(d) > MPS_MAX_KEY_WORDS)
+        mps_fatal(c, __FILE__, __LINE__, "radix size %zu bytes exceeds the supported maximum %d",
+                  (size_t) d->width * d->nwords, MPS_MAX_KEY_WORDS * 8);
+    if (elsize == 0) mps_fatal(c, __FILE__, __LINE__, "element size is zero");
+}
+
+void mpsort_mpi_newarray_desc_impl(void * base, size_t nmemb,
+        void * out, size_t outnmemb, size_t elsize,
+        const struct mpsort_radix_desc * desc, mpsort_comm_t c,
+        const int line, const char * file)
+{
+    mps_caller_file = file ? file : "?";
+    mps_caller_line = line;
+    validate(c, elsize, desc);
+    CUDA_OK(c, cudaSetDevice(c->device));
+
+    memset(&c->stats, 0, sizeof(c->stats));
+    memset(c->sendcounts, 0, sizeof(c->sendcounts));
+    c->stats.nmemb = nmemb; c->stats.outnmemb = outnmemb; c->stats.elsize = elsize;
+    c->stats.key_words = key_words(desc);
+    timer_reset(c);
+
+    /* host or device buffers? */
+    const int in_dev = (nmemb == 0) ? 1 : is_device_pointer(c, base);
+    const int out_dev = (outnmemb == 0) ? 1 : is_device_pointer(c, out);
+    const void * dbase = base;
+    void * dout = out;
+    if (!in_dev) {
+        void * din = mps_arena_get(c, MPS_S_DIN, nmemb * elsize);
+        CUDA_OK(c, cudaMemcpyAsync(din, base, nmemb * elsize, cudaMemcpyHostToDevice, c->stream));
+        dbase = din;
+    }
+    if (!out_dev) {
+        /* a separate staged output also for host in-place: saves the copy-back pass */
+        dout = mps_arena_get(c, MPS_S_DOUT, outnmemb * elsize);
+    } else if (out == base) {
+        dout = (void *) dbase;
+    }
+
+    uint64_t sum1 = 0;
+    const int verify = mpsort_mpi_has_options(MPSORT_VERIFY_CHECKSUM);
+    if (verify) sum1 = device_checksum(c, dbase, nmemb * elsize);
+
+    histogram_sort(c, dbase, nmemb, dout, outnmemb, elsize, desc);
+
+    if (verify) {
+        const uint64_t sum2 = device_checksum(c, dout, outnmemb * elsize);
+        if (sum1 != sum2)
+            mps_fatal(c, __FILE__, __LINE__, "Data changed after sorting; checksum mismatch");   /* :324-330 */
+    }
+    if (!out_dev && outnmemb > 0)
+        CUDA_OK(c, cudaMemcpyAsync(out, dout, outnmemb * elsize, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    timer_publish(c);
+}
+
+void mpsort_mpi_desc_impl(void * base, size_t nmemb, size_t elsize,
+        const struct mpsort_radix_desc * desc, mpsort_comm_t comm,
+        const int line, const char * file)
+{
+    mpsort_mpi_newarray_desc_impl(base, nmemb, base, nmemb, elsize, desc, comm, line, file);
+}
+
+void radix_sort_desc(void * base, size_t nmemb, size_t size,
+        const struct mpsort_radix_desc * desc, int device)
+{
+    /* one cached size-1 communicator per device and thread */
+    static __thread mpsort_comm_t self[64];
+    if (device < 0 || device >= 64) { fprintf(stderr, "MPSort: bad device %d\n", device); abort(); }
+    if (!self[device]) self[device] = mpsort_comm_self(device);
+    mpsort_mpi_newarray_desc_impl(base, nmemb, base, nmemb, size, desc, self[device], __LINE__, __FILE__);
+}

@@ -1,0 +1,113 @@
+/*
+ * mpsort_internal.h -- shared declarations of the C host code of mpsort-b200.
+ */
+#ifndef MPSORT_INTERNAL_H
+#define MPSORT_INTERNAL_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <pthread.h>
+
+#include <cuda_runtime_api.h>
+#include <nccl.h>
+
+#include "mpsort.h"
+#include "mpsort_kernels.h"
+
+#define MPS_MAX_RANKS 64
+#define MPS_MAX_KEY_WORDS 16
+
+enum mps_transport { MPS_T_SELF = 0, MPS_T_NCCL = 1, MPS_T_LOCAL = 2 };
+
+/* device arena slots (grow-only, per communicator) */
+enum mps_slot {
+    MPS_S_DIN = 0,     /* staged copy of a host input                  */
+    MPS_S_DOUT,        /* staged copy of a host output                 */
+    MPS_S_KW,          /* key words in original order  [nw][n] u64     */
+    MPS_S_KB,          /* ping-pong key buffer         [n] u64         */
+    MPS_S_KA,          /* second ping-pong key buffer (multi-word)     */
+    MPS_S_IA,          /* ping-pong index buffers      [n] u32         */
+    MPS_S_IB,
+    MPS_S_SK,          /* sorted key words (multi-word) [nw][n] u64    */
+    MPS_S_HIST,        /* histograms + scanned bins                    */
+    MPS_S_SCRATCH,     /* look-back status words                       */
+    MPS_S_SEND,        /* packed records, destination-contiguous       */
+    MPS_S_RECV,        /* received runs, source-rank order             */
+    MPS_S_SPLIT,       /* splitter state: prefix, target, counts, out  */
+    MPS_S_STAGE,       /* device side of small host collectives        */
+    MPS_S_STAGE2,      /* scratch for the in-process allreduce         */
+    MPS_S_MISC,        /* checksum / small outputs                     */
+    MPS_NSLOTS
+};
+
+struct mps_local_group {
+    int size;
+    pthread_barrier_t barrier;
+    pthread_mutex_t lock;
+    int refcount;
+    const void * slot[MPS_MAX_RANKS];
+    const void * slot2[MPS_MAX_RANKS];
+    size_t val[MPS_MAX_RANKS];
+};
+
+#define MPS_MAX_TIMERS 48
+struct mps_timers {
+    cudaEvent_t ev[MPS_MAX_TIMERS];
+    char name[MPS_MAX_TIMERS][20];
+    int n;
+    int created;
+};
+
+struct mpsort_comm {
+    int kind;
+    int rank, size, device;
+    cudaStream_t stream;
+    ncclComm_t nccl;
+    struct mps_local_group * grp;
+
+    struct { void * ptr; size_t cap; } slot[MPS_NSLOTS];
+    void * h_stage;        /* pinned */
+    size_t h_stage_cap;
+
+    int verbose_malloc;
+    struct mps_timers timers;
+
+    struct mpsort_last_stats stats;
+    int64_t sendcounts[MPS_MAX_RANKS];
+};
+
+/* ---- errors (reference convention: message incl. caller site, then abort) ---- */
+void mps_fatal(struct mpsort_comm * c, const char * file, int line, const char * fmt, ...)
+    __attribute__((noreturn, format(printf, 4, 5)));
+
+extern __thread const char * mps_caller_file;
+extern __thread int mps_caller_line;
+
+#define CUDA_OK(c, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) \
+    mps_fatal((c), __FILE__, __LINE__, "CUDA error %d (%s) in %s", (int) e__, cudaGetErrorString(e__), #call); } while (0)
+#define KERN_OK(c, call) do { int e__ = (call); if (e__ != 0) \
+    mps_fatal((c), __FILE__, __LINE__, "kernel launch error %d (%s) in %s", e__, cudaGetErrorString((cudaError_t) e__), #call); } while (0)
+#define NCCL_OK(c, call) do { ncclResult_t e__ = (call); if (e__ != ncclSuccess) \
+    mps_fatal((c), __FILE__, __LINE__, "NCCL error %d (%s) in %s", (int) e__, ncclGetErrorString(e__), #call); } while (0)
+
+/* ---- arena ---- */
+void * mps_arena_get(struct mpsort_comm * c, int slot, size_t bytes);
+void * mps_host_stage(struct mpsort_comm * c, size_t bytes);
+
+/* ---- communicator primitives (mpsort_comm.c) ---- */
+void mps_comm_allreduce_u64_dev(struct mpsort_comm * c, uint64_t * dptr, size_t count);
+/* items of elsize bytes; cut[j*(p+1) + k] = first item of rank j's sorted array that
+ * goes to rank k (full matrix, known on every rank) */
+void mps_comm_alltoallv_dev(struct mpsort_comm * c, const void * sendbuf, void * recvbuf,
+        const int64_t * cut, size_t elsize, int dense, uint64_t * bytes_remote);
+
+/* ---- layout solver (mpsort_layout.c; pure host arithmetic, unit-testable) ---- */
+/* C[p+1] desired cumulative output counts; clt/cle[j*(p-1) + b] local counts of rank j
+ * for splitter b; nmemb[j]; writes cut[j*(p+1) + k]. Returns 0, or a negative code on
+ * the reference's "serious bug" conditions (mpsort-mpi.c:707-716). */
+int mpsort_solve_layout(int p, const int64_t * C, const int64_t * clt, const int64_t * cle,
+        const int64_t * nmemb, int64_t * cut);
+
+#endif

@@ -1,0 +1,935 @@
+/*
+ * mpsort_kernels.cu -- hand-written sm_100a kernels of mpsort-b200.
+ *
+ * All kernels here are HBM-bound integer/byte work (no tensor cores: no stage of a
+ * sort is a dense contraction). Design rules applied throughout:
+ *   - coalesced warp-striped loads, shared-memory staging so that every global
+ *     store is a run of consecutive addresses,
+ *   - grids sized as multiples of the SM count for the streaming kernels,
+ *   - no global atomics on the hot path other than one ticket per tile and the
+ *     decoupled look-back status words.
+ *
+ * Kernel <-> reference map (paths relative to MP-sort v0.1.19):
+ *   extract_kernel        radix() callbacks               binding.pyx:81-121, bench-mpi.c:13-15
+ *   onesweep_kernel       mpsort_qsort_r / msort_with_tmp stdlib/msort.c:52-174,177-314
+ *   gather_records_kernel record moves of the merge sort  stdlib/msort.c:153-173,270-294
+ *   splitter_*_kernel     _histogram/_bsearch_last_lt/le  internal-parallel.h:8-126
+ *   checksum_kernel       checksum()                      mpsort-mpi.c:148-159
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "mpsort_kernels.h"
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+#define FULL_MASK 0xffffffffu
+
+static int g_num_sms = 0;
+static int num_sms()
+{
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+/* every kernel launch of this library passes through here: counted for bench.py's
+ * "gpu_launches" claim */
+static unsigned long long g_launches = 0;
+#define CUDA_LAUNCH_CHECK() do { __atomic_fetch_add(&g_launches, 1ULL, __ATOMIC_RELAXED); \
+    cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return (int) e__; } while (0)
+
+extern "C" uint64_t mpsk_launch_count(int reset)
+{
+    const unsigned long long v = __atomic_load_n(&g_launches, __ATOMIC_RELAXED);
+    if (reset) __atomic_store_n(&g_launches, 0ULL, __ATOMIC_RELAXED);
+    return (uint64_t) v;
+}
+
+__device__ __forceinline__ u32 lanemask_lt()
+{
+    u32 m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+/* ========================================================================= */
+/* K1: key extraction + 8 digit histograms                                   */
+/* ========================================================================= */
+
+struct KeyDesc {
+    size_t elsize;
+    size_t offset;
+    u32 width;
+    u32 nwords;
+    int is_signed;
+    u32 g;          /* which packed 64-bit word to produce */
+};
+
+/* little-endian load of `width` bytes, alignment-safe */
+__device__ __forceinline__ u64 load_narrow(const unsigned char * p, u32 width)
+{
+    switch (width) {
+        case 8:
+            if ((((uintptr_t) p) & 7) == 0) return *(const u64 *) p;
+            break;
+        case 4:
+            if ((((uintptr_t) p) & 3) == 0) return *(const u32 *) p;
+            break;
+        case 2:
+            if ((((uintptr_t) p) & 1) == 0) return *(const unsigned short *) p;
+            break;
+        default:
+            return *p;
+    }
+    u64 v = 0;
+    for (u32 b = 0; b < width; b++) v |= ((u64) p[b]) << (8 * b);
+    return v;
+}
+
+/* Packed 64-bit word g of the key of one record: key bytes [8g, 8g+8) of the
+ * little-endian byte string formed by the (sign-flipped) key words. */
+__device__ __forceinline__ u64 pack_key_word(const unsigned char * rec, const KeyDesc & d)
+{
+    const u32 per = 8 / d.width;
+    const u32 first = d.g * per;
+    u64 out = 0;
+#pragma unroll 1
+    for (u32 k = 0; k < per; k++) {
+        const u32 wi = first + k;
+        if (wi >= d.nwords) break;
+        u64 v = load_narrow(rec + d.offset + (size_t) wi * d.width, d.width);
+        if (d.is_signed) v ^= 1ULL << (8 * d.width - 1);
+        out |= v << (8 * d.width * k);
+    }
+    return out;
+}
+
+/* fast path of the benchmark configs: one aligned 8-byte word */
+__device__ __forceinline__ u64 load_key_fast8(const unsigned char * rec, size_t offset, u64 flip)
+{
+    return (*(const u64 *) (rec + offset)) ^ flip;
+}
+
+__device__ __forceinline__ void hist8_add(u32 * sh, u64 k, bool warp_full)
+{
+#pragma unroll
+    for (int d = 0; d < 8; d++) {
+        const u32 digit = (u32) (k >> (8 * d)) & 255u;
+        u32 * slot = &sh[d * 256 + digit];
+        if (warp_full) {
+            /* constant digits (small ids, zero high bytes) would serialise 32 same
+             * address atomics: one lane adds 32 instead */
+            int all_same;
+            __match_all_sync(FULL_MASK, digit, &all_same);
+            if (all_same) {
+                if ((threadIdx.x & 31) == 0) atomicAdd(slot, 32u);
+            } else {
+                atomicAdd(slot, 1u);
+            }
+        } else {
+            atomicAdd(slot, 1u);
+        }
+    }
+}
+
+template <bool FAST8>
+__global__ void __launch_bounds__(512)
+extract_kernel(const unsigned char * __restrict__ base, size_t n, KeyDesc d,
+               u64 * __restrict__ kout, u32 * __restrict__ hist)
+{
+    __shared__ u32 sh[8 * 256];
+    for (u32 t = threadIdx.x; t < 8 * 256; t += blockDim.x) sh[t] = 0;
+    __syncthreads();
+
+    const u64 flip = (d.is_signed ? (1ULL << 63) : 0ULL);
+    const size_t nthreads = (size_t) gridDim.x * blockDim.x;
+    const size_t nround = (n + 31) & ~(size_t) 31;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += nthreads) {
+        const bool valid = i < n;
+        const bool warp_full = __all_sync(FULL_MASK, valid);
+        if (valid) {
+            const unsigned char * rec = base + i * d.elsize;
+            u64 k;
+            if (FAST8) k = load_key_fast8(rec, d.offset, flip);
+            else k = pack_key_word(rec, d);
+            kout[i] = k;
+            hist8_add(sh, k, warp_full);
+        }
+    }
+    __syncthreads();
+    for (u32 t = threadIdx.x; t < 8 * 256; t += blockDim.x) {
+        const u32 c = sh[t];
+        if (c) atomicAdd(&hist[t], c);
+    }
+}
+
+extern "C" int mpsk_extract_keys(const void * base, size_t n, size_t elsize,
+        size_t offset, uint32_t width, uint32_t nwords, int is_signed,
+        uint32_t g, uint64_t * kout, uint32_t * hist, mpsk_stream_t stream)
+{
+    if (n == 0) return 0;
+    KeyDesc d;
+    d.elsize = elsize; d.offset = offset; d.width = width; d.nwords = nwords;
+    d.is_signed = is_signed; d.g = g;
+    const int threads = 512;
+    size_t blocks = (n + threads - 1) / threads;
+    const size_t maxb = (size_t) num_sms() * 8;
+    if (blocks > maxb) blocks = maxb;
+    const bool fast8 = (width == 8) && (nwords >= 1) && (elsize % 8 == 0)
+                       && (offset % 8 == 0) && ((((uintptr_t) base) & 7) == 0);
+    if (fast8) {
+        /* word g of an 8-byte-word key is simply word g */
+        d.offset = offset + (size_t) g * 8;
+        extract_kernel<true><<<(unsigned) blocks, threads, 0, (cudaStream_t) stream>>>(
+            (const unsigned char *) base, n, d, (u64 *) kout, hist);
+    } else {
+        extract_kernel<false><<<(unsigned) blocks, threads, 0, (cudaStream_t) stream>>>(
+            (const unsigned char *) base, n, d, (u64 *) kout, hist);
+    }
+    CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
+/* exclusive scan of nhist 256-bin histograms, one warp-synchronous block each */
+__global__ void __launch_bounds__(256)
+scan_hist_kernel(const u32 * __restrict__ hist, u32 * __restrict__ bins)
+{
+    __shared__ u32 wsum[8];
+    const u32 t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const u32 c = hist[blockIdx.x * 256 + t];
+    u32 incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 y = __shfl_up_sync(FULL_MASK, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    u32 add = 0;
+    for (u32 w = 0; w < warp; w++) add += wsum[w];
+    bins[blockIdx.x * 256 + t] = incl - c + add;
+}
+
+extern "C" int mpsk_scan_histograms(const uint32_t * hist, uint32_t * bins, int nhist, mpsk_stream_t stream)
+{
+    if (nhist <= 0) return 0;
+    scan_hist_kernel<<<nhist, 256, 0, (cudaStream_t) stream>>>(hist, bins);
+    CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
+/* ========================================================================= */
+/* K2: onesweep pass                                                         */
+/* ========================================================================= */
+
+#ifndef MPSK_SWEEP_THREADS
+#define MPSK_SWEEP_THREADS 384
+#endif
+#ifndef MPSK_SWEEP_IPT
+#define MPSK_SWEEP_IPT 16
+#endif
+#ifndef MPSK_SWEEP_MINBLOCKS
+#define MPSK_SWEEP_MINBLOCKS 2
+#endif
+#ifndef MPSK_USE_MATCH
+#define MPSK_USE_MATCH 1
+#endif
+
+constexpr u32 LB_PART = 1u << 30;
+constexpr u32 LB_INCL = 2u << 30;
+constexpr u32 LB_MASK = (1u << 30) - 1u;
+
+__device__ __forceinline__ u32 ld_relaxed_u32(const u32 * p)
+{
+    u32 v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(u32 * p, u32 v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+/* lanes of the warp whose digit equals mine */
+__device__ __forceinline__ u32 match_digit(u32 digit)
+{
+#if MPSK_USE_MATCH
+    return __match_any_sync(FULL_MASK, digit);
+#else
+    u32 peers = FULL_MASK;
+#pragma unroll
+    for (int b = 0; b < MPSK_RADIX_BITS; b++) {
+        const u32 bit = (digit >> b) & 1u;
+        const u32 vote = __ballot_sync(FULL_MASK, bit);
+        peers &= bit ? vote : ~vote;
+    }
+    return peers;
+#endif
+}
+
+template <int THREADS, int IPT>
+struct SweepCfg {
+    static constexpr int TILE = THREADS * IPT;
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int VAL_BYTES = (TILE * 4 > WARPS * 256 * 4) ? TILE * 4 : WARPS * 256 * 4;
+    static constexpr int SMEM = TILE * 8 + VAL_BYTES + 256 * 4 * 2 + 64;
+};
+
+/*
+ * One CTA sorts one tile of TILE (key,value) pairs by the 8-bit digit at `shift`
+ * and appends every digit's run to that digit's global output region. The global
+ * position of a tile's run is  bins[d] (all smaller digits, whole array)
+ *                            + sum over earlier tiles of their count of digit d,
+ * the second term found with a decoupled look-back over per-(tile,digit) status
+ * words {flag:2, count:30}. Tiles take a ticket so that every predecessor of a
+ * running tile has itself started (forward progress of the spin).
+ *
+ * Stability: tile order = ticket order = input order; inside a tile items are
+ * ranked in (warp, round j, lane) order, which is exactly the order they were
+ * loaded in (position = warp*IPT*32 + j*32 + lane).
+ */
+template <int THREADS, int IPT, bool IOTA>
+__global__ void __launch_bounds__(THREADS, MPSK_SWEEP_MINBLOCKS)
+onesweep_kernel(const u64 * __restrict__ kin, const u32 * __restrict__ vin,
+                u64 * __restrict__ kout, u32 * __restrict__ vout,
+                u32 n, u32 shift, const u32 * __restrict__ bins,
+                u32 * lookback, u32 * ticket)
+{
+    typedef SweepCfg<THREADS, IPT> Cfg;
+    constexpr int TILE = Cfg::TILE;
+    constexpr int WARPS = Cfg::WARPS;
+    static_assert(THREADS >= 256, "one thread per digit needs >= 256 threads");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 * s_keys = (u64 *) smem_raw;
+    u32 * s_vals = (u32 *) (smem_raw + TILE * 8);
+    u32 * s_whist = s_vals;   /* [WARPS][256]; dead before values are staged */
+    u32 * s_local = (u32 *) (smem_raw + TILE * 8 + Cfg::VAL_BYTES);
+    u32 * s_gofs = s_local + 256;
+    u32 * s_misc = s_gofs + 256;  /* [0] tile id, [1..8] digit-scan warp totals */
+
+    const u32 tid = threadIdx.x;
+    const u32 lane = tid & 31u;
+    const u32 warp = tid >> 5;
+
+    if (tid == 0) s_misc[0] = atomicAdd(ticket, 1u);
+    for (u32 i = tid; i < WARPS * 256; i += THREADS) s_whist[i] = 0;
+    __syncthreads();
+
+    const u32 tile = s_misc[0];
+    const u32 tile_base = tile * (u32) TILE;
+    const u32 remaining = n - tile_base;
+    const u32 valid = remaining < (u32) TILE ? remaining : (u32) TILE;
+    const u32 wbase = tile_base + warp * (IPT * 32) + lane;
+
+    /* ---- load keys, warp-striped: each load instruction covers 256 contiguous bytes */
+    u64 key[IPT];
+    if (valid == (u32) TILE) {
+#pragma unroll
+        for (int j = 0; j < IPT; j++) key[j] = kin[wbase + j * 32];
+    } else {
+#pragma unroll
+        for (int j = 0; j < IPT; j++) {
+            const u32 pos = wbase + j * 32;
+            key[j] = pos < n ? kin[pos] : ~0ULL;   /* padding ranks last in bin 255 */
+        }
+    }
+
+    /* ---- rank inside (warp, digit): match peers, leader bumps the warp counter */
+    u32 rank[IPT];
+    u32 * my_hist = s_whist + warp * 256;
+    const u32 lt = lanemask_lt();
+#pragma unroll
+    for (int j = 0; j < IPT; j++) {
+        const u32 digit = (u32) (key[j] >> shift) & 255u;
+        const u32 peers = match_digit(digit);
+        const u32 leader = __ffs(peers) - 1;
+        u32 c = 0;
+        if (lane == leader) {
+            c = my_hist[digit];
+            my_hist[digit] = c + __popc(peers);
+        }
+        c = __shfl_sync(FULL_MASK, c, leader);
+        rank[j] = c + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    /* ---- per digit: exclusive scan over warps, publish the tile count */
+    u32 cnt_full = 0, cnt_valid = 0;
+    if (tid < 256) {
+        u32 c[WARPS];
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) c[w] = s_whist[w * 256 + tid];
+        u32 run = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) {
+            s_whist[w * 256 + tid] = run;
+            run += c[w];
+        }
+        cnt_full = run;
+        cnt_valid = run;
+        if (tid == 255) cnt_valid -= ((u32) TILE - valid);
+        st_relaxed_u32(&lookback[(size_t) tile * 256 + tid],
+                       (tile == 0 ? LB_INCL : LB_PART) | cnt_valid);
+        /* digit scan, warp part */
+        u32 incl = cnt_full;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 y = __shfl_up_sync(FULL_MASK, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) s_misc[1 + warp] = incl;
+        cnt_full = incl - cnt_full;  /* exclusive within the warp of digits */
+    }
+    __syncthreads();
+    if (tid < 256) {
+        u32 add = 0;
+        for (u32 w = 0; w < warp; w++) add += s_misc[1 + w];
+        const u32 local = cnt_full + add;      /* first slot of digit tid in the sorted tile */
+        s_local[tid] = local;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) s_whist[w * 256 + tid] += local;
+    }
+    __syncthreads();
+
+    /* ---- scatter keys into tile-sorted order in shared memory */
+#pragma unroll
+    for (int j = 0; j < IPT; j++) {
+        const u32 digit = (u32) (key[j] >> shift) & 255u;
+        rank[j] += my_hist[digit];
+        s_keys[rank[j]] = key[j];
+    }
+
+    /* ---- values: issue the loads now so they overlap the look-back spin */
+    u32 val[IPT];
+    if (IOTA) {
+#pragma unroll
+        for (int j = 0; j < IPT; j++) val[j] = wbase + j * 32;
+    } else if (valid == (u32) TILE) {
+#pragma unroll
+        for (int j = 0; j < IPT; j++) val[j] = vin[wbase + j * 32];
+    } else {
+#pragma unroll
+        for (int j = 0; j < IPT; j++) {
+            const u32 pos = wbase + j * 32;
+            val[j] = pos < n ? vin[pos] : 0u;
+        }
+    }
+    __syncthreads();  /* all ranks read from s_whist: it may now be reused as s_vals */
+
+    /* ---- decoupled look-back: exclusive count of my digit over earlier tiles */
+    if (tid < 256) {
+        u32 excl = 0;
+        if (tile > 0) {
+            int t = (int) tile - 1;
+            while (true) {
+                const u32 s = ld_relaxed_u32(&lookback[(size_t) t * 256 + tid]);
+                if (s & LB_INCL) { excl += s & LB_MASK; break; }
+                if (s & LB_PART) { excl += s & LB_MASK; t--; }
+            }
+            st_relaxed_u32(&lookback[(size_t) tile * 256 + tid], LB_INCL | (excl + cnt_valid));
+        }
+        s_gofs[tid] = bins[tid] + excl - s_local[tid];
+    }
+#pragma unroll
+    for (int j = 0; j < IPT; j++) s_vals[rank[j]] = val[j];
+    __syncthreads();
+
+    /* ---- coalesced stores: consecutive threads write consecutive addresses of a run */
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+        const u32 s = tid + k * THREADS;
+        if (s < valid) {
+            const u64 kk = s_keys[s];
+            const u32 digit = (u32) (kk >> shift) & 255u;
+            const u32 g = s_gofs[digit] + s;
+            kout[g] = kk;
+            vout[g] = s_vals[s];
+        }
+    }
+}
+
+typedef SweepCfg<MPSK_SWEEP_THREADS, MPSK_SWEEP_IPT> TheSweep;
+
+extern "C" size_t mpsk_onesweep_tile_items(void) { return TheSweep::TILE; }
+
+extern "C" size_t mpsk_onesweep_scratch_bytes(size_t n)
+{
+    const size_t ntiles = (n + TheSweep::TILE - 1) / TheSweep::TILE;
+    return (ntiles * 256 + 64) * sizeof(u32);
+}
+
+extern "C" int mpsk_onesweep_pass(const uint64_t * kin, const uint32_t * vin,
+        uint64_t * kout, uint32_t * vout, size_t n, int shift,
+        const uint32_t * bins, void * scratch, mpsk_stream_t stream_)
+{
+    if (n == 0) return 0;
+    if (n > MPSK_MAX_ITEMS) return (int) cudaErrorInvalidValue;
+    cudaStream_t stream = (cudaStream_t) stream_;
+    const size_t ntiles = (n + TheSweep::TILE - 1) / TheSweep::TILE;
+    cudaError_t e = cudaMemsetAsync(scratch, 0, mpsk_onesweep_scratch_bytes(n), stream);
+    if (e != cudaSuccess) return (int) e;
+    u32 * ticket = (u32 *) scratch;
+    u32 * lookback = ticket + 64;
+    static bool attr_set[2] = {false, false};
+    if (vin == NULL) {
+        auto kern = onesweep_kernel<MPSK_SWEEP_THREADS, MPSK_SWEEP_IPT, true>;
+        if (!attr_set[0]) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TheSweep::SMEM);
+            if (e != cudaSuccess) return (int) e;
+            attr_set[0] = true;
+        }
+        kern<<<(unsigned) ntiles, MPSK_SWEEP_THREADS, TheSweep::SMEM, stream>>>(
+            (const u64 *) kin, vin, (u64 *) kout, vout, (u32) n, (u32) shift, bins, lookback, ticket);
+    } else {
+        auto kern = onesweep_kernel<MPSK_SWEEP_THREADS, MPSK_SWEEP_IPT, false>;
+        if (!attr_set[1]) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TheSweep::SMEM);
+            if (e != cudaSuccess) return (int) e;
+            attr_set[1] = true;
+        }
+        kern<<<(unsigned) ntiles, MPSK_SWEEP_THREADS, TheSweep::SMEM, stream>>>(
+            (const u64 *) kin, vin, (u64 *) kout, vout, (u32) n, (u32) shift, bins, lookback, ticket);
+    }
+    CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
+/* ========================================================================= */
+/* gathers                                                                   */
+/* ========================================================================= */
+
+__global__ void __launch_bounds__(256)
+gather_u64_kernel(const u64 * __restrict__ src, const u32 * __restrict__ idx,
+                  u64 * __restrict__ dst, size_t n)
+{
+    const size_t base = ((size_t) blockIdx.x * blockDim.x) * 4 + threadIdx.x;
+    u32 ix[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const size_t i = base + (size_t) k * blockDim.x;
+        ix[k] = i < n ? idx[i] : 0u;
+    }
+    u64 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const size_t i = base + (size_t) k * blockDim.x;
+        v[k] = i < n ? src[ix[k]] : 0ULL;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const size_t i = base + (size_t) k * blockDim.x;
+        if (i < n) dst[i] = v[k];
+    }
+}
+
+extern "C" int mpsk_gather_u64(const uint64_t * src, const uint32_t * idx, uint64_t * dst,
+        size_t n, mpsk_stream_t stream)
+{
+    if (n == 0) return 0;
+    const size_t per_block = 256 * 4;
+    const size_t blocks = (n + per_block - 1) / per_block;
+    gather_u64_kernel<<<(unsigned) blocks, 256, 0, (cudaStream_t) stream>>>(
+        (const u64 *) src, idx, (u64 *) dst, n);
+    CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
+/*
+ * K3 payload gather. A record of `elsize` bytes is moved by elsize/VEC lanes, each
+ * moving one VEC-byte piece, so the lanes of one record read/write consecutive
+ * addresses. Writes are fully coalesced (out is written in order); reads are one
+ * random record each. UNROLL independent records per thread keep enough loads in
+ * flight to cover the random-access latency.
+ */
+template <typename V, int UNROLL>
+__global__ void __launch_bounds__(256)
+gather_records_kernel(const V * __restrict__ base, const u32 * __restrict__ idx,
+                      V * __restrict__ out, size_t n, u32 lpr /* lanes per record */)
+{
+    const size_t total = n * (size_t) lpr;
+    const size_t t0 = ((size_t) blockIdx.x * blockDim.x) * UNROLL + threadIdx.x;
+    size_t src[UNROLL];
+#pragma unroll
+    for (int k = 0; k < UNROLL; k++) {
+        const size_t t = t0 + (size_t) k * blockDim.x;
+        if (t < total) {
+            const size_t rec = t / lpr;
+            const u32 part = (u32) (t - rec * lpr);
+            src[k] = (size_t) idx[rec] * lpr + part;
+        } else {
+            src[k] = 0;
+        }
+    }
+    V v[UNROLL];
+#pragma unroll
+    for (int k = 0; k < UNROLL; k++) {
+        const size_t t = t0 + (size_t) k * blockDim.x;
+        if (t < total) v[k] = base[src[k]];
+    }
+#pragma unroll
+    for (int k = 0; k < UNROLL; k++) {
+        const size_t t = t0 + (size_t) k * blockDim.x;
+        if (t < total) out[t] = v[k];
+    }
+}
+
+template <typename V>
+static int launch_gather_records(const void * base, const u32 * idx, void * out, size_t n,
+                                 size_t elsize, cudaStream_t stream)
+{
+    constexpr int UNROLL = 4;
+    const u32 lpr = (u32) (elsize / sizeof(V));
+    const size_t total = n * (size_t) lpr;
+    const size_t per_block = 256 * UNROLL;
+    const size_t blocks = (total + per_block - 1) / per_block;
+    if (blocks > 0x7fffffffULL) return (int) cudaErrorInvalidValue;
+    gather_records_kernel<V, UNROLL><<<(unsigned) blocks, 256, 0, stream>>>(
+        (const V *) base, idx, (V *) out, n, lpr);
+    CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mpsk_gather_records(const void * base, const uint32_t * idx, void * out,
+        size_t n, size_t elsize, mpsk_stream_t stream_)
+{
+    if (n == 0 || elsize == 0) return 0;
+    cudaStream_t stream = (cudaStream_t) stream_;
+    const uintptr_t a = ((uintptr_t) base) | ((uintptr_t) out) | (uintptr_t) elsize;
+    if ((a & 15) == 0) return launch_gather_records<uint4>(base, idx, out, n, elsize, stream);
+    if ((a & 7) == 0) return launch_gather_records<u64>(base, idx, out, n, elsize, stream);
+    if ((a & 3) == 0) return launch_gather_records<u32>(base, idx, out, n, elsize, stream);
+    if ((a & 1) == 0) return launch_gather_records<unsigned short>(base, idx, out, n, elsize, stream);
+    return launch_gather_records<unsigned char>(base, idx, out, n, elsize, stream);
+}
+
+/* ========================================================================= */
+/* K4: splitter kernels                                                      */
+/* ========================================================================= */
+
+#define MPSK_MAX_KEY_WORDS 16
+
+/* compare key i of the SoA sorted key words with cand[]: -1, 0, +1 */
+__device__ __forceinline__ int cmp_key(const u64 * __restrict__ skeys, size_t stride, size_t i,
+                                       const u64 * cand, u32 nw)
+{
+    for (int w = (int) nw - 1; w >= 0; w--) {
+        const u64 k = skeys[(size_t) w * stride + i];
+        if (k < cand[w]) return -1;
+        if (k > cand[w]) return 1;
+    }
+    return 0;
+}
+
+/* number of keys <= cand (UPPER) or < cand (!UPPER) */
+template <bool UPPER>
+__device__ __forceinline__ u64 bound_key(const u64 * __restrict__ skeys, size_t stride, size_t n,
+                                         const u64 * cand, u32 nw)
+{
+    size_t lo = 0, hi = n;
+    while (lo < hi) {
+        const size_t mid = lo + ((hi - lo) >> 1);
+        const int c = cmp_key(skeys, stride, mid, cand, nw);
+        const bool go_right = UPPER ? (c <= 0) : (c < 0);
+        if (go_right) lo = mid + 1; else hi = mid;
+    }
+    return (u64) lo;
+}
+
+__global__ void __launch_bounds__(256)
+splitter_count_kernel(const u64 * __restrict__ skeys, size_t stride, size_t n, u32 nw,
+                      const u64 * __restrict__ prefix, int level, u64 * __restrict__ counts)
+{
+    const u32 b = blockIdx.x;
+    const u32 d = threadIdx.x;
+    const u32 byteidx = 8 * nw - 1 - (u32) level;   /* from the least significant byte */
+    const u32 wi = byteidx >> 3;
+    const u32 sh = (byteidx & 7) * 8;
+    u64 cand[MPSK_MAX_KEY_WORDS];
+    for (u32 w = 0; w < nw; w++) {
+        u64 v = prefix[(size_t) b * nw + w];
+        if (w < wi) v = ~0ULL;
+        else if (w == wi) v |= ((u64) d << sh) | ((sh == 0) ? 0ULL : ((1ULL << sh) - 1ULL));
+        cand[w] = v;
+    }
+    counts[(size_t) b * 256 + d] = bound_key<true>(skeys, stride, n, cand, nw);
+}
+
+extern "C" int mpsk_splitter_count(const uint64_t * skeys, size_t stride, size_t n, uint32_t nw,
+        const uint64_t * prefix, int nsplit, int level, uint64_t * counts, mpsk_stream_t stream)
+{
+    if (nsplit <= 0) return 0;
+    if (nw > MPSK_MAX_KEY_WORDS) return (int) cudaErrorInvalidValue;
+    splitter_count_kernel<<<nsplit, 256, 0, (cudaStream_t) stream>>>(
+        (const u64 *) skeys, stride, n, nw, (const u64 *) prefix, level, (u64 *) counts);
+    CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+splitter_select_kernel(const u64 * __restrict__ counts, const u64 * __restrict__ target,
+                       u64 * __restrict__ prefix, u32 nw, int level)
+{
+    __shared__ u32 s_min;
+    const u32 b = blockIdx.x;
+    const u32 d = threadIdx.x;
+    if (d == 0) s_min = 255u;
+    __syncthreads();
+    const bool ok = counts[(size_t) b * 256 + d] >= target[b];
+    if (ok) atomicMin(&s_min, d);
+    __syncthreads();
+    if (d == 0) {
+        const u32 byteidx = 8 * nw - 1 - (u32) level;
+        const u32 wi = byteidx >> 3;
+        const u32 sh = (byteidx & 7) * 8;
+        prefix[(size_t) b * nw + wi] |= ((u64) s_min) << sh;
+    }
+}
+
+extern "C" int mpsk_splitter_select(const uint64_t * counts, const uint64_t * target,
+        uint64_t * prefix, uint32_t nw, int nsplit, int level, mpsk_stream_t stream)
+{
+    if (nsplit <= 0) return 0;
+    splitter_select_kernel<<<nsplit, 256, 0, (cudaStream_t) stream>>>(
+        (const u64 *) counts, (const u64 *) target, (u64 *) prefix, nw, level);
+    CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void splitter_final_kernel(const u64 * __restrict__ skeys, size_t stride, size_t n, u32 nw,
+                                      const u64 * __restrict__ prefix, int nsplit, u64 * __restrict__ out)
+{
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2u * (u32) nsplit) return;
+    const u32 b = t % (u32) nsplit;
+    const bool upper = t >= (u32) nsplit;
+    u64 cand[MPSK_MAX_KEY_WORDS];
+    for (u32 w = 0; w < nw; w++) cand[w] = prefix[(size_t) b * nw + w];
+    out[t] = upper ? bound_key<true>(skeys, stride, n, cand, nw)
+                   : bound_key<false>(skeys, stride, n, cand, nw);
+}
+
+extern "C" int mpsk_splitter_final(const uint64_t * skeys, size_t stride, size_t n, uint32_t nw,
+        const uint64_t * prefix, int nsplit, uint64_t * out, mpsk_stream_t stream)
+{
+    if (nsplit <= 0) return 0;
+    if (nw > MPSK_MAX_KEY_WORDS) return (int) cudaErrorInvalidValue;
+    const int threads = 64;
+    const int blocks = (2 * nsplit + threads - 1) / threads;
+    splitter_final_kernel<<<blocks, threads, 0, (cudaStream_t) stream>>>(
+        (const u64 *) skeys, stride, n, nw, (const u64 *) prefix, nsplit, (u64 *) out);
+    CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
+#define MPSK_MAX_SUM_SRCS 64
+struct SumSrcs { const u64 * p[MPSK_MAX_SUM_SRCS]; };
+
+__global__ void sum_u64_kernel(u64 * __restrict__ dst, SumSrcs srcs, int nsrc, size_t count)
+{
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    u64 s = 0;
+    for (int k = 0; k < nsrc; k++) s += srcs.p[k][i];
+    dst[i] = s;
+}
+
+extern "C" int mpsk_sum_u64(uint64_t * dst, const uint64_t * const * srcs, int nsrc, size_t count,
+        mpsk_stream_t stream)
+{
+    if (count == 0) return 0;
+    if (nsrc > MPSK_MAX_SUM_SRCS) return (int) cudaErrorInvalidValue;
+    SumSrcs s;
+    for (int k = 0; k < nsrc; k++) s.p[k] = (const u64 *) srcs[k];
+    const int threads = 256;
+    const size_t blocks = (count + threads - 1) / threads;
+    sum_u64_kernel<<<(unsigned) blocks, threads, 0, (cudaStream_t) stream>>>((u64 *) dst, s, nsrc, count);
+    CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
+/* ========================================================================= */
+/* K8: checksum                                                              */
+/* ========================================================================= */
+
+__global__ void __launch_bounds__(256)
+checksum_kernel(const unsigned char * __restrict__ base, size_t nbytes, u64 * sum)
+{
+    /* head bytes up to 16-byte alignment, body as uint4 with dp4a, tail bytes */
+    const uintptr_t addr = (uintptr_t) base;
+    size_t head = (16 - (addr & 15)) & 15;
+    if (head > nbytes) head = nbytes;
+    const size_t nvec = (nbytes - head) / 16;
+    const size_t tail_start = head + nvec * 16;
+    const uint4 * body = (const uint4 *) (base + head);
+
+    long long acc = 0;
+    const size_t gtid = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nthreads = (size_t) gridDim.x * blockDim.x;
+    int part = 0;
+    int since = 0;
+    for (size_t i = gtid; i < nvec; i += nthreads) {
+        const uint4 v = body[i];
+        part = __dp4a((int) v.x, 0x01010101, part);
+        part = __dp4a((int) v.y, 0x01010101, part);
+        part = __dp4a((int) v.z, 0x01010101, part);
+        part = __dp4a((int) v.w, 0x01010101, part);
+        if (++since == 65536) { acc += part; part = 0; since = 0; }
+    }
+    acc += part;
+    if (gtid < head) acc += (signed char) base[gtid];
+    if (gtid < nbytes - tail_start) acc += (signed char) base[tail_start + gtid];
+
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL_MASK, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc != 0) atomicAdd(sum, (u64) acc);
+}
+
+extern "C" int mpsk_checksum(const void * base, size_t nbytes, uint64_t * sum, mpsk_stream_t stream)
+{
+    if (nbytes == 0) return 0;
+    size_t blocks = (nbytes / 16 + 255) / 256;
+    const size_t maxb = (size_t) num_sms() * 16;
+    if (blocks > maxb) blocks = maxb;
+    if (blocks == 0) blocks = 1;
+    checksum_kernel<<<(unsigned) blocks, 256, 0, (cudaStream_t) stream>>>(
+        (const unsigned char *) base, nbytes, (u64 *) sum);
+    CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
+/* ========================================================================= */
+/* bench / test support                                                      */
+/* ========================================================================= */
+
+__host__ __device__ __forceinline__ u64 mix64(u64 x)
+{
+    u64 z = x + 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+/* one synthetic record; the same arithmetic is restated in oracle/synth.h */
+__device__ void synth_record(unsigned char * rec, size_t elsize, int kind, u64 seed,
+                             u64 rank, u64 nranks, u64 n, u64 i)
+{
+    const u64 h = mix64(seed ^ (rank << 32) ^ i);
+    const u64 tag = (rank << 40) + i;
+    u64 key;
+    if (kind == 1) {
+        const u64 gi = rank * n + i;
+        u64 src = gi;
+        if (mix64(gi ^ 0xA5A5A5A5ULL) % 100 == 0 && n > 0) {
+            src = (gi + 1 + mix64(gi ^ 0x5A5A5A5AULL) % n) % (nranks * n);
+        }
+        key = (src << 20) + (mix64(seed ^ src) & 0xFFFFFULL);
+    } else if (kind == 2) {
+        const double u = (double) (h >> 11) * (1.0 / 9007199254740992.0);
+        const double u2 = u * u;
+        const double u4 = u2 * u2;
+        long long id = (long long) (u4 * 16777216.0) - (1LL << 20);
+        if (mix64(h) % 20 == 0) id = 0;
+        key = (u64) id;
+    } else {
+        key = h;
+    }
+    for (size_t b = 0; b < elsize; b++) {
+        unsigned char v;
+        if (b < 8) v = (unsigned char) (key >> (8 * b));
+        else if (b < 16) v = (unsigned char) (tag >> (8 * (b - 8)));
+        else v = (unsigned char) (mix64(h + b / 8) >> (8 * (b & 7)));
+        rec[b] = v;
+    }
+}
+
+__global__ void generate_kernel(unsigned char * dst, size_t n, size_t elsize, int kind, u64 seed,
+                                u64 rank, u64 nranks)
+{
+    const size_t nthreads = (size_t) gridDim.x * blockDim.x;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+        if (elsize == 16 && ((((uintptr_t) dst) & 15) == 0)) {
+            __align__(16) unsigned char tmp[16];
+            synth_record(tmp, 16, kind, seed, rank, nranks, n, i);
+            ((uint4 *) dst)[i] = *(uint4 *) tmp;
+        } else {
+            synth_record(dst + i * elsize, elsize, kind, seed, rank, nranks, n, i);
+        }
+    }
+}
+
+extern "C" int mpsk_generate(void * dst, size_t n, size_t elsize, int kind, uint64_t seed,
+        uint64_t rank, uint64_t nranks, mpsk_stream_t stream)
+{
+    if (n == 0) return 0;
+    size_t blocks = (n + 255) / 256;
+    const size_t maxb = (size_t) num_sms() * 16;
+    if (blocks > maxb) blocks = maxb;
+    generate_kernel<<<(unsigned) blocks, 256, 0, (cudaStream_t) stream>>>(
+        (unsigned char *) dst, n, elsize, kind, seed, rank, nranks);
+    CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void check_sorted_kernel(const unsigned char * __restrict__ base, size_t n, KeyDesc d, u32 nw,
+                                    int check_ties, size_t tie_offset, u64 * violations, u64 * firstlast)
+{
+    const size_t nthreads = (size_t) gridDim.x * blockDim.x;
+    u64 bad = 0;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+        const unsigned char * cur = base + i * d.elsize;
+        if (i == 0 || i == n - 1) {
+            for (u32 w = 0; w < nw; w++) {
+                KeyDesc dd = d; dd.g = w;
+                const u64 k = pack_key_word(cur, dd);
+                if (i == 0) firstlast[w] = k;
+                if (i == n - 1) firstlast[nw + w] = k;
+            }
+        }
+        if (i == 0) continue;
+        const unsigned char * prev = cur - d.elsize;
+        int c = 0;
+        for (int w = (int) nw - 1; w >= 0 && c == 0; w--) {
+            KeyDesc dd = d; dd.g = (u32) w;
+            const u64 a = pack_key_word(prev, dd);
+            const u64 b = pack_key_word(cur, dd);
+            c = (a > b) - (a < b);
+        }
+        if (c > 0) bad++;
+        else if (c == 0 && check_ties) {
+            const u64 ta = load_narrow(prev + tie_offset, 8);
+            const u64 tb = load_narrow(cur + tie_offset, 8);
+            if (ta >= tb) bad++;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(FULL_MASK, bad, o);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(violations, bad);
+}
+
+extern "C" int mpsk_check_sorted(const void * base, size_t n, size_t elsize,
+        size_t offset, uint32_t width, uint32_t nwords, int is_signed,
+        int check_ties, size_t tie_offset,
+        uint64_t * violations, uint64_t * firstlast, mpsk_stream_t stream)
+{
+    if (n == 0) return 0;
+    KeyDesc d;
+    d.elsize = elsize; d.offset = offset; d.width = width; d.nwords = nwords;
+    d.is_signed = is_signed; d.g = 0;
+    const u32 nw = (u32) (((size_t) width * nwords + 7) / 8);
+    size_t blocks = (n + 255) / 256;
+    const size_t maxb = (size_t) num_sms() * 16;
+    if (blocks > maxb) blocks = maxb;
+    check_sorted_kernel<<<(unsigned) blocks, 256, 0, (cudaStream_t) stream>>>(
+        (const unsigned char *) base, n, d, nw, check_ties, tie_offset, (u64 *) violations, (u64 *) firstlast);
+    CUDA_LAUNCH_CHECK();
+    return 0;
+}

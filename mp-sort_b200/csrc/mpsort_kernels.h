@@ -1,0 +1,123 @@
+/*
+ * mpsort_kernels.h -- internal thin C ABI between the C host code (mpsort_host.c)
+ * and the hand-written sm_100a kernels (mpsort_kernels.cu). Plain pointers and
+ * sizes only. Every launcher enqueues on `stream` and returns without syncing;
+ * a non-zero return is a cudaError_t.
+ */
+#ifndef MPSORT_KERNELS_H
+#define MPSORT_KERNELS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void * mpsk_stream_t; /* cudaStream_t */
+
+#define MPSK_RADIX_BITS 8
+#define MPSK_RADIX 256
+#define MPSK_MAX_ITEMS ((size_t)0x3fffffffu) /* look-back status words carry 30-bit counts */
+
+/* K1: key extraction + all-digit histogram. Replaces the reference's radix()
+ * callbacks (binding.pyx:81-121, bench-mpi.c:13-15).
+ * Packs key bytes [8*g, 8*g+8) of every record (little-endian over the nwords*width
+ * key bytes, signed words sign-flipped) into kout[i] and accumulates the eight
+ * 8-bit digit histograms of that word into hist[8][256] (must be zeroed by caller).
+ */
+int mpsk_extract_keys(const void * base, size_t n, size_t elsize,
+        size_t offset, uint32_t width, uint32_t nwords, int is_signed,
+        uint32_t g, uint64_t * kout, uint32_t * hist, mpsk_stream_t stream);
+
+/* Exclusive scan of each of `nhist` 256-bin histograms: hist[h][b] -> bins[h][b]. */
+int mpsk_scan_histograms(const uint32_t * hist, uint32_t * bins, int nhist, mpsk_stream_t stream);
+
+/* Geometry of one onesweep pass (so the host can size the look-back buffer). */
+size_t mpsk_onesweep_tile_items(void);
+/* bytes of scratch needed for a pass over n items (look-back words + ticket) */
+size_t mpsk_onesweep_scratch_bytes(size_t n);
+
+/* K2: one stable 8-bit LSD onesweep pass on (u64 key, u32 value) pairs.
+ * Replaces mpsort_qsort_r (stdlib/msort.c:177-314).
+ * vin == NULL means "values are 0..n-1" (first pass).
+ * vout may be NULL and kout may be NULL to drop that output (last pass variants).
+ * bins = exclusive-scanned global histogram of this digit (256 words, device).
+ * scratch = mpsk_onesweep_scratch_bytes(n) bytes; zeroed by this call.
+ */
+int mpsk_onesweep_pass(const uint64_t * kin, const uint32_t * vin,
+        uint64_t * kout, uint32_t * vout, size_t n, int shift,
+        const uint32_t * bins, void * scratch, mpsk_stream_t stream);
+
+/* dst[i] = src[idx[i]] for 64-bit words (key words of multi-word keys). If hist is
+ * non-NULL nothing is accumulated (histograms are permutation invariant). */
+int mpsk_gather_u64(const uint64_t * src, const uint32_t * idx, uint64_t * dst,
+        size_t n, mpsk_stream_t stream);
+
+/* K3: payload gather out[i] = base[idx[i]] for elsize-byte records. Replaces the
+ * record moves of the merge sort (msort.c:153-173,270-294). */
+int mpsk_gather_records(const void * base, const uint32_t * idx, void * out,
+        size_t n, size_t elsize, mpsk_stream_t stream);
+
+/* K4: splitter counting on the sorted key words skeys[w][n] (word w at
+ * skeys + w*stride). Replaces _histogram/_bsearch_last_lt/le
+ * (internal-parallel.h:8-126).
+ *
+ * Byte-wise descent state: prefix[b][nw] (u64 words, device) holds the bytes of
+ * splitter b decided so far (undecided bytes zero). `level` counts bytes from the
+ * most significant one (0 .. 8*nw-1). For every splitter b and digit d the kernel
+ * writes counts[b*256+d] = #local keys <= (prefix_b | d at this byte | 0xff below).
+ */
+int mpsk_splitter_count(const uint64_t * skeys, size_t stride, size_t n, uint32_t nw,
+        const uint64_t * prefix, int nsplit, int level,
+        uint64_t * counts, mpsk_stream_t stream);
+
+/* After the counts were summed over ranks: for each splitter pick the smallest d
+ * with counts[b][d] >= target[b] and OR it into prefix[b] at byte `level`. */
+int mpsk_splitter_select(const uint64_t * counts, const uint64_t * target,
+        uint64_t * prefix, uint32_t nw, int nsplit, int level, mpsk_stream_t stream);
+
+/* Final local counts for decided splitters: clt[b] = #keys < P_b, cle[b] = #keys <= P_b
+ * written to out[0..nsplit) and out[nsplit..2*nsplit). */
+int mpsk_splitter_final(const uint64_t * skeys, size_t stride, size_t n, uint32_t nw,
+        const uint64_t * prefix, int nsplit, uint64_t * out, mpsk_stream_t stream);
+
+/* dst[i] += src_k[i] over nsrc sources (u64), for the in-process transport. */
+int mpsk_sum_u64(uint64_t * dst, const uint64_t * const * srcs, int nsrc, size_t count,
+        mpsk_stream_t stream);
+
+/* K7: stable merge of two adjacent sorted runs of records (keys read from the
+ * records through the descriptor). a = [0,na), b = [0,nb) -> out[0, na+nb); ties
+ * take from a first (stdlib/msort.c:78 "<= 0 => left first"). Keys are the packed
+ * u64 words ka[w][.], kb[w][.] carried beside the records. */
+int mpsk_merge_pairs(const uint64_t * ka, const uint32_t * va, size_t na,
+        const uint64_t * kb, const uint32_t * vb, size_t nb,
+        uint64_t * kout, uint32_t * vout, mpsk_stream_t stream);
+
+/* K8: reference checksum (mpsort-mpi.c:148-159): sum of all bytes as SIGNED chars,
+ * wrapping in 64 bits; accumulated (atomicAdd) into *sum which the caller zeroes. */
+int mpsk_checksum(const void * base, size_t nbytes, uint64_t * sum, mpsk_stream_t stream);
+
+/* ---- bench / test support (not on the product path) ---- */
+
+/* Synthetic records, SURVEY.md 8(d). kind:
+ *  0 = uniform u64 key, 16-byte {key,payload}; payload = (rank<<40)+i
+ *  1 = mostly sorted (1% perturbed) u64 key, 16-byte records
+ *  2 = 48-byte particle struct, skewed signed i64 ID with heavy duplicates
+ *  3 = uniform u64 key with arbitrary elsize (key at offset 0, payload u64 at 8 if room)
+ */
+int mpsk_generate(void * dst, size_t n, size_t elsize, int kind, uint64_t seed,
+        uint64_t rank, uint64_t nranks, mpsk_stream_t stream);
+
+/* Order check of a sorted output: counts i with key[i-1] > key[i] (or, when
+ * check_ties, key equal and payload u64 at `tie_offset` decreasing) into
+ * *violations; also returns first/last packed key words through firstlast[2*nw]. */
+int mpsk_check_sorted(const void * base, size_t n, size_t elsize,
+        size_t offset, uint32_t width, uint32_t nwords, int is_signed,
+        int check_ties, size_t tie_offset,
+        uint64_t * violations, uint64_t * firstlast, mpsk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
