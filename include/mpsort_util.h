@@ -57,6 +57,15 @@ void   mpsort_util_flush_l2(mpsort_comm_t comm);
 /* how many of this library's kernels were launched since the last reset */
 uint64_t mpsort_util_launch_count(int reset);
 
+/* Per-kernel-class device time, for roofline numbers: with timing on, every launch
+ * of the library on this communicator is bracketed by CUDA events on its stream and
+ * the durations are summed per class ("extract_hist", "onesweep_pass", "gather_keys",
+ * "gather_records", "splitter", "checksum", "exchange"). Turning it on (or off)
+ * resets the sums. kernel_times returns the number of classes. */
+void   mpsort_util_kernel_timing(mpsort_comm_t comm, int on);
+int    mpsort_util_kernel_times(mpsort_comm_t comm, const char ** names, double * ms,
+                                uint64_t * launches, int max);
+
 /* free/total device memory in bytes */
 void   mpsort_util_mem_info(int device, size_t * free_bytes, size_t * total_bytes);
 

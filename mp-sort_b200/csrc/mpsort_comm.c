@@ -121,6 +121,41 @@ void * mps_host_stage(struct mpsort_comm * c, size_t bytes)
 }
 
 /* ------------------------------------------------------------------------- */
+/* per-kernel-class timing                                                    */
+
+void mps_kt_begin(struct mpsort_comm * c, int cls)
+{
+    struct mps_ktimes * k = &c->kt;
+    if (!k->on) return;
+    if (k->n >= MPS_KT_MAX) { CUDA_OK(c, cudaStreamSynchronize(c->stream)); mps_kt_collect(c); }
+    while (k->nev < 2 * (k->n + 1)) { CUDA_OK(c, cudaEventCreate(&k->ev[k->nev])); k->nev++; }
+    k->cls[k->n] = cls;
+    CUDA_OK(c, cudaEventRecord(k->ev[2 * k->n], c->stream));
+}
+
+void mps_kt_end(struct mpsort_comm * c)
+{
+    struct mps_ktimes * k = &c->kt;
+    if (!k->on) return;
+    CUDA_OK(c, cudaEventRecord(k->ev[2 * k->n + 1], c->stream));
+    k->n++;
+}
+
+void mps_kt_collect(struct mpsort_comm * c)
+{
+    struct mps_ktimes * k = &c->kt;
+    int i;
+    for (i = 0; i < k->n; i++) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, k->ev[2 * i], k->ev[2 * i + 1]) == cudaSuccess) {
+            k->ms[k->cls[i]] += ms;
+            k->launches[k->cls[i]]++;
+        } else cudaGetLastError();
+    }
+    k->n = 0;
+}
+
+/* ------------------------------------------------------------------------- */
 /* construction                                                               */
 
 static struct mpsort_comm * comm_alloc(int kind, int rank, int size, int device)
@@ -222,6 +257,7 @@ void mpsort_comm_destroy(mpsort_comm_t c)
             free(c->grp);
         }
     }
+    { int i; for (i = 0; i < c->kt.nev; i++) cudaEventDestroy(c->kt.ev[i]); }
     if (c->timers.created) { int i; for (i = 0; i < MPS_MAX_TIMERS; i++) cudaEventDestroy(c->timers.ev[i]); }
     cudaStreamDestroy(c->stream);
     free(c);

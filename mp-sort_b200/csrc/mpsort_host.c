@@ -198,10 +198,10 @@ static void local_sort(struct mpsort_comm * c, const void * dbase, size_t n, siz
 
     CUDA_OK(c, cudaMemsetAsync(hist, 0, nhist * 256 * sizeof(uint32_t), c->stream));
     for (g = 0; g < nw; g++) {
-        KERN_OK(c, mpsk_extract_keys(dbase, n, elsize, desc->offset, desc->width, desc->nwords,
+        KERN_T(c, MPS_K_EXTRACT, mpsk_extract_keys(dbase, n, elsize, desc->offset, desc->width, desc->nwords,
                                      desc->is_signed, g, kw + (size_t) g * n, hist + (size_t) g * 8 * 256, c->stream));
     }
-    KERN_OK(c, mpsk_scan_histograms(hist, bins, (int) nhist, c->stream));
+    KERN_T(c, MPS_K_EXTRACT, mpsk_scan_histograms(hist, bins, (int) nhist, c->stream));
 
     /* which digits are constant? (one small D2H per sort) */
     uint32_t * hhist = (uint32_t *) mps_host_stage(c, nhist * 256 * sizeof(uint32_t));
@@ -232,7 +232,7 @@ static void local_sort(struct mpsort_comm * c, const void * dbase, size_t n, siz
         if (cur_idx == NULL) {
             kin = kw + (size_t) g * n;
         } else {
-            KERN_OK(c, mpsk_gather_u64(kw + (size_t) g * n, cur_idx, ka == kw ? kb : ka, n, c->stream));
+            KERN_T(c, MPS_K_GATHER_KEYS, mpsk_gather_u64(kw + (size_t) g * n, cur_idx, ka == kw ? kb : ka, n, c->stream));
             kin = (ka == kw ? kb : ka);
         }
         for (d = 0; d < 8; d++) {
@@ -241,7 +241,7 @@ static void local_sort(struct mpsort_comm * c, const void * dbase, size_t n, siz
             if (nw == 1) kout = (kin == kw) ? kb : kw;
             else kout = (kin == ka) ? kb : ka;
             uint32_t * vout = (cur_idx == ia) ? ib : ia;
-            KERN_OK(c, mpsk_onesweep_pass(kin, cur_idx, kout, vout, n, (int) (8 * d),
+            KERN_T(c, MPS_K_ONESWEEP, mpsk_onesweep_pass(kin, cur_idx, kout, vout, n, (int) (8 * d),
                                           bins + (size_t) (g * 8 + d) * 256, scratch, c->stream));
             kin = kout;
             cur_idx = vout;
@@ -257,7 +257,7 @@ static void local_sort(struct mpsort_comm * c, const void * dbase, size_t n, siz
         } else {
             uint64_t * sk = (uint64_t *) mps_arena_get(c, MPS_S_SK, (size_t) nw * n * sizeof(uint64_t));
             for (g = 0; g < nw; g++)
-                KERN_OK(c, mpsk_gather_u64(kw + (size_t) g * n, cur_idx, sk + (size_t) g * n, n, c->stream));
+                KERN_T(c, MPS_K_GATHER_KEYS, mpsk_gather_u64(kw + (size_t) g * n, cur_idx, sk + (size_t) g * n, n, c->stream));
             out->skeys = sk;
         }
     }
@@ -281,7 +281,7 @@ static uint64_t device_checksum(struct mpsort_comm * c, const void * d, size_t n
     uint64_t h = 0, all[MPS_MAX_RANKS];
     int j;
     CUDA_OK(c, cudaMemsetAsync(dsum, 0, sizeof(uint64_t), c->stream));
-    KERN_OK(c, mpsk_checksum(d, nbytes, dsum, c->stream));
+    KERN_T(c, MPS_K_CHECKSUM, mpsk_checksum(d, nbytes, dsum, c->stream));
     CUDA_OK(c, cudaMemcpyAsync(&h, dsum, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
     mpsort_comm_allgather_host(c, &h, all, sizeof(h));
@@ -324,7 +324,7 @@ static void gather_sort(struct mpsort_comm * c, const void * dbase, void * dout,
     if (c->rank == leader) {
         struct sorted_view v;
         local_sort(c, all, (size_t) total, elsize, desc, 0, &v);
-        KERN_OK(c, mpsk_gather_records(all, v.idx, sorted, (size_t) total, elsize, c->stream));
+        KERN_T(c, MPS_K_GATHER_RECORDS, mpsk_gather_records(all, v.idx, sorted, (size_t) total, elsize, c->stream));
         c->stats.first_sort_passes = v.npasses;
     }
     timer_mark(c, "FirstSort");
@@ -416,10 +416,10 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
         /* one rank: the exchange is a self copy and the second sort the identity
          * (SURVEY.md appendix B.6): gather straight into the output */
         if (dout != dbase) {
-            KERN_OK(c, mpsk_gather_records(dbase, v1.idx, dout, n, elsize, c->stream));
+            KERN_T(c, MPS_K_GATHER_RECORDS, mpsk_gather_records(dbase, v1.idx, dout, n, elsize, c->stream));
         } else {
             void * tmp = mps_arena_get(c, MPS_S_SEND, n * elsize);
-            KERN_OK(c, mpsk_gather_records(dbase, v1.idx, tmp, n, elsize, c->stream));
+            KERN_T(c, MPS_K_GATHER_RECORDS, mpsk_gather_records(dbase, v1.idx, tmp, n, elsize, c->stream));
             if (n) CUDA_OK(c, cudaMemcpyAsync(dout, tmp, n * elsize, cudaMemcpyDeviceToDevice, c->stream));
         }
         c->sendcounts[0] = (int64_t) n;
@@ -473,9 +473,9 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
     }
     int level, round = 0;
     for (level = level0; level < nlevels; level++) {
-        KERN_OK(c, mpsk_splitter_count(v1.skeys, v1.stride, n, nw, d_prefix, ns, level, d_counts, c->stream));
+        KERN_T(c, MPS_K_SPLITTER, mpsk_splitter_count(v1.skeys, v1.stride, n, nw, d_prefix, ns, level, d_counts, c->stream));
         mps_comm_allreduce_u64_dev(c, d_counts, (size_t) ns * 256);
-        KERN_OK(c, mpsk_splitter_select(d_counts, d_target, d_prefix, nw, ns, level, c->stream));
+        KERN_T(c, MPS_K_SPLITTER, mpsk_splitter_select(d_counts, d_target, d_prefix, nw, ns, level, c->stream));
         round++;
         if (round <= 10) {
             char name[20];
@@ -484,7 +484,7 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
         }
     }
     c->stats.splitter_rounds = (uint32_t) round;
-    KERN_OK(c, mpsk_splitter_final(v1.skeys, v1.stride, n, nw, d_prefix, ns, d_final, c->stream));
+    KERN_T(c, MPS_K_SPLITTER, mpsk_splitter_final(v1.skeys, v1.stride, n, nw, d_prefix, ns, d_final, c->stream));
     timer_mark(c, "findP");
 
     /* ---- LayDistr: all-gather the local rows (replaces the 8-byte Alltoalls :450-456) */
@@ -526,12 +526,14 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
      * :483-501) then grouped send/recv */
     void * sendbuf = mps_arena_get(c, MPS_S_SEND, n * elsize);
     void * recvbuf = mps_arena_get(c, MPS_S_RECV, outn * elsize);
-    KERN_OK(c, mpsk_gather_records(dbase, v1.idx, sendbuf, n, elsize, c->stream));
+    KERN_T(c, MPS_K_GATHER_RECORDS, mpsk_gather_records(dbase, v1.idx, sendbuf, n, elsize, c->stream));
     timer_mark(c, "Pack");
     const int dense = mpsort_mpi_has_options(MPSORT_DISABLE_SPARSE_ALLTOALLV)
                       && !mpsort_mpi_has_options(MPSORT_REQUIRE_SPARSE_ALLTOALLV);
     c->stats.dense_exchange = (uint32_t) dense;
+    mps_kt_begin(c, MPS_K_EXCHANGE);
     mps_comm_alltoallv_dev(c, sendbuf, recvbuf, cut, elsize, dense, &c->stats.bytes_sent_remote);
+    mps_kt_end(c);
     timer_mark(c, "Exchange");
 
     /* ---- SecondSort: the received buffer is p sorted runs in source-rank order;
@@ -539,7 +541,7 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
     {
         struct sorted_view v2;
         local_sort(c, recvbuf, outn, elsize, desc, 0, &v2);
-        KERN_OK(c, mpsk_gather_records(recvbuf, v2.idx, dout, outn, elsize, c->stream));
+        KERN_T(c, MPS_K_GATHER_RECORDS, mpsk_gather_records(recvbuf, v2.idx, dout, outn, elsize, c->stream));
         c->stats.second_sort_passes = v2.npasses;
     }
     timer_mark(c, "SecondSort");
@@ -614,6 +616,7 @@ void mpsort_mpi_newarray_desc_impl(void * base, size_t nmemb,
     if (!out_dev && outnmemb > 0)
         CUDA_OK(c, cudaMemcpyAsync(out, dout, outnmemb * elsize, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    mps_kt_collect(c);
     timer_publish(c);
 }
 

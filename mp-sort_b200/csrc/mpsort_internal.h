@@ -60,6 +60,21 @@ struct mps_timers {
     int created;
 };
 
+/* per-kernel-class timing (bench.py's roofline numbers): CUDA events around every
+ * launch of a class on the communicator's stream, summed after the stream sync */
+enum mps_kclass { MPS_K_EXTRACT = 0, MPS_K_ONESWEEP, MPS_K_GATHER_KEYS, MPS_K_GATHER_RECORDS,
+                  MPS_K_SPLITTER, MPS_K_CHECKSUM, MPS_K_EXCHANGE, MPS_NKCLASS };
+#define MPS_KT_MAX 512
+struct mps_ktimes {
+    int on;
+    int n;                               /* pending event pairs */
+    int nev;                             /* events created */
+    cudaEvent_t ev[2 * MPS_KT_MAX];
+    int cls[MPS_KT_MAX];
+    double ms[MPS_NKCLASS];
+    uint64_t launches[MPS_NKCLASS];
+};
+
 struct mpsort_comm {
     int kind;
     int rank, size, device;
@@ -76,7 +91,13 @@ struct mpsort_comm {
 
     struct mpsort_last_stats stats;
     int64_t sendcounts[MPS_MAX_RANKS];
+    struct mps_ktimes kt;
 };
+
+void mps_kt_begin(struct mpsort_comm * c, int cls);
+void mps_kt_end(struct mpsort_comm * c);
+void mps_kt_collect(struct mpsort_comm * c);   /* call after the stream was synchronised */
+#define KERN_T(c, cls, call) do { mps_kt_begin((c), (cls)); KERN_OK((c), call); mps_kt_end((c)); } while (0)
 
 /* ---- errors (reference convention: message incl. caller site, then abort) ---- */
 void mps_fatal(struct mpsort_comm * c, const char * file, int line, const char * fmt, ...)

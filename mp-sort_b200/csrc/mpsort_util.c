@@ -151,3 +151,28 @@ void mpsort_util_mem_info(int device, size_t * free_bytes, size_t * total_bytes)
     CUDA_OK(NULL, cudaSetDevice(device));
     CUDA_OK(NULL, cudaMemGetInfo(free_bytes, total_bytes));
 }
+
+static const char * kclass_names[MPS_NKCLASS] = {
+    "extract_hist", "onesweep_pass", "gather_keys", "gather_records", "splitter", "checksum", "exchange"
+};
+
+void mpsort_util_kernel_timing(mpsort_comm_t c, int on)
+{
+    int i;
+    CUDA_OK(c, cudaSetDevice(c->device));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    mps_kt_collect(c);
+    for (i = 0; i < MPS_NKCLASS; i++) { c->kt.ms[i] = 0; c->kt.launches[i] = 0; }
+    c->kt.on = on;
+}
+
+int mpsort_util_kernel_times(mpsort_comm_t c, const char ** names, double * ms, uint64_t * launches, int max)
+{
+    int i;
+    for (i = 0; i < MPS_NKCLASS && i < max; i++) {
+        if (names) names[i] = kclass_names[i];
+        if (ms) ms[i] = c->kt.ms[i];
+        if (launches) launches[i] = c->kt.launches[i];
+    }
+    return MPS_NKCLASS;
+}

@@ -109,6 +109,9 @@ _proto("mpsort_util_event_destroy", None, c_void_p)
 _proto("mpsort_util_stream_sync", None, c_void_p)
 _proto("mpsort_util_flush_l2", None, c_void_p)
 _proto("mpsort_util_launch_count", c_u64, c_int)
+_proto("mpsort_util_kernel_timing", None, c_void_p, c_int)
+_proto("mpsort_util_kernel_times", c_int, c_void_p, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_double),
+       ctypes.POINTER(c_u64), c_int)
 _proto("mpsort_util_mem_info", None, c_int, ctypes.POINTER(c_size_t), ctypes.POINTER(c_size_t))
 
 
@@ -127,3 +130,14 @@ def last_stats(comm_handle, size):
     d = {name: getattr(st, name) for name, _ in LastStats._fields_}
     d["sendcounts"] = list(sc)[:size]
     return d
+
+byref = ctypes.byref
+
+
+def kernel_times(comm_handle):
+    """{class: (milliseconds, launches)} accumulated since mpsort_util_kernel_timing(on)"""
+    names = (ctypes.c_char_p * 16)()
+    ms = (ctypes.c_double * 16)()
+    cnt = (c_u64 * 16)()
+    n = lib.mpsort_util_kernel_times(comm_handle, names, ms, cnt, 16)
+    return {names[i].decode(): (ms[i], int(cnt[i])) for i in range(n)}

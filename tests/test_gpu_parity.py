@@ -1,0 +1,342 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI of
+libmpsort-b200.so (ctypes, plain pointers), compared with the oracle on the same
+inputs -- bit-exact, integer/byte work. Multi-rank cases run as an in-process group
+of rank threads sharing cuda:0, the way the reference's `mpirun -n 4/12` cases are
+run on one machine; NCCL process-per-GPU cases need >= 2 GPUs.
+
+Full-size cases (BASELINE.json: 2^28 16-byte records) are checked through
+size-independent properties: sortedness, tie order by tag, checksum of bytes."""
+import ctypes
+import os
+import subprocess
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+import mpsort_oracle as O
+from conftest import GOLDEN, GOLDEN_CASES, ROOT, load_golden
+
+import mpsort
+from mpsort import _capi as C
+
+pytestmark = pytest.mark.gpu
+lib = C.lib
+
+TUNINGS = [0, C.MPSORT_DISABLE_SPARSE_ALLTOALLV, C.MPSORT_REQUIRE_SPARSE_ALLTOALLV,
+           C.MPSORT_REQUIRE_GATHER_SORT, C.MPSORT_DISABLE_GATHER_SORT]
+
+
+def cdesc(d):
+    return C.RadixDesc(d.offset, d.width, d.nwords, d.is_signed, 0)
+
+
+def sort_group(recs, outsizes, desc, tuning=0, inplace=False, devices=None):
+    """one collective sort over len(recs) rank threads through the C ABI (host buffers)"""
+    p = len(recs)
+    elsize = recs[0].shape[1]
+    ins = [np.ascontiguousarray(r).copy() for r in recs]
+    outs = ins if inplace else [np.zeros((outsizes[r], elsize), np.uint8) for r in range(p)]
+    d = cdesc(desc)
+    lib.mpsort_mpi_unset_options(-1)
+    if tuning:
+        lib.mpsort_mpi_set_options(tuning)
+
+    def work(comm):
+        r = comm.rank
+        lib.mpsort_mpi_newarray_desc_impl(ins[r].ctypes.data, len(ins[r]), outs[r].ctypes.data, len(outs[r]),
+                                          elsize, ctypes.byref(d), comm.handle, 0, b"test_gpu_parity")
+        return C.last_stats(comm.handle, p)
+
+    stats = mpsort.run_local(p, work, devices)
+    lib.mpsort_mpi_unset_options(-1)
+    return outs, stats
+
+
+def same(a, b):
+    return len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+# ------------------------------------------------------------------ local sort
+LOCAL_CASES = [
+    (O.Desc(0, 8, 1, 0, 0), 16), (O.Desc(8, 8, 1, 1, 0), 16), (O.Desc(0, 8, 1, 1, 0), 48),
+    (O.Desc(0, 8, 1, 0, 0), 8), (O.Desc(4, 4, 1, 0, 0), 12), (O.Desc(0, 4, 1, 1, 0), 8),
+    (O.Desc(0, 8, 2, 0, 0), 40), (O.Desc(8, 8, 3, 1, 0), 36), (O.Desc(0, 4, 3, 1, 0), 20),
+    (O.Desc(2, 2, 1, 0, 1), 7), (O.Desc(1, 1, 5, 0, 1), 9), (O.Desc(0, 8, 1, 0, 0), 24),
+    (O.Desc(0, 8, 1, 0, 0), 32), (O.Desc(16, 8, 1, 1, 0), 64), (O.Desc(3, 8, 1, 0, 0), 19),
+]
+
+
+@pytest.mark.parametrize("desc,elsize", LOCAL_CASES)
+def test_radix_sort_desc_matches_oracle(desc, elsize):
+    """radix_sort replacement vs the oracle's stable merge sort (radixsort.c:35-44)"""
+    rng = np.random.default_rng(elsize * 131 + desc.offset)
+    tile = 6144
+    for n in [0, 1, 2, 31, 32, 33, 1000, tile - 1, tile, tile + 1, 3 * tile + 17, 200003]:
+        a = rng.integers(0, 256, size=(n, elsize), dtype=np.uint8)
+        got = a.copy()
+        lib.radix_sort_desc(got.ctypes.data, n, elsize, ctypes.byref(cdesc(desc)), 0)
+        assert np.array_equal(got, O.c_radix_sort(a, desc)), "n=%d" % n
+
+
+@pytest.mark.parametrize("distinct", [1, 2, 5, 300])
+def test_radix_sort_desc_stable_on_duplicates(distinct):
+    rng = np.random.default_rng(distinct)
+    dt = np.dtype([("key", "i8"), ("tag", "u8")])
+    a = np.zeros(400000, dtype=dt)
+    a["key"] = rng.integers(-distinct, distinct, size=len(a))
+    a["tag"] = np.arange(len(a))
+    got = a.copy()
+    lib.radix_sort_desc(got.ctypes.data, len(a), 16, ctypes.byref(C.RadixDesc(0, 8, 1, 1, 0)), 0)
+    assert np.array_equal(got, a[np.argsort(a["key"], kind="stable")])
+
+
+def test_sorted_reverse_and_constant_inputs():
+    d = C.RadixDesc(0, 8, 1, 0, 0)
+    dt = np.dtype([("key", "u8"), ("tag", "u8")])
+    n = 100000
+    for keys in (np.arange(n), np.arange(n)[::-1], np.full(n, 7), np.arange(n) << 40, np.arange(n) % 2):
+        a = np.zeros(n, dtype=dt)
+        a["key"] = keys
+        a["tag"] = np.arange(n)
+        got = a.copy()
+        lib.radix_sort_desc(got.ctypes.data, n, 16, ctypes.byref(d), 0)
+        assert np.array_equal(got, a[np.argsort(a["key"], kind="stable")])
+
+
+# ------------------------------------------------------------------ golden vectors
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("tuning", TUNINGS)
+def test_golden_vectors(name, tuning):
+    """the reference's own fixtures (issue7: 12 ranks / 40-byte records / 16-byte key,
+    mismatched zeros, struct) and reference-generated ones (ties, synthetic kinds)"""
+    g = load_golden(name)
+    out, stats = sort_group(g["recs"], g["outsizes"], g["desc"], tuning)
+    assert same(out, g["exp"])
+
+
+def test_golden_issue7_inplace():
+    g = load_golden("issue7")
+    out, _ = sort_group(g["recs"], g["outsizes"], g["desc"], C.MPSORT_DISABLE_GATHER_SORT, inplace=True)
+    assert same(out, g["exp"])
+
+
+def test_few_items_golden():
+    """test_mpsort.py:330-351: all 81 size combinations x 5 tunings on 4 ranks"""
+    z = np.load(os.path.join(GOLDEN, "few_items.npz"))
+    desc = C.RadixDesc(*[int(v) for v in z["desc"]][:4], 0)
+    dt = np.dtype([("vkey", ("u8", 3)), ("vector", ("u4", 3))])
+    cases, off = [], 0
+    for sizes in z["sizes"]:
+        n = int(sum(sizes))
+        cases.append(([int(s) for s in sizes], z["expected"][off:off + n]))
+        off += n
+    failures = []
+    bar = threading.Barrier(4)
+
+    def work(comm):
+        r = comm.rank
+        for tuning in TUNINGS:
+            for sizes, exp in cases:
+                s = np.empty(sizes[r], dtype=dt)
+                s["vkey"] = np.array(range(sizes[r]), dtype="u8")[:, None]
+                s["vector"] = 1
+                out = np.empty(sizes[r], dtype=dt)
+                if r == 0:
+                    lib.mpsort_mpi_unset_options(-1)
+                    if tuning:
+                        lib.mpsort_mpi_set_options(tuning)
+                bar.wait()
+                lib.mpsort_mpi_newarray_desc_impl(s.ctypes.data, len(s), out.ctypes.data, len(out), dt.itemsize,
+                                                  ctypes.byref(desc), comm.handle, 0, b"few_items")
+                lo = sum(sizes[:r])
+                if not np.array_equal(O.as_bytes(out), exp[lo:lo + sizes[r]]):
+                    failures.append((sizes, tuning, r))
+                bar.wait()
+
+    mpsort.run_local(4, work)
+    lib.mpsort_mpi_unset_options(-1)
+    assert not failures, failures[:5]
+
+
+# ------------------------------------------------------------------ randomized parity
+@pytest.mark.parametrize("p", [2, 3, 4, 8, 12])
+@pytest.mark.parametrize("distinct", [None, 3])
+def test_distributed_sort_matches_oracle_and_reference_layout(p, distinct):
+    """output bit-exact vs the oracle; SendCount rows equal the reference algorithm's
+    (mpsort-mpi.c:483-485) -- ties split by (source rank, source index)"""
+    rng = np.random.default_rng(p * 17 + (distinct or 0))
+    desc = O.Desc(0, 8, 1, 0, 0)
+    for trial in range(3):
+        sizes = [int(rng.integers(0, 30000)) for _ in range(p)]
+        if trial == 1:
+            sizes[int(rng.integers(0, p))] = 0
+        total = sum(sizes)
+        cuts = sorted(int(c) for c in rng.integers(0, total + 1, size=p - 1))
+        outsizes = [b - a for a, b in zip([0] + cuts, cuts + [total])]
+        recs = []
+        for r in range(p):
+            a = np.zeros(sizes[r], dtype=[("key", "u8"), ("tag", "u8")])
+            a["key"] = rng.integers(0, distinct, size=sizes[r]) if distinct else rng.integers(0, 1 << 63, size=sizes[r])
+            a["tag"] = (r << 40) + np.arange(sizes[r])
+            recs.append(O.as_bytes(a))
+        exp, info = O.c_sort(recs, desc, outsizes, O.DISABLE_GATHER_SORT)
+        out, stats = sort_group(recs, outsizes, desc, C.MPSORT_DISABLE_GATHER_SORT)
+        assert same(out, exp)
+        if info["nleaders"] == p:
+            for r in range(p):
+                assert stats[r]["sendcounts"] == list(info["sendcounts"][r])
+
+
+@pytest.mark.parametrize("desc,elsize", [(O.Desc(0, 8, 2, 0, 0), 40), (O.Desc(8, 8, 3, 1, 0), 36),
+                                          (O.Desc(0, 4, 1, 1, 0), 8), (O.Desc(0, 8, 1, 1, 0), 48),
+                                          (O.Desc(4, 4, 3, 0, 0), 16)])
+def test_distributed_sort_other_key_shapes(desc, elsize):
+    rng = np.random.default_rng(elsize)
+    for p in (2, 4):
+        sizes = [int(rng.integers(0, 5000)) for _ in range(p)]
+        recs = [rng.integers(0, 256, size=(n, elsize), dtype=np.uint8) for n in sizes]
+        for r in recs:          # make the most significant word collide often
+            lo = desc.offset + (desc.nwords - 1) * desc.width
+            r[:, lo + 1:lo + desc.width] = 0
+            r[:, lo] %= 3
+        exp = O.numpy_sort(recs, desc, sizes)
+        for tuning in (0, C.MPSORT_DISABLE_GATHER_SORT, C.MPSORT_REQUIRE_GATHER_SORT):
+            out, _ = sort_group(recs, sizes, desc, tuning)
+            assert same(out, exp)
+
+
+def test_all_empty_and_single_rank():
+    desc = O.Desc(0, 8, 1, 0, 0)
+    for tuning in TUNINGS:
+        out, _ = sort_group([np.zeros((0, 16), np.uint8)] * 4, [0, 0, 0, 0], desc, tuning)
+        assert all(len(o) == 0 for o in out)
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, size=(1000, 16), dtype=np.uint8)
+    out, _ = sort_group([a], [1000], desc)
+    assert same(out, O.numpy_sort([a], desc))
+
+
+# ------------------------------------------------------------------ device pointers
+def test_device_pointers_inplace_and_newarray():
+    comm = mpsort.Comm.self(0)
+    d = C.RadixDesc(0, 8, 1, 0, 0)
+    n, E = 300001, 16
+    host = O.generate(n, E, 0, 42, 0, 1)
+    exp = O.numpy_sort([host], O.Desc(0, 8, 1, 0, 0))[0]
+    din = lib.mpsort_util_dev_malloc(0, n * E)
+    dout = lib.mpsort_util_dev_malloc(0, n * E)
+    lib.mpsort_util_memcpy(0, din, host.ctypes.data, n * E)
+    lib.mpsort_mpi_newarray_desc_impl(din, n, dout, n, E, ctypes.byref(d), comm.handle, 0, b"t")
+    got = np.zeros_like(host)
+    lib.mpsort_util_memcpy(0, got.ctypes.data, dout, n * E)
+    assert np.array_equal(got, exp)
+    lib.mpsort_util_memcpy(0, din, host.ctypes.data, n * E)
+    lib.mpsort_mpi_desc_impl(din, n, E, ctypes.byref(d), comm.handle, 0, b"t")
+    lib.mpsort_util_memcpy(0, got.ctypes.data, din, n * E)
+    assert np.array_equal(got, exp)
+    lib.mpsort_util_dev_free(0, din)
+    lib.mpsort_util_dev_free(0, dout)
+    comm.destroy()
+
+
+def test_device_generator_and_checksum_match_oracle():
+    comm = mpsort.Comm.self(0)
+    for kind, E in ((0, 16), (1, 16), (2, 48), (3, 24)):
+        n = 50001
+        buf = lib.mpsort_util_dev_malloc(0, n * E)
+        lib.mpsort_util_generate(comm.handle, buf, n, E, kind, 0x5EED0001)
+        got = np.zeros((n, E), np.uint8)
+        lib.mpsort_util_memcpy(0, got.ctypes.data, buf, n * E)
+        assert np.array_equal(got, O.generate(n, E, kind, 0x5EED0001, 0, 1))
+        assert lib.mpsort_util_checksum(comm.handle, buf, n * E) == O.checksum(got)
+        assert lib.mpsort_util_checksum(comm.handle, ctypes.c_void_p(buf + 3), n * E - 5) == O.checksum(got.reshape(-1)[3:-2])
+        lib.mpsort_util_dev_free(0, buf)
+    comm.destroy()
+
+
+def test_verify_checksum_option():
+    a = O.generate(20000, 16, 0, 1, 0, 1)
+    lib.mpsort_mpi_unset_options(-1)
+    out, _ = sort_group([a[:9000], a[9000:]], [10000, 10000], O.Desc(0, 8, 1, 0, 0), C.MPSORT_VERIFY_CHECKSUM)
+    assert same(out, O.numpy_sort([a[:9000], a[9000:]], O.Desc(0, 8, 1, 0, 0), [10000, 10000]))
+
+
+# ------------------------------------------------------------------ full size, by properties
+def _property_check(comm, n, E, kind, desc, seed):
+    buf = lib.mpsort_util_dev_malloc(0, n * E)
+    lib.mpsort_util_generate(comm.handle, buf, n, E, kind, seed)
+    s1 = lib.mpsort_util_checksum(comm.handle, buf, n * E)
+    lib.mpsort_mpi_desc_impl(buf, n, E, ctypes.byref(desc), comm.handle, 0, b"fullsize")
+    s2 = lib.mpsort_util_checksum(comm.handle, buf, n * E)
+    fl = (ctypes.c_uint64 * 2)()
+    bad = lib.mpsort_util_check_sorted(comm.handle, buf, n, E, ctypes.byref(desc), 1, 8, fl)
+    # idempotence: sorting the sorted array changes nothing (stable)
+    lib.mpsort_mpi_desc_impl(buf, n, E, ctypes.byref(desc), comm.handle, 0, b"fullsize")
+    s3 = lib.mpsort_util_checksum(comm.handle, buf, n * E)
+    bad2 = lib.mpsort_util_check_sorted(comm.handle, buf, n, E, ctypes.byref(desc), 1, 8, fl)
+    lib.mpsort_util_dev_free(0, buf)
+    assert s1 == s2 == s3, "bytes changed"
+    assert bad == 0 and bad2 == 0, "order or tie order violated"
+
+
+def test_full_size_config_b_by_properties():
+    """BASELINE.json configs[1]: 2^28 uniform u64-keyed 16-byte records on one B200"""
+    comm = mpsort.Comm.self(0)
+    _property_check(comm, 1 << 28, 16, 0, C.RadixDesc(0, 8, 1, 0, 0), 0x5EED0001)
+    comm.destroy()
+
+
+def test_large_particles48_and_mostly_sorted_by_properties():
+    comm = mpsort.Comm.self(0)
+    _property_check(comm, 1 << 26, 48, 2, C.RadixDesc(0, 8, 1, 1, 0), 7)     # heavy duplicates: tie order by tag
+    _property_check(comm, 1 << 27, 16, 1, C.RadixDesc(0, 8, 1, 0, 0), 9)
+    comm.destroy()
+
+
+def test_large_multirank_by_properties():
+    """4 rank threads x 2^22 records with a 5 % equal-key run spanning ranks: global
+    order, tie order across rank boundaries, checksum of checksums"""
+    p, n, E = 4, 1 << 22, 48
+    desc = C.RadixDesc(0, 8, 1, 1, 0)
+    res = [None] * p
+
+    def work(comm):
+        r = comm.rank
+        buf = lib.mpsort_util_dev_malloc(0, n * E)
+        lib.mpsort_util_generate(comm.handle, buf, n, E, 2, 0x5EED0001)
+        s1 = lib.mpsort_util_checksum(comm.handle, buf, n * E)
+        lib.mpsort_mpi_desc_impl(buf, n, E, ctypes.byref(desc), comm.handle, 0, b"multirank")
+        s2 = lib.mpsort_util_checksum(comm.handle, buf, n * E)
+        fl = (ctypes.c_uint64 * 2)()
+        bad = lib.mpsort_util_check_sorted(comm.handle, buf, n, E, ctypes.byref(desc), 1, 8, fl)
+        first = np.zeros((1, E), np.uint8)
+        last = np.zeros((1, E), np.uint8)
+        lib.mpsort_util_memcpy(0, first.ctypes.data, buf, E)
+        lib.mpsort_util_memcpy(0, last.ctypes.data, ctypes.c_void_p(buf + (n - 1) * E), E)
+        lib.mpsort_util_dev_free(0, buf)
+        res[r] = (s1, s2, bad, first, last)
+        return None
+
+    mpsort.run_local(p, work)
+    mask = (1 << 64) - 1
+    assert sum(x[0] for x in res) & mask == sum(x[1] for x in res) & mask
+    assert all(x[2] == 0 for x in res)
+    for r in range(1, p):
+        a = res[r - 1][4].view("<i8").reshape(-1)
+        b = res[r][3].view("<i8").reshape(-1)
+        assert (a[0], a[1]) < (b[0], b[1]), "rank boundary %d out of (key, tag) order" % r
+
+
+# ------------------------------------------------------------------ NCCL, one process per GPU
+@pytest.mark.skipif(lib.mpsort_util_device_count() < 2, reason="needs >= 2 GPUs (run with gpurun --gpus 2)")
+def test_nccl_process_per_gpu():
+    n = min(lib.mpsort_util_device_count(), 8)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29517")
+    rc = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+                         "--master-addr", "127.0.0.1", "--master-port", "29517",
+                         os.path.join(ROOT, "tests", "nccl_worker.py")], env=env, timeout=600,
+                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert rc.returncode == 0, rc.stdout.decode()[-4000:]
+    assert b"NCCL PARITY OK" in rc.stdout
