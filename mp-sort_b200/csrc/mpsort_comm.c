@@ -173,6 +173,16 @@ static struct mpsort_comm * comm_alloc(int kind, int rank, int size, int device)
     }
     if (device < 0 || device >= ndev) mps_fatal(c, __FILE__, __LINE__, "device %d out of range (have %d)", device, ndev);
     CUDA_OK(c, cudaSetDevice(device));
+    {
+        /* the payload gather reads one random record per thread: fetch only the
+         * sectors asked for instead of whole 128-byte lines */
+        const char * g = getenv("MPSORT_L2_FETCH_GRANULARITY");
+        const int gran = g ? atoi(g) : 0;
+        if (gran > 0) {
+            cudaError_t e2 = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t) gran);
+            if (e2 != cudaSuccess) cudaGetLastError();
+        }
+    }
     CUDA_OK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     return c;
 }

@@ -239,7 +239,7 @@ extern "C" int mpsk_scan_histograms(const uint32_t * hist, uint32_t * bins, int 
 #define MPSK_SWEEP_MINBLOCKS 2
 #endif
 #ifndef MPSK_USE_MATCH
-#define MPSK_USE_MATCH 1
+#define MPSK_USE_MATCH 0
 #endif
 
 constexpr u32 LB_PART = 1u << 30;

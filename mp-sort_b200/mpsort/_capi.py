@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libmpsort-b200.so")
+LIB_PATH = os.environ.get("MPSORT_LIB") or os.path.join(os.path.dirname(_HERE), "libmpsort-b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
