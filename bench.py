@@ -151,6 +151,8 @@ def main():
             return subprocess.call(cmd)
         raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
 
+    # NCCL prints its version banner to stdout when NCCL_DEBUG is set: keep stdout for the JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import numpy as np
     import mpsort                       # raises if libmpsort-b200.so / the binding are missing
     from mpsort import _capi as C

@@ -76,7 +76,8 @@ void MPIU_Set_verbose_malloc(mpsort_comm_t comm)
 
 static const char * slot_names[MPS_NSLOTS] = {
     "din", "dout", "keywords", "keys_b", "keys_a", "idx_a", "idx_b", "sortedkeys",
-    "hist", "lookback", "sendbuf", "recvbuf", "splitters", "stage", "stage2", "misc"
+    "hist", "lookback", "sendbuf", "recvbuf", "splitters", "stage", "stage2", "misc",
+    "merge_samples", "merge_cuts"
 };
 
 void * mps_arena_get(struct mpsort_comm * c, int slot, size_t bytes)
@@ -129,7 +130,7 @@ void mps_kt_begin(struct mpsort_comm * c, int cls)
     if (!k->on) return;
     if (k->n >= MPS_KT_MAX) { CUDA_OK(c, cudaStreamSynchronize(c->stream)); mps_kt_collect(c); }
     while (k->nev < 2 * (k->n + 1)) { CUDA_OK(c, cudaEventCreate(&k->ev[k->nev])); k->nev++; }
-    k->cls[k->n] = cls;
+    k->cls[k->n] = k->force_cls > 0 ? k->force_cls : cls;
     CUDA_OK(c, cudaEventRecord(k->ev[2 * k->n], c->stream));
 }
 

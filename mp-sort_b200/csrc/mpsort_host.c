@@ -264,6 +264,61 @@ static void local_sort(struct mpsort_comm * c, const void * dbase, size_t n, siz
 }
 
 /* ------------------------------------------------------------------------- */
+/* SecondSort as a stable p-way merge of the received runs                    */
+
+/* The receive buffer is p sorted runs in source-rank order (reference RecvDispl
+ * layout, mpsort-mpi.c:490-503); the reference re-sorts it with the stable merge
+ * sort (:597), which leaves equal keys in (source rank, source index) order. A
+ * stable p-way merge that prefers the lower run on ties gives the same bytes with
+ * E read + E write per record instead of a full radix sort.
+ * Returns 0 if the merge ran, 1 if the caller must use the radix path. */
+static int merge_received_runs(struct mpsort_comm * c, const void * recvbuf, const int64_t * rdispl,
+        void * dout, size_t outn, size_t elsize, const struct mpsort_radix_desc * desc)
+{
+    const int p = c->size;
+    const size_t T = mpsk_merge_tile_items();
+    int r;
+    if (key_words(desc) != 1 || p > 32 || p < 2 || outn < 4 * T || outn > 0xfffffff0u) return 1;
+    if (getenv("MPSORT_NO_MERGE")) return 1;
+    /* (k + p) * S <= T with k = 3p: S = T / (4p) rounded down to a power of two */
+    uint32_t S = 1;
+    while ((size_t) S * 2 * 4 * (size_t) p <= T) S *= 2;
+    const uint32_t k = (uint32_t) (T / S) - (uint32_t) p;
+    uint32_t rd[33], ss[33];
+    ss[0] = 0;
+    for (r = 0; r < p; r++) {
+        rd[r] = (uint32_t) rdispl[r];
+        ss[r + 1] = ss[r] + (uint32_t) ((rdispl[r + 1] - rdispl[r]) / S);
+    }
+    rd[p] = (uint32_t) rdispl[p];
+    const uint32_t ns = ss[p];
+    const uint32_t ntiles = ns == 0 ? 1 : (ns + k - 1) / k;
+
+    uint64_t * skeys = (uint64_t *) mps_arena_get(c, MPS_S_MERGE_SAMP, (size_t) (ns ? ns : 1) * sizeof(uint64_t));
+    uint32_t * cut = (uint32_t *) mps_arena_get(c, MPS_S_MERGE_CUT, ((size_t) ntiles + 1) * p * sizeof(uint32_t) + 256);
+    uint32_t * overflow = cut + ((size_t) ntiles + 1) * p;
+    CUDA_OK(c, cudaMemsetAsync(overflow, 0, sizeof(uint32_t), c->stream));
+    KERN_T(c, MPS_K_MERGE, mpsk_merge_samples(recvbuf, elsize, desc->offset, desc->width, desc->nwords, desc->is_signed,
+                                              (uint32_t) p, S, k, rd, ss, skeys, c->stream));
+    /* sample keys are already packed (sign-flipped): sort them as bare unsigned u64 records */
+    struct sorted_view sv;
+    const struct mpsort_radix_desc sdesc = { 0, 8, 1, 0, 0 };
+    c->kt.force_cls = MPS_K_MERGE;      /* the sample sort is part of the merge, not a full-size pass */
+    local_sort(c, skeys, ns, sizeof(uint64_t), &sdesc, 1, &sv);
+    c->kt.force_cls = 0;
+    KERN_T(c, MPS_K_MERGE, mpsk_merge_runs(recvbuf, dout, elsize, desc->offset, desc->width, desc->nwords, desc->is_signed,
+                                           (uint32_t) p, S, k, rd, ss, sv.skeys, sv.idx, ntiles, cut, overflow, c->stream));
+    {
+        uint32_t * h = (uint32_t *) mps_host_stage(c, sizeof(uint32_t));
+        CUDA_OK(c, cudaMemcpyAsync(h, overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(c, cudaStreamSynchronize(c->stream));
+        if (*h != 0) mps_fatal(c, __FILE__, __LINE__, "serious bug: %u merge tiles exceeded their bound", *h);
+    }
+    c->stats.second_sort_merge_tiles = ntiles;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------- */
 /* helpers                                                                    */
 
 static int is_device_pointer(struct mpsort_comm * c, const void * p)
@@ -539,10 +594,15 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
     /* ---- SecondSort: the received buffer is p sorted runs in source-rank order;
      * a stable sort of it restores global order with ties by (source rank, index) */
     {
-        struct sorted_view v2;
-        local_sort(c, recvbuf, outn, elsize, desc, 0, &v2);
-        KERN_T(c, MPS_K_GATHER_RECORDS, mpsk_gather_records(recvbuf, v2.idx, dout, outn, elsize, c->stream));
-        c->stats.second_sort_passes = v2.npasses;
+        int64_t rdispl[MPS_MAX_RANKS + 1];
+        rdispl[0] = 0;
+        for (j = 0; j < p; j++) rdispl[j + 1] = rdispl[j] + (cut[(size_t) j * (p + 1) + c->rank + 1] - cut[(size_t) j * (p + 1) + c->rank]);
+        if (merge_received_runs(c, recvbuf, rdispl, dout, outn, elsize, desc) != 0) {
+            struct sorted_view v2;
+            local_sort(c, recvbuf, outn, elsize, desc, 0, &v2);
+            KERN_T(c, MPS_K_GATHER_RECORDS, mpsk_gather_records(recvbuf, v2.idx, dout, outn, elsize, c->stream));
+            c->stats.second_sort_passes = v2.npasses;
+        }
     }
     timer_mark(c, "SecondSort");
     timer_mark(c, "END");

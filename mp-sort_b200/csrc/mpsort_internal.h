@@ -39,6 +39,8 @@ enum mps_slot {
     MPS_S_STAGE,       /* device side of small host collectives        */
     MPS_S_STAGE2,      /* scratch for the in-process allreduce         */
     MPS_S_MISC,        /* checksum / small outputs                     */
+    MPS_S_MERGE_SAMP,  /* merge: sample keys                           */
+    MPS_S_MERGE_CUT,   /* merge: per-tile cut positions                */
     MPS_NSLOTS
 };
 
@@ -63,10 +65,11 @@ struct mps_timers {
 /* per-kernel-class timing (bench.py's roofline numbers): CUDA events around every
  * launch of a class on the communicator's stream, summed after the stream sync */
 enum mps_kclass { MPS_K_EXTRACT = 0, MPS_K_ONESWEEP, MPS_K_GATHER_KEYS, MPS_K_GATHER_RECORDS,
-                  MPS_K_SPLITTER, MPS_K_CHECKSUM, MPS_K_EXCHANGE, MPS_NKCLASS };
+                  MPS_K_SPLITTER, MPS_K_CHECKSUM, MPS_K_EXCHANGE, MPS_K_MERGE, MPS_NKCLASS };
 #define MPS_KT_MAX 512
 struct mps_ktimes {
     int on;
+    int force_cls;                       /* >= 0: book every launch under this class */
     int n;                               /* pending event pairs */
     int nev;                             /* events created */
     cudaEvent_t ev[2 * MPS_KT_MAX];

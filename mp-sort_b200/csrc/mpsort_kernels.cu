@@ -257,19 +257,39 @@ __device__ __forceinline__ void st_relaxed_u32(u32 * p, u32 v)
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
-/* lanes of the warp whose digit equals mine */
+/* lanes of the warp whose digit equals mine.
+ * __match_any_sync (MATCH.ANY) costs ~2x more MIO time than eight ballots on B200
+ * (profiles/r01_sweep1_match_vs_ballot.log), so the default splits bit by bit:
+ * per bit one predicate, one VOTE and one predicated AND. */
+template <int BIT>
+__device__ __forceinline__ u32 match_bit(u32 peers, u32 digit)
+{
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 t, v;\n\t"
+        "and.b32 t, %1, %2;\n\t"
+        "setp.ne.u32 p, t, 0;\n\t"
+        "vote.sync.ballot.b32 v, p, 0xffffffff;\n\t"
+        "@!p not.b32 v, v;\n\t"
+        "and.b32 %0, %0, v;\n\t"
+        "}" : "+r"(peers) : "r"(digit), "n"(1u << BIT));
+    return peers;
+}
+
 __device__ __forceinline__ u32 match_digit(u32 digit)
 {
 #if MPSK_USE_MATCH
     return __match_any_sync(FULL_MASK, digit);
 #else
     u32 peers = FULL_MASK;
-#pragma unroll
-    for (int b = 0; b < MPSK_RADIX_BITS; b++) {
-        const u32 bit = (digit >> b) & 1u;
-        const u32 vote = __ballot_sync(FULL_MASK, bit);
-        peers &= bit ? vote : ~vote;
-    }
+    peers = match_bit<0>(peers, digit);
+    peers = match_bit<1>(peers, digit);
+    peers = match_bit<2>(peers, digit);
+    peers = match_bit<3>(peers, digit);
+    peers = match_bit<4>(peers, digit);
+    peers = match_bit<5>(peers, digit);
+    peers = match_bit<6>(peers, digit);
+    peers = match_bit<7>(peers, digit);
     return peers;
 #endif
 }
@@ -425,15 +445,26 @@ onesweep_kernel(const u64 * __restrict__ kin, const u32 * __restrict__ vin,
     }
     __syncthreads();  /* all ranks read from s_whist: it may now be reused as s_vals */
 
-    /* ---- decoupled look-back: exclusive count of my digit over earlier tiles */
+    /* ---- decoupled look-back: exclusive count of my digit over earlier tiles.
+     * Four predecessors are polled per round trip (the walk is latency bound: one L2
+     * access per predecessor otherwise). */
     if (tid < 256) {
         u32 excl = 0;
         if (tile > 0) {
             int t = (int) tile - 1;
-            while (true) {
-                const u32 s = ld_relaxed_u32(&lookback[(size_t) t * 256 + tid]);
-                if (s & LB_INCL) { excl += s & LB_MASK; break; }
-                if (s & LB_PART) { excl += s & LB_MASK; t--; }
+            bool done = false;
+            while (!done) {
+                u32 s[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    s[k] = (t - k >= 0) ? ld_relaxed_u32(&lookback[(size_t) (t - k) * 256 + tid]) : LB_INCL;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (done) break;
+                    if (s[k] & LB_INCL) { excl += s[k] & LB_MASK; done = true; }
+                    else if (s[k] & LB_PART) { excl += s[k] & LB_MASK; t--; }
+                    else break;          /* not published yet: poll again from here */
+                }
             }
             st_relaxed_u32(&lookback[(size_t) tile * 256 + tid], LB_INCL | (excl + cnt_valid));
         }
@@ -479,23 +510,17 @@ extern "C" int mpsk_onesweep_pass(const uint64_t * kin, const uint32_t * vin,
     if (e != cudaSuccess) return (int) e;
     u32 * ticket = (u32 *) scratch;
     u32 * lookback = ticket + 64;
-    static bool attr_set[2] = {false, false};
+    /* the attribute is per device: set it on every launch (local groups span devices) */
     if (vin == NULL) {
         auto kern = onesweep_kernel<MPSK_SWEEP_THREADS, MPSK_SWEEP_IPT, true>;
-        if (!attr_set[0]) {
-            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TheSweep::SMEM);
-            if (e != cudaSuccess) return (int) e;
-            attr_set[0] = true;
-        }
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TheSweep::SMEM);
+        if (e != cudaSuccess) return (int) e;
         kern<<<(unsigned) ntiles, MPSK_SWEEP_THREADS, TheSweep::SMEM, stream>>>(
             (const u64 *) kin, vin, (u64 *) kout, vout, (u32) n, (u32) shift, bins, lookback, ticket);
     } else {
         auto kern = onesweep_kernel<MPSK_SWEEP_THREADS, MPSK_SWEEP_IPT, false>;
-        if (!attr_set[1]) {
-            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TheSweep::SMEM);
-            if (e != cudaSuccess) return (int) e;
-            attr_set[1] = true;
-        }
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TheSweep::SMEM);
+        if (e != cudaSuccess) return (int) e;
         kern<<<(unsigned) ntiles, MPSK_SWEEP_THREADS, TheSweep::SMEM, stream>>>(
             (const u64 *) kin, vin, (u64 *) kout, vout, (u32) n, (u32) shift, bins, lookback, ticket);
     }
@@ -754,6 +779,235 @@ extern "C" int mpsk_sum_u64(uint64_t * dst, const uint64_t * const * srcs, int n
     sum_u64_kernel<<<(unsigned) blocks, threads, 0, (cudaStream_t) stream>>>((u64 *) dst, s, nsrc, count);
     CUDA_LAUNCH_CHECK();
     return 0;
+}
+
+/* ========================================================================= */
+/* K7: stable p-way merge of the received runs (replaces the second radix_sort, */
+/* mpsort-mpi.c:597, whose input is p sorted runs in source-rank order)          */
+/* ========================================================================= */
+/*
+ * The receive buffer holds p sorted runs (run r = records [rdispl[r], rdispl[r+1])).
+ * 1. merge_sample_kernel: every S-th key of every run (the last key of each full
+ *    block of S) -> samples in (run, position) order.
+ * 2. the samples are sorted stably by key with the onesweep sort (host side), which
+ *    orders them by (key, run, position).
+ * 3. merge_bounds_kernel: every k-th merged sample is a tile boundary; its cut
+ *    position in every run is found by binary search (upper bound in lower runs,
+ *    lower bound in higher runs: ties go to the lower run first, like the stable
+ *    merge of stdlib/msort.c:78). A tile holds < (k + p) * S records.
+ * 4. merge_tile_kernel: one CTA per tile loads the p sub-ranges' keys into shared
+ *    memory, merges them pairwise in log2(p) rounds (every key finds its rank in the
+ *    sibling sequence by binary search: A-side lower bound, B-side upper bound) and
+ *    writes the records out in merged order.
+ * HBM traffic: E read + E write per record (+ ~8/S for the samples).
+ */
+#define MPSK_MERGE_MAX_RUNS 32
+#define MPSK_MERGE_TILE 4096
+#define MPSK_MERGE_THREADS 512
+
+struct MergeRuns {
+    u32 p;
+    u32 S;            /* sample stride */
+    u32 k;            /* samples per tile */
+    u32 rdispl[MPSK_MERGE_MAX_RUNS + 1];   /* run starts in records */
+    u32 sstart[MPSK_MERGE_MAX_RUNS + 1];   /* first sample id of every run */
+};
+
+__device__ __forceinline__ u64 load_key_any(const unsigned char * rec, const KeyDesc & d, bool fast8)
+{
+    if (fast8) return (*(const u64 *) (rec + d.offset)) ^ (d.is_signed ? (1ULL << 63) : 0ULL);
+    return pack_key_word(rec, d);
+}
+
+__global__ void __launch_bounds__(256)
+merge_sample_kernel(const unsigned char * __restrict__ recv, KeyDesc d, bool fast8, MergeRuns m,
+                    u64 * __restrict__ skeys)
+{
+    const u32 ns = m.sstart[m.p];
+    for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < ns; s += gridDim.x * blockDim.x) {
+        u32 r = 0;
+        while (s >= m.sstart[r + 1]) r++;
+        const u32 j = s - m.sstart[r];
+        const size_t pos = (size_t) m.rdispl[r] + (size_t) (j + 1) * m.S - 1;
+        skeys[s] = load_key_any(recv + pos * d.elsize, d, fast8);
+    }
+}
+
+/* cut[t * p + r] for t = 0 .. ntiles */
+__global__ void __launch_bounds__(256)
+merge_bounds_kernel(const unsigned char * __restrict__ recv, KeyDesc d, bool fast8, MergeRuns m,
+                    const u64 * __restrict__ sorted_skeys, const u32 * __restrict__ sorted_sid,
+                    u32 ntiles, u32 * __restrict__ cut)
+{
+    const u32 total = (ntiles + 1) * m.p;
+    for (u32 x = blockIdx.x * blockDim.x + threadIdx.x; x < total; x += gridDim.x * blockDim.x) {
+        const u32 t = x / m.p, r = x - t * m.p;
+        const u32 len = m.rdispl[r + 1] - m.rdispl[r];
+        u32 c;
+        if (t == 0) c = 0;
+        else if (t == ntiles) c = len;
+        else {
+            const u32 mi = t * m.k - 1;
+            const u64 kb = sorted_skeys[mi];
+            const u32 sid = sorted_sid[mi];
+            u32 rb = 0;
+            while (sid >= m.sstart[rb + 1]) rb++;
+            if (r == rb) {
+                c = (sid - m.sstart[rb] + 1) * m.S;
+            } else {
+                const unsigned char * base = recv + (size_t) m.rdispl[r] * d.elsize;
+                u32 lo = 0, hi = len;
+                const bool upper = r < rb;
+                while (lo < hi) {
+                    const u32 mid = lo + ((hi - lo) >> 1);
+                    const u64 kk = load_key_any(base + (size_t) mid * d.elsize, d, fast8);
+                    const bool right = upper ? (kk <= kb) : (kk < kb);
+                    if (right) lo = mid + 1; else hi = mid;
+                }
+                c = lo;
+            }
+        }
+        cut[x] = c;
+    }
+}
+
+template <typename V>
+__global__ void __launch_bounds__(MPSK_MERGE_THREADS, 2)
+merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, bool fast8, MergeRuns m,
+                  const u32 * __restrict__ cut, unsigned char * __restrict__ out, u32 * __restrict__ overflow)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 * kA = (u64 *) smem_raw;
+    u64 * kB = kA + MPSK_MERGE_TILE;
+    u32 * sA = (u32 *) (kB + MPSK_MERGE_TILE);
+    u32 * sB = sA + MPSK_MERGE_TILE;
+    __shared__ u32 seqoff[MPSK_MERGE_MAX_RUNS + 1];
+    __shared__ u32 srcbase[MPSK_MERGE_MAX_RUNS];
+    __shared__ u32 s_outstart;
+
+    const u32 t = blockIdx.x, p = m.p, tid = threadIdx.x;
+    if (tid == 0) {
+        u32 acc = 0, ostart = 0;
+        for (u32 r = 0; r < p; r++) {
+            const u32 c0 = cut[t * p + r], c1 = cut[(t + 1) * p + r];
+            seqoff[r] = acc;
+            srcbase[r] = m.rdispl[r] + c0;
+            acc += c1 - c0;
+            ostart += c0;
+        }
+        seqoff[p] = acc;
+        s_outstart = ostart;
+    }
+    __syncthreads();
+    const u32 cnt = seqoff[p];
+    if (cnt > MPSK_MERGE_TILE) {            /* cannot happen (tile bound); never corrupt memory */
+        if (tid == 0) atomicAdd(overflow, 1u);
+        return;
+    }
+    /* ---- load keys of the p sub-ranges, run-major */
+    for (u32 i = tid; i < cnt; i += MPSK_MERGE_THREADS) {
+        u32 r = 0;
+        while (i >= seqoff[r + 1]) r++;
+        const u32 src = srcbase[r] + (i - seqoff[r]);
+        kA[i] = load_key_any(recv + (size_t) src * d.elsize, d, fast8);
+        sA[i] = src;
+    }
+    __syncthreads();
+    /* ---- pairwise merge rounds over groups of w runs */
+    for (u32 w = 1; w < p; w <<= 1) {
+        for (u32 i = tid; i < cnt; i += MPSK_MERGE_THREADS) {
+            u32 g = 0;
+            while ((g + 1) * w < p && i >= seqoff[(g + 1) * w]) g++;
+            const u32 ga = g & ~1u;
+            const u32 a0 = seqoff[ga * w];
+            const u32 a1 = seqoff[min((ga + 1) * w, p)];
+            const u32 b1 = seqoff[min((ga + 2) * w, p)];
+            const u64 key = kA[i];
+            u32 pos;
+            if (g == ga) {                      /* A side: count of B keys < key */
+                u32 lo = a1, hi = b1;
+                while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (kA[mid] < key) lo = mid + 1; else hi = mid; }
+                pos = i + (lo - a1);
+            } else {                            /* B side: count of A keys <= key */
+                u32 lo = a0, hi = a1;
+                while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (kA[mid] <= key) lo = mid + 1; else hi = mid; }
+                pos = a0 + (lo - a0) + (i - a1);
+            }
+            kB[pos] = key;
+            sB[pos] = sA[i];
+        }
+        __syncthreads();
+        u64 * tk = kA; kA = kB; kB = tk;
+        u32 * ts = sA; sA = sB; sB = ts;
+    }
+    /* ---- write the records in merged order (lanes of one record move consecutive pieces) */
+    const u32 lpr = (u32) (d.elsize / sizeof(V));
+    const V * in = (const V *) recv;
+    V * o = (V *) out + (size_t) s_outstart * lpr;
+    const u32 totalv = cnt * lpr;
+    for (u32 x = tid; x < totalv; x += MPSK_MERGE_THREADS) {
+        const u32 i = x / lpr, part = x - i * lpr;
+        o[x] = in[(size_t) sA[i] * lpr + part];
+    }
+}
+
+extern "C" size_t mpsk_merge_tile_items(void) { return MPSK_MERGE_TILE; }
+
+extern "C" int mpsk_merge_samples(const void * recv, size_t elsize, size_t offset, uint32_t width,
+        uint32_t nwords, int is_signed, uint32_t p, uint32_t S, uint32_t k,
+        const uint32_t * rdispl, const uint32_t * sstart, uint64_t * skeys, mpsk_stream_t stream)
+{
+    if (p > MPSK_MERGE_MAX_RUNS) return (int) cudaErrorInvalidValue;
+    MergeRuns m; m.p = p; m.S = S; m.k = k;
+    for (u32 r = 0; r <= p; r++) { m.rdispl[r] = rdispl[r]; m.sstart[r] = sstart[r]; }
+    const u32 ns = sstart[p];
+    if (ns == 0) return 0;
+    KeyDesc d; d.elsize = elsize; d.offset = offset; d.width = width; d.nwords = nwords; d.is_signed = is_signed; d.g = 0;
+    const bool fast8 = (width == 8) && (nwords == 1) && (elsize % 8 == 0) && (offset % 8 == 0) && ((((uintptr_t) recv) & 7) == 0);
+    u32 blocks = (ns + 255) / 256;
+    if (blocks > (u32) num_sms() * 8) blocks = (u32) num_sms() * 8;
+    merge_sample_kernel<<<blocks, 256, 0, (cudaStream_t) stream>>>((const unsigned char *) recv, d, fast8, m, (u64 *) skeys);
+    CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
+template <typename V>
+static int launch_merge_tiles(const void * recv, KeyDesc d, bool fast8, const MergeRuns & m, const u32 * cut,
+                              void * out, u32 * overflow, u32 ntiles, cudaStream_t stream)
+{
+    const int smem = MPSK_MERGE_TILE * (8 + 8 + 4 + 4);
+    auto kern = merge_tile_kernel<V>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int) e;
+    kern<<<ntiles, MPSK_MERGE_THREADS, smem, stream>>>((const unsigned char *) recv, d, fast8, m, cut,
+                                                       (unsigned char *) out, overflow);
+    CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mpsk_merge_runs(const void * recv, void * out, size_t elsize, size_t offset, uint32_t width,
+        uint32_t nwords, int is_signed, uint32_t p, uint32_t S, uint32_t k,
+        const uint32_t * rdispl, const uint32_t * sstart,
+        const uint64_t * sorted_skeys, const uint32_t * sorted_sid, uint32_t ntiles,
+        uint32_t * cut, uint32_t * overflow, mpsk_stream_t stream_)
+{
+    if (p > MPSK_MERGE_MAX_RUNS) return (int) cudaErrorInvalidValue;
+    cudaStream_t stream = (cudaStream_t) stream_;
+    MergeRuns m; m.p = p; m.S = S; m.k = k;
+    for (u32 r = 0; r <= p; r++) { m.rdispl[r] = rdispl[r]; m.sstart[r] = sstart[r]; }
+    KeyDesc d; d.elsize = elsize; d.offset = offset; d.width = width; d.nwords = nwords; d.is_signed = is_signed; d.g = 0;
+    const bool fast8 = (width == 8) && (nwords == 1) && (elsize % 8 == 0) && (offset % 8 == 0) && ((((uintptr_t) recv) & 7) == 0);
+    const u32 total = (ntiles + 1) * p;
+    u32 blocks = (total + 255) / 256;
+    merge_bounds_kernel<<<blocks, 256, 0, stream>>>((const unsigned char *) recv, d, fast8, m,
+                                                    (const u64 *) sorted_skeys, sorted_sid, ntiles, cut);
+    CUDA_LAUNCH_CHECK();
+    const uintptr_t a = ((uintptr_t) recv) | ((uintptr_t) out) | (uintptr_t) elsize;
+    if ((a & 15) == 0) return launch_merge_tiles<uint4>(recv, d, fast8, m, cut, out, overflow, ntiles, stream);
+    if ((a & 7) == 0) return launch_merge_tiles<u64>(recv, d, fast8, m, cut, out, overflow, ntiles, stream);
+    if ((a & 3) == 0) return launch_merge_tiles<u32>(recv, d, fast8, m, cut, out, overflow, ntiles, stream);
+    if ((a & 1) == 0) return launch_merge_tiles<unsigned short>(recv, d, fast8, m, cut, out, overflow, ntiles, stream);
+    return launch_merge_tiles<unsigned char>(recv, d, fast8, m, cut, out, overflow, ntiles, stream);
 }
 
 /* ========================================================================= */

@@ -86,13 +86,25 @@ int mpsk_splitter_final(const uint64_t * skeys, size_t stride, size_t n, uint32_
 int mpsk_sum_u64(uint64_t * dst, const uint64_t * const * srcs, int nsrc, size_t count,
         mpsk_stream_t stream);
 
-/* K7: stable merge of two adjacent sorted runs of records (keys read from the
- * records through the descriptor). a = [0,na), b = [0,nb) -> out[0, na+nb); ties
- * take from a first (stdlib/msort.c:78 "<= 0 => left first"). Keys are the packed
- * u64 words ka[w][.], kb[w][.] carried beside the records. */
-int mpsk_merge_pairs(const uint64_t * ka, const uint32_t * va, size_t na,
-        const uint64_t * kb, const uint32_t * vb, size_t nb,
-        uint64_t * kout, uint32_t * vout, mpsk_stream_t stream);
+/* K7: stable p-way merge of the received runs (replaces the second radix_sort,
+ * mpsort-mpi.c:597). recv holds p sorted runs, run r = records [rdispl[r], rdispl[r+1]).
+ * Single-word keys, p <= 32. S = sample stride, k = samples per tile with
+ * (k + p) * S <= mpsk_merge_tile_items(); sstart[r] = first sample id of run r
+ * (run r has (len_r / S) samples).
+ *   mpsk_merge_samples  writes the sample keys skeys[sstart[p]] in (run, position) order;
+ *   the caller sorts them stably by key (sorted_skeys, sorted_sid = permutation);
+ *   mpsk_merge_runs     computes cut[(ntiles+1)*p] and merges tile by tile into out.
+ * *overflow (device, zeroed by the caller) counts tiles that exceeded the bound
+ * (never happens; such a tile is left unwritten instead of corrupting memory). */
+size_t mpsk_merge_tile_items(void);
+int mpsk_merge_samples(const void * recv, size_t elsize, size_t offset, uint32_t width,
+        uint32_t nwords, int is_signed, uint32_t p, uint32_t S, uint32_t k,
+        const uint32_t * rdispl, const uint32_t * sstart, uint64_t * skeys, mpsk_stream_t stream);
+int mpsk_merge_runs(const void * recv, void * out, size_t elsize, size_t offset, uint32_t width,
+        uint32_t nwords, int is_signed, uint32_t p, uint32_t S, uint32_t k,
+        const uint32_t * rdispl, const uint32_t * sstart,
+        const uint64_t * sorted_skeys, const uint32_t * sorted_sid, uint32_t ntiles,
+        uint32_t * cut, uint32_t * overflow, mpsk_stream_t stream);
 
 /* K8: reference checksum (mpsort-mpi.c:148-159): sum of all bytes as SIGNED chars,
  * wrapping in 64 bits; accumulated (atomicAdd) into *sum which the caller zeroes. */

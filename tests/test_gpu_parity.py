@@ -207,6 +207,40 @@ def test_distributed_sort_other_key_shapes(desc, elsize):
             assert same(out, exp)
 
 
+@pytest.mark.parametrize("p,elsize,desc,distinct", [
+    (2, 16, O.Desc(0, 8, 1, 0, 0), None), (3, 16, O.Desc(0, 8, 1, 0, 0), 7), (8, 16, O.Desc(8, 8, 1, 1, 0), None),
+    (4, 48, O.Desc(0, 8, 1, 1, 0), 100), (5, 12, O.Desc(4, 4, 1, 0, 0), None), (12, 24, O.Desc(8, 8, 1, 0, 0), 2),
+    (4, 7, O.Desc(1, 2, 1, 0, 1), None)])
+def test_second_sort_merge_path(p, elsize, desc, distinct):
+    """SecondSort as a stable p-way merge (replaces the second radix_sort,
+    mpsort-mpi.c:597): bit-exact vs the oracle incl. ties across runs"""
+    rng = np.random.default_rng(p * 1000 + elsize)
+    sizes = [int(rng.integers(40000, 90000)) for _ in range(p)]
+    sizes[int(rng.integers(0, p))] = 0
+    total = sum(sizes)
+    outsizes = [total // p] * p
+    outsizes[-1] += total - sum(outsizes)
+    recs = []
+    for r in range(p):
+        a = rng.integers(0, 256, size=(sizes[r], elsize), dtype=np.uint8)
+        if distinct:
+            lo, hi = desc.offset, desc.offset + desc.width * desc.nwords
+            a[:, lo:hi] = 0
+            a[:, lo] = rng.integers(0, distinct, size=sizes[r])
+        recs.append(a)
+    exp = O.numpy_sort(recs, desc, outsizes)
+    out, stats = sort_group(recs, outsizes, desc, C.MPSORT_DISABLE_GATHER_SORT)
+    assert same(out, exp)
+    assert all(st["second_sort_merge_tiles"] > 0 for st in stats), "the merge path did not run"
+    # and the radix SecondSort gives the same bytes
+    os.environ["MPSORT_NO_MERGE"] = "1"
+    try:
+        out2, stats2 = sort_group(recs, outsizes, desc, C.MPSORT_DISABLE_GATHER_SORT)
+    finally:
+        del os.environ["MPSORT_NO_MERGE"]
+    assert same(out2, exp) and all(st["second_sort_merge_tiles"] == 0 for st in stats2)
+
+
 def test_all_empty_and_single_rank():
     desc = O.Desc(0, 8, 1, 0, 0)
     for tuning in TUNINGS:
