@@ -222,12 +222,16 @@ def main():
 
     # ---- roofline of the dominant kernel (the onesweep pass), measured live above
     peak, peak_src = peaks()
-    ms_sweep, n_sweep = ktimes.get("onesweep_pass", (0.0, 0))
+    # record mode (16-byte records carried through the passes) moves 32 B per record and
+    # pass, index mode (u64 key + u32 index) 24 B; whichever ran is the dominant kernel
+    cand = [("onesweep_pass_rec16", "onesweep_rec16_kernel", 32.0), ("onesweep_pass", "onesweep_kernel", 24.0)]
+    cand = [(ktimes.get(c[0], (0.0, 0)), c) for c in cand]
+    (ms_sweep, n_sweep), (kclass, kname, bytes_per_item) = max(cand, key=lambda x: x[0][0])
     roofline = None
     if n_sweep:
-        alg_bytes = 24.0 * n            # per launch: read (u64 key + u32 index), write the same
+        alg_bytes = bytes_per_item * n   # per launch: every record (or key+index pair) read once, written once
         ach = alg_bytes / (ms_sweep / n_sweep * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "onesweep_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "launches_timed": n_sweep,
                     "avg_launch_ms": ms_sweep / n_sweep,
@@ -236,12 +240,13 @@ def main():
         if os.path.exists(prof):
             try:
                 with open(prof) as f:
-                    roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
+                    roofline["traffic"] = json.load(f).get(kname, {}).get("dram_bytes_per_launch")
             except Exception:
                 pass
     kernels = {}
     passes = stats["first_sort_passes"] + stats["second_sort_passes"]
-    algo = {"extract_hist": (E + 8.0) * n, "onesweep_pass": 24.0 * n, "gather_records": (2.0 * E + 4) * n}
+    algo = {"onesweep_pass": 24.0 * n, "onesweep_pass_rec16": 32.0 * n, "gather_records": (2.0 * E + 4) * n,
+            "merge_runs": 2.0 * E * n}
     for name, (ms, cnt) in ktimes.items():
         if cnt:
             kernels[name] = {"ms_per_step": ms / K, "launches_per_step": cnt / K}
@@ -249,7 +254,10 @@ def main():
                 per_launch_ms = ms / cnt
                 kernels[name]["achieved_gbs"] = algo[name] / (per_launch_ms * 1e-3) / 1e9
                 kernels[name]["frac_of_peak"] = kernels[name]["achieved_gbs"] / peak
-    local_sort_bytes = (3.0 * E + 12 + 24.0 * stats["first_sort_passes"]) * n
+    if stats.get("record_mode"):
+        local_sort_bytes = (E + 32.0 * stats["first_sort_passes"]) * n
+    else:
+        local_sort_bytes = (3.0 * E + 12 + 24.0 * stats["first_sort_passes"]) * n
 
     # ---- end to end through the public API with pinned host buffers
     e2e = None
@@ -316,6 +324,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu,
             "kernels": kernels,
             "local_sort": {"algorithmic_bytes": local_sort_bytes, "passes": stats["first_sort_passes"],
+                           "record_mode": bool(stats.get("record_mode")), "merge_tiles": stats.get("second_sort_merge_tiles"),
                            "second_sort_passes": stats["second_sort_passes"],
                            "ms": sum(v for k, v in phases if k == "FirstSort") * 1e3},
             "phases_ms": [[k, v * 1e3] for k, v in phases],

@@ -181,7 +181,7 @@ struct mpsort_last_stats {
     uint32_t dense_exchange;     /* 1 if zero-length pairs were also posted     */
     uint64_t bytes_sent_remote;  /* record bytes that left this GPU             */
     uint32_t second_sort_merge_tiles; /* > 0: SecondSort ran as a p-way merge of this many tiles */
-    uint32_t reserved;
+    uint32_t record_mode;        /* 1: 16-byte records were carried through the passes themselves */
 };
 void mpsort_comm_last_stats(mpsort_comm_t comm, struct mpsort_last_stats * st,
                             int64_t * sendcounts, int max);

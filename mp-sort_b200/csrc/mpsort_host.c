@@ -157,6 +157,8 @@ struct sorted_view {
     const uint32_t * idx;     /* idx[i] = original position of the i-th smallest record */
     uint32_t nw;
     uint32_t npasses;
+    struct mpsk_keyview kv;   /* how the splitter kernels read the sorted keys */
+    const void * sorted_recs; /* record mode: the records themselves, already in sorted order */
 };
 
 static uint32_t key_words(const struct mpsort_radix_desc * d)
@@ -254,12 +256,75 @@ static void local_sort(struct mpsort_comm * c, const void * dbase, size_t n, siz
     if (want_keys) {
         if (nw == 1) {
             out->skeys = cur_keys;
+            out->kv.base = cur_keys; out->kv.item_stride = 8; out->kv.word_stride = 0; out->kv.flip = 0;
         } else {
             uint64_t * sk = (uint64_t *) mps_arena_get(c, MPS_S_SK, (size_t) nw * n * sizeof(uint64_t));
             for (g = 0; g < nw; g++)
                 KERN_T(c, MPS_K_GATHER_KEYS, mpsk_gather_u64(kw + (size_t) g * n, cur_idx, sk + (size_t) g * n, n, c->stream));
             out->skeys = sk;
+            out->kv.base = sk; out->kv.item_stride = 8; out->kv.word_stride = n * sizeof(uint64_t); out->kv.flip = 0;
         }
+    }
+}
+
+/*
+ * Record mode: a 16-byte record that is nothing but an aligned 8-byte key and 8 more
+ * bytes is carried through the passes itself (mpsk_onesweep_pass_rec16): no key
+ * extraction, no index array, no payload gather. `dest` receives the sorted records;
+ * it may equal dbase (in place). dbase is only read when dest != dbase.
+ */
+static int rec16_applicable(size_t elsize, const struct mpsort_radix_desc * d, const void * dbase, const void * dest)
+{
+    if (getenv("MPSORT_NO_REC16")) return 0;
+    return elsize == 16 && d->nwords == 1 && d->width == 8 && (d->offset == 0 || d->offset == 8)
+           && ((((uintptr_t) dbase) | ((uintptr_t) dest)) & 15) == 0;
+}
+
+static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t n,
+        const struct mpsort_radix_desc * desc, void * dest, struct sorted_view * out)
+{
+    const uint64_t flip = desc->is_signed ? (1ULL << 63) : 0ULL;
+    uint32_t d, b;
+    memset(out, 0, sizeof(*out));
+    out->nw = 1;
+    out->stride = n;
+    out->sorted_recs = dest;
+    out->kv.base = (const char *) dest + desc->offset;
+    out->kv.item_stride = 16; out->kv.word_stride = 0; out->kv.flip = flip;
+    if (n == 0) return;
+    if (n > MPSK_MAX_ITEMS)
+        mps_fatal(c, __FILE__, __LINE__, "%zu local items exceed the supported maximum %zu per rank", n, (size_t) MPSK_MAX_ITEMS);
+
+    uint32_t * hist = (uint32_t *) mps_arena_get(c, MPS_S_HIST, 8 * 256 * sizeof(uint32_t) * 2);
+    uint32_t * bins = hist + 8 * 256;
+    void * scratch = mps_arena_get(c, MPS_S_SCRATCH, mpsk_onesweep_scratch_bytes(n));
+    CUDA_OK(c, cudaMemsetAsync(hist, 0, 8 * 256 * sizeof(uint32_t), c->stream));
+    KERN_T(c, MPS_K_EXTRACT, mpsk_extract_keys(dbase, n, 16, desc->offset, 8, 1, desc->is_signed, 0, NULL, hist, c->stream));
+    KERN_T(c, MPS_K_EXTRACT, mpsk_scan_histograms(hist, bins, 8, c->stream));
+    uint32_t * hhist = (uint32_t *) mps_host_stage(c, 8 * 256 * sizeof(uint32_t));
+    CUDA_OK(c, cudaMemcpyAsync(hhist, hist, 8 * 256 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    int digits[8], P = 0;
+    for (d = 0; d < 8; d++) {
+        int constant = 0;
+        for (b = 0; b < 256; b++) if (hhist[d * 256 + b] == (uint32_t) n) { constant = 1; break; }
+        if (!constant) digits[P++] = (int) d;
+    }
+    out->npasses = (uint32_t) P;
+    if (P == 0) {
+        if (dest != dbase) CUDA_OK(c, cudaMemcpyAsync(dest, dbase, n * 16, cudaMemcpyDeviceToDevice, c->stream));
+        return;
+    }
+    void * Y = mps_arena_get(c, MPS_S_KW, n * 16);
+    const void * src = dbase;
+    int i;
+    for (i = 0; i < P; i++) {
+        const int remaining_after = P - 1 - i;
+        void * tgt = (remaining_after % 2 == 0) ? dest : Y;
+        if (tgt == src) tgt = mps_arena_get(c, MPS_S_KB, n * 16);   /* first pass of an odd in-place chain */
+        KERN_T(c, MPS_K_ONESWEEP_REC, mpsk_onesweep_pass_rec16(src, tgt, n, 8 * digits[i], desc->offset == 8, flip,
+                                                              bins + (size_t) digits[i] * 256, scratch, c->stream));
+        src = tgt;
     }
 }
 
@@ -463,7 +528,25 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
     }
 
     /* ---- FirstSort */
-    local_sort(c, dbase, n, elsize, desc, p > 1, &v1);
+    void * sendbuf = NULL;
+    if (p == 1 && rec16_applicable(elsize, desc, dbase, dout)) {
+        /* one rank, record mode: the passes leave the sorted records in the output */
+        local_sort_rec16(c, dbase, n, desc, dout, &v1);
+        c->stats.first_sort_passes = v1.npasses;
+        c->stats.record_mode = 1;
+        c->sendcounts[0] = (int64_t) n;
+        timer_mark(c, "FirstSort");
+        timer_mark(c, "END");
+        free(info);
+        return;
+    }
+    if (p > 1) sendbuf = mps_arena_get(c, MPS_S_SEND, n * elsize);
+    if (p > 1 && rec16_applicable(elsize, desc, dbase, sendbuf)) {
+        local_sort_rec16(c, dbase, n, desc, sendbuf, &v1);
+        c->stats.record_mode = 1;
+    } else {
+        local_sort(c, dbase, n, elsize, desc, p > 1, &v1);
+    }
     c->stats.first_sort_passes = v1.npasses;
     c->stats.key_words = nw;
 
@@ -488,12 +571,14 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
     /* ---- PmaxPmin (mpsort-mpi.c:606-661): ends of the locally sorted keys */
     if (n > 0) {
         uint64_t * h = (uint64_t *) mps_host_stage(c, 2 * MPS_MAX_KEY_WORDS * sizeof(uint64_t));
+        const char * kb = (const char *) v1.kv.base;
         for (w = 0; w < (int) nw; w++) {
-            CUDA_OK(c, cudaMemcpyAsync(h + w, v1.skeys + (size_t) w * v1.stride, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
-            CUDA_OK(c, cudaMemcpyAsync(h + MPS_MAX_KEY_WORDS + w, v1.skeys + (size_t) w * v1.stride + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_OK(c, cudaMemcpyAsync(h + w, kb + (size_t) w * v1.kv.word_stride, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_OK(c, cudaMemcpyAsync(h + MPS_MAX_KEY_WORDS + w, kb + (n - 1) * v1.kv.item_stride + (size_t) w * v1.kv.word_stride,
+                                       sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
         }
         CUDA_OK(c, cudaStreamSynchronize(c->stream));
-        for (w = 0; w < (int) nw; w++) { mine.kmin[w] = h[w]; mine.kmax[w] = h[MPS_MAX_KEY_WORDS + w]; }
+        for (w = 0; w < (int) nw; w++) { mine.kmin[w] = h[w] ^ v1.kv.flip; mine.kmax[w] = h[MPS_MAX_KEY_WORDS + w] ^ v1.kv.flip; }
     }
     mpsort_comm_allgather_host(c, &mine, info, sizeof(mine));
     uint64_t kmin[MPS_MAX_RANKS * MPS_MAX_KEY_WORDS], kmax[MPS_MAX_RANKS * MPS_MAX_KEY_WORDS];
@@ -528,7 +613,7 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
     }
     int level, round = 0;
     for (level = level0; level < nlevels; level++) {
-        KERN_T(c, MPS_K_SPLITTER, mpsk_splitter_count(v1.skeys, v1.stride, n, nw, d_prefix, ns, level, d_counts, c->stream));
+        KERN_T(c, MPS_K_SPLITTER, mpsk_splitter_count(v1.kv, n, nw, d_prefix, ns, level, d_counts, c->stream));
         mps_comm_allreduce_u64_dev(c, d_counts, (size_t) ns * 256);
         KERN_T(c, MPS_K_SPLITTER, mpsk_splitter_select(d_counts, d_target, d_prefix, nw, ns, level, c->stream));
         round++;
@@ -539,7 +624,7 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
         }
     }
     c->stats.splitter_rounds = (uint32_t) round;
-    KERN_T(c, MPS_K_SPLITTER, mpsk_splitter_final(v1.skeys, v1.stride, n, nw, d_prefix, ns, d_final, c->stream));
+    KERN_T(c, MPS_K_SPLITTER, mpsk_splitter_final(v1.kv, n, nw, d_prefix, ns, d_final, c->stream));
     timer_mark(c, "findP");
 
     /* ---- LayDistr: all-gather the local rows (replaces the 8-byte Alltoalls :450-456) */
@@ -579,9 +664,9 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
     /* ---- Exchange: pack (payload gather into destination-contiguous order; the
      * destinations are contiguous slices of the sorted order, SendDispl[i] == myC[i]
      * :483-501) then grouped send/recv */
-    void * sendbuf = mps_arena_get(c, MPS_S_SEND, n * elsize);
     void * recvbuf = mps_arena_get(c, MPS_S_RECV, outn * elsize);
-    KERN_T(c, MPS_K_GATHER_RECORDS, mpsk_gather_records(dbase, v1.idx, sendbuf, n, elsize, c->stream));
+    if (v1.sorted_recs != sendbuf)
+        KERN_T(c, MPS_K_GATHER_RECORDS, mpsk_gather_records(dbase, v1.idx, sendbuf, n, elsize, c->stream));
     timer_mark(c, "Pack");
     const int dense = mpsort_mpi_has_options(MPSORT_DISABLE_SPARSE_ALLTOALLV)
                       && !mpsort_mpi_has_options(MPSORT_REQUIRE_SPARSE_ALLTOALLV);

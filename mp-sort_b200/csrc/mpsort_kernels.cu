@@ -159,7 +159,7 @@ extract_kernel(const unsigned char * __restrict__ base, size_t n, KeyDesc d,
             u64 k;
             if (FAST8) k = load_key_fast8(rec, d.offset, flip);
             else k = pack_key_word(rec, d);
-            kout[i] = k;
+            if (kout) kout[i] = k;
             hist8_add(sh, k, warp_full);
         }
     }
@@ -494,7 +494,9 @@ extern "C" size_t mpsk_onesweep_tile_items(void) { return TheSweep::TILE; }
 
 extern "C" size_t mpsk_onesweep_scratch_bytes(size_t n)
 {
-    const size_t ntiles = (n + TheSweep::TILE - 1) / TheSweep::TILE;
+    /* enough for the smallest tile of any pass flavour (record passes use 3072) */
+    const size_t tile = 2048;
+    const size_t ntiles = (n + tile - 1) / tile;
     return (ntiles * 256 + 64) * sizeof(u32);
 }
 
@@ -506,7 +508,7 @@ extern "C" int mpsk_onesweep_pass(const uint64_t * kin, const uint32_t * vin,
     if (n > MPSK_MAX_ITEMS) return (int) cudaErrorInvalidValue;
     cudaStream_t stream = (cudaStream_t) stream_;
     const size_t ntiles = (n + TheSweep::TILE - 1) / TheSweep::TILE;
-    cudaError_t e = cudaMemsetAsync(scratch, 0, mpsk_onesweep_scratch_bytes(n), stream);
+    cudaError_t e = cudaMemsetAsync(scratch, 0, (ntiles * 256 + 64) * sizeof(u32), stream);
     if (e != cudaSuccess) return (int) e;
     u32 * ticket = (u32 *) scratch;
     u32 * lookback = ticket + 64;
@@ -524,6 +526,210 @@ extern "C" int mpsk_onesweep_pass(const uint64_t * kin, const uint32_t * vin,
         kern<<<(unsigned) ntiles, MPSK_SWEEP_THREADS, TheSweep::SMEM, stream>>>(
             (const u64 *) kin, vin, (u64 *) kout, vout, (u32) n, (u32) shift, bins, lookback, ticket);
     }
+    CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* onesweep pass over whole 16-byte records {u64 key, u64 payload} (either order) */
+/*
+ * When a record is nothing but its 8-byte key and 8 more bytes, carrying the record
+ * through the passes (32 B of HBM traffic per record and pass) is cheaper than
+ * sorting (key, index) pairs (24 B) and gathering afterwards: a random 16-byte read
+ * costs a whole 128-byte DRAM line on B200 (profiles/r01_gather_probe.log), i.e. the
+ * gather alone moves 148 B per record. Same algorithm as onesweep_kernel; the key is
+ * read in place (low or high half, sign flip applied on the fly), items move as uint4.
+ */
+#ifndef MPSK_REC_THREADS
+#define MPSK_REC_THREADS 384
+#endif
+#ifndef MPSK_REC_IPT
+#define MPSK_REC_IPT 8
+#endif
+#ifndef MPSK_REC_MINBLOCKS
+#define MPSK_REC_MINBLOCKS 3
+#endif
+
+template <int THREADS, int IPT>
+struct RecCfg {
+    static constexpr int TILE = THREADS * IPT;
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int SMEM = TILE * 16 + WARPS * 256 * 4 + 256 * 4 * 2 + 64;
+};
+
+__device__ __forceinline__ u32 rec_digit(const uint4 & it, u32 khi, u64 flip, u32 shift)
+{
+    const u64 k = (khi ? (((u64) it.w << 32) | it.z) : (((u64) it.y << 32) | it.x)) ^ flip;
+    return (u32) (k >> shift) & 255u;
+}
+
+template <int THREADS, int IPT>
+__global__ void __launch_bounds__(THREADS, MPSK_REC_MINBLOCKS)
+onesweep_rec16_kernel(const uint4 * __restrict__ in, uint4 * __restrict__ out,
+                      u32 n, u32 shift, u32 khi, u64 flip, const u32 * __restrict__ bins,
+                      u32 * lookback, u32 * ticket)
+{
+    typedef RecCfg<THREADS, IPT> Cfg;
+    constexpr int TILE = Cfg::TILE;
+    constexpr int WARPS = Cfg::WARPS;
+    static_assert(THREADS >= 256, "one thread per digit needs >= 256 threads");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4 * s_items = (uint4 *) smem_raw;
+    u32 * s_whist = (u32 *) (smem_raw + TILE * 16);     /* [WARPS][256] */
+    u32 * s_local = s_whist + WARPS * 256;
+    u32 * s_gofs = s_local + 256;
+    u32 * s_misc = s_gofs + 256;
+
+    const u32 tid = threadIdx.x;
+    const u32 lane = tid & 31u;
+    const u32 warp = tid >> 5;
+
+    if (tid == 0) s_misc[0] = atomicAdd(ticket, 1u);
+    for (u32 i = tid; i < WARPS * 256; i += THREADS) s_whist[i] = 0;
+    __syncthreads();
+
+    const u32 tile = s_misc[0];
+    const u32 tile_base = tile * (u32) TILE;
+    const u32 remaining = n - tile_base;
+    const u32 valid = remaining < (u32) TILE ? remaining : (u32) TILE;
+    const u32 wbase = tile_base + warp * (IPT * 32) + lane;
+
+    /* ---- load records, warp-striped: each load instruction covers 512 contiguous bytes */
+    uint4 it[IPT];
+    if (valid == (u32) TILE) {
+#pragma unroll
+        for (int j = 0; j < IPT; j++) it[j] = in[wbase + j * 32];
+    } else {
+        /* padding must rank last in bin 255: (key ^ flip) == ~0 */
+        const u64 padk = ~flip;
+        const uint4 pad = make_uint4((u32) padk, (u32) (padk >> 32), (u32) padk, (u32) (padk >> 32));
+#pragma unroll
+        for (int j = 0; j < IPT; j++) {
+            const u32 pos = wbase + j * 32;
+            it[j] = pos < n ? in[pos] : pad;
+        }
+    }
+
+    /* ---- rank inside (warp, digit) */
+    u32 rank[IPT];
+    u32 * my_hist = s_whist + warp * 256;
+    const u32 lt = lanemask_lt();
+#pragma unroll
+    for (int j = 0; j < IPT; j++) {
+        const u32 digit = rec_digit(it[j], khi, flip, shift);
+        const u32 peers = match_digit(digit);
+        const u32 leader = __ffs(peers) - 1;
+        u32 c = 0;
+        if (lane == leader) {
+            c = my_hist[digit];
+            my_hist[digit] = c + __popc(peers);
+        }
+        c = __shfl_sync(FULL_MASK, c, leader);
+        rank[j] = c + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    /* ---- per digit: exclusive scan over warps, publish the tile count */
+    u32 cnt_full = 0, cnt_valid = 0;
+    if (tid < 256) {
+        u32 c[WARPS];
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) c[w] = s_whist[w * 256 + tid];
+        u32 run = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) {
+            s_whist[w * 256 + tid] = run;
+            run += c[w];
+        }
+        cnt_full = run;
+        cnt_valid = run;
+        if (tid == 255) cnt_valid -= ((u32) TILE - valid);
+        st_relaxed_u32(&lookback[(size_t) tile * 256 + tid],
+                       (tile == 0 ? LB_INCL : LB_PART) | cnt_valid);
+        u32 incl = cnt_full;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 y = __shfl_up_sync(FULL_MASK, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) s_misc[1 + warp] = incl;
+        cnt_full = incl - cnt_full;
+    }
+    __syncthreads();
+    if (tid < 256) {
+        u32 add = 0;
+        for (u32 w = 0; w < warp; w++) add += s_misc[1 + w];
+        const u32 local = cnt_full + add;
+        s_local[tid] = local;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) s_whist[w * 256 + tid] += local;
+    }
+    __syncthreads();
+
+    /* ---- scatter records into tile-sorted order in shared memory */
+#pragma unroll
+    for (int j = 0; j < IPT; j++) {
+        const u32 digit = rec_digit(it[j], khi, flip, shift);
+        s_items[rank[j] + my_hist[digit]] = it[j];
+    }
+
+    /* ---- decoupled look-back (see onesweep_kernel) */
+    if (tid < 256) {
+        u32 excl = 0;
+        if (tile > 0) {
+            int t = (int) tile - 1;
+            bool done = false;
+            while (!done) {
+                u32 s[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    s[k] = (t - k >= 0) ? ld_relaxed_u32(&lookback[(size_t) (t - k) * 256 + tid]) : LB_INCL;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (done) break;
+                    if (s[k] & LB_INCL) { excl += s[k] & LB_MASK; done = true; }
+                    else if (s[k] & LB_PART) { excl += s[k] & LB_MASK; t--; }
+                    else break;
+                }
+            }
+            st_relaxed_u32(&lookback[(size_t) tile * 256 + tid], LB_INCL | (excl + cnt_valid));
+        }
+        s_gofs[tid] = bins[tid] + excl - s_local[tid];
+    }
+    __syncthreads();
+
+    /* ---- coalesced stores of the digit runs */
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+        const u32 s = tid + k * THREADS;
+        if (s < valid) {
+            const uint4 v = s_items[s];
+            out[s_gofs[rec_digit(v, khi, flip, shift)] + s] = v;
+        }
+    }
+}
+
+typedef RecCfg<MPSK_REC_THREADS, MPSK_REC_IPT> TheRec;
+
+extern "C" int mpsk_onesweep_pass_rec16(const void * in, void * out, size_t n, int shift,
+        int key_in_high, uint64_t flip, const uint32_t * bins, void * scratch, mpsk_stream_t stream_)
+{
+    if (n == 0) return 0;
+    if (n > MPSK_MAX_ITEMS) return (int) cudaErrorInvalidValue;
+    cudaStream_t stream = (cudaStream_t) stream_;
+    const size_t ntiles = (n + TheRec::TILE - 1) / TheRec::TILE;
+    cudaError_t e = cudaMemsetAsync(scratch, 0, (ntiles * 256 + 64) * sizeof(u32), stream);
+    if (e != cudaSuccess) return (int) e;
+    u32 * ticket = (u32 *) scratch;
+    u32 * lookback = ticket + 64;
+    auto kern = onesweep_rec16_kernel<MPSK_REC_THREADS, MPSK_REC_IPT>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TheRec::SMEM);
+    if (e != cudaSuccess) return (int) e;
+    kern<<<(unsigned) ntiles, MPSK_REC_THREADS, TheRec::SMEM, stream>>>(
+        (const uint4 *) in, (uint4 *) out, (u32) n, (u32) shift, key_in_high ? 1u : 0u, (u64) flip,
+        bins, lookback, ticket);
     CUDA_LAUNCH_CHECK();
     return 0;
 }
@@ -642,12 +848,12 @@ extern "C" int mpsk_gather_records(const void * base, const uint32_t * idx, void
 
 #define MPSK_MAX_KEY_WORDS 16
 
-/* compare key i of the SoA sorted key words with cand[]: -1, 0, +1 */
-__device__ __forceinline__ int cmp_key(const u64 * __restrict__ skeys, size_t stride, size_t i,
-                                       const u64 * cand, u32 nw)
+/* compare key i of the sorted keys (seen through a key view) with cand[]: -1, 0, +1 */
+__device__ __forceinline__ int cmp_key(const mpsk_keyview & v, size_t i, const u64 * cand, u32 nw)
 {
+    const unsigned char * p = (const unsigned char *) v.base + i * v.item_stride;
     for (int w = (int) nw - 1; w >= 0; w--) {
-        const u64 k = skeys[(size_t) w * stride + i];
+        const u64 k = (*(const u64 *) (p + (size_t) w * v.word_stride)) ^ v.flip;
         if (k < cand[w]) return -1;
         if (k > cand[w]) return 1;
     }
@@ -656,13 +862,12 @@ __device__ __forceinline__ int cmp_key(const u64 * __restrict__ skeys, size_t st
 
 /* number of keys <= cand (UPPER) or < cand (!UPPER) */
 template <bool UPPER>
-__device__ __forceinline__ u64 bound_key(const u64 * __restrict__ skeys, size_t stride, size_t n,
-                                         const u64 * cand, u32 nw)
+__device__ __forceinline__ u64 bound_key(const mpsk_keyview & v, size_t n, const u64 * cand, u32 nw)
 {
     size_t lo = 0, hi = n;
     while (lo < hi) {
         const size_t mid = lo + ((hi - lo) >> 1);
-        const int c = cmp_key(skeys, stride, mid, cand, nw);
+        const int c = cmp_key(v, mid, cand, nw);
         const bool go_right = UPPER ? (c <= 0) : (c < 0);
         if (go_right) lo = mid + 1; else hi = mid;
     }
@@ -670,7 +875,7 @@ __device__ __forceinline__ u64 bound_key(const u64 * __restrict__ skeys, size_t 
 }
 
 __global__ void __launch_bounds__(256)
-splitter_count_kernel(const u64 * __restrict__ skeys, size_t stride, size_t n, u32 nw,
+splitter_count_kernel(mpsk_keyview v, size_t n, u32 nw,
                       const u64 * __restrict__ prefix, int level, u64 * __restrict__ counts)
 {
     const u32 b = blockIdx.x;
@@ -680,21 +885,21 @@ splitter_count_kernel(const u64 * __restrict__ skeys, size_t stride, size_t n, u
     const u32 sh = (byteidx & 7) * 8;
     u64 cand[MPSK_MAX_KEY_WORDS];
     for (u32 w = 0; w < nw; w++) {
-        u64 v = prefix[(size_t) b * nw + w];
-        if (w < wi) v = ~0ULL;
-        else if (w == wi) v |= ((u64) d << sh) | ((sh == 0) ? 0ULL : ((1ULL << sh) - 1ULL));
-        cand[w] = v;
+        u64 x = prefix[(size_t) b * nw + w];
+        if (w < wi) x = ~0ULL;
+        else if (w == wi) x |= ((u64) d << sh) | ((sh == 0) ? 0ULL : ((1ULL << sh) - 1ULL));
+        cand[w] = x;
     }
-    counts[(size_t) b * 256 + d] = bound_key<true>(skeys, stride, n, cand, nw);
+    counts[(size_t) b * 256 + d] = bound_key<true>(v, n, cand, nw);
 }
 
-extern "C" int mpsk_splitter_count(const uint64_t * skeys, size_t stride, size_t n, uint32_t nw,
+extern "C" int mpsk_splitter_count(struct mpsk_keyview view, size_t n, uint32_t nw,
         const uint64_t * prefix, int nsplit, int level, uint64_t * counts, mpsk_stream_t stream)
 {
     if (nsplit <= 0) return 0;
     if (nw > MPSK_MAX_KEY_WORDS) return (int) cudaErrorInvalidValue;
     splitter_count_kernel<<<nsplit, 256, 0, (cudaStream_t) stream>>>(
-        (const u64 *) skeys, stride, n, nw, (const u64 *) prefix, level, (u64 *) counts);
+        view, n, nw, (const u64 *) prefix, level, (u64 *) counts);
     CUDA_LAUNCH_CHECK();
     return 0;
 }
@@ -729,7 +934,7 @@ extern "C" int mpsk_splitter_select(const uint64_t * counts, const uint64_t * ta
     return 0;
 }
 
-__global__ void splitter_final_kernel(const u64 * __restrict__ skeys, size_t stride, size_t n, u32 nw,
+__global__ void splitter_final_kernel(mpsk_keyview v, size_t n, u32 nw,
                                       const u64 * __restrict__ prefix, int nsplit, u64 * __restrict__ out)
 {
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -738,11 +943,10 @@ __global__ void splitter_final_kernel(const u64 * __restrict__ skeys, size_t str
     const bool upper = t >= (u32) nsplit;
     u64 cand[MPSK_MAX_KEY_WORDS];
     for (u32 w = 0; w < nw; w++) cand[w] = prefix[(size_t) b * nw + w];
-    out[t] = upper ? bound_key<true>(skeys, stride, n, cand, nw)
-                   : bound_key<false>(skeys, stride, n, cand, nw);
+    out[t] = upper ? bound_key<true>(v, n, cand, nw) : bound_key<false>(v, n, cand, nw);
 }
 
-extern "C" int mpsk_splitter_final(const uint64_t * skeys, size_t stride, size_t n, uint32_t nw,
+extern "C" int mpsk_splitter_final(struct mpsk_keyview view, size_t n, uint32_t nw,
         const uint64_t * prefix, int nsplit, uint64_t * out, mpsk_stream_t stream)
 {
     if (nsplit <= 0) return 0;
@@ -750,7 +954,7 @@ extern "C" int mpsk_splitter_final(const uint64_t * skeys, size_t stride, size_t
     const int threads = 64;
     const int blocks = (2 * nsplit + threads - 1) / threads;
     splitter_final_kernel<<<blocks, threads, 0, (cudaStream_t) stream>>>(
-        (const u64 *) skeys, stride, n, nw, (const u64 *) prefix, nsplit, (u64 *) out);
+        view, n, nw, (const u64 *) prefix, nsplit, (u64 *) out);
     CUDA_LAUNCH_CHECK();
     return 0;
 }

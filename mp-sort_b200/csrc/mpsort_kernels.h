@@ -25,6 +25,7 @@ typedef void * mpsk_stream_t; /* cudaStream_t */
  * Packs key bytes [8*g, 8*g+8) of every record (little-endian over the nwords*width
  * key bytes, signed words sign-flipped) into kout[i] and accumulates the eight
  * 8-bit digit histograms of that word into hist[8][256] (must be zeroed by caller).
+ * kout may be NULL (histogram only).
  */
 int mpsk_extract_keys(const void * base, size_t n, size_t elsize,
         size_t offset, uint32_t width, uint32_t nwords, int is_signed,
@@ -49,6 +50,12 @@ int mpsk_onesweep_pass(const uint64_t * kin, const uint32_t * vin,
         uint64_t * kout, uint32_t * vout, size_t n, int shift,
         const uint32_t * bins, void * scratch, mpsk_stream_t stream);
 
+/* The same pass over whole 16-byte records {u64 key, u64 other} (key in the low or
+ * the high half; `flip` is XORed onto the key before the digit is taken, i.e. the
+ * sign bit for signed keys). in/out 16-byte aligned. */
+int mpsk_onesweep_pass_rec16(const void * in, void * out, size_t n, int shift,
+        int key_in_high, uint64_t flip, const uint32_t * bins, void * scratch, mpsk_stream_t stream);
+
 /* dst[i] = src[idx[i]] for 64-bit words (key words of multi-word keys). If hist is
  * non-NULL nothing is accumulated (histograms are permutation invariant). */
 int mpsk_gather_u64(const uint64_t * src, const uint32_t * idx, uint64_t * dst,
@@ -59,8 +66,12 @@ int mpsk_gather_u64(const uint64_t * src, const uint32_t * idx, uint64_t * dst,
 int mpsk_gather_records(const void * base, const uint32_t * idx, void * out,
         size_t n, size_t elsize, mpsk_stream_t stream);
 
-/* K4: splitter counting on the sorted key words skeys[w][n] (word w at
- * skeys + w*stride). Replaces _histogram/_bsearch_last_lt/le
+/* How the splitter kernels see the locally sorted keys: word w of key i is the u64
+ * at base + i*item_stride + w*word_stride, XOR flip. SoA key arrays of the index
+ * sort: {skeys, 8, n*8, 0}; sorted 16-byte records: {recs + offset, 16, 0, signbit}. */
+struct mpsk_keyview { const void * base; size_t item_stride; size_t word_stride; uint64_t flip; };
+
+/* K4: splitter counting on the sorted keys. Replaces _histogram/_bsearch_last_lt/le
  * (internal-parallel.h:8-126).
  *
  * Byte-wise descent state: prefix[b][nw] (u64 words, device) holds the bytes of
@@ -68,7 +79,7 @@ int mpsk_gather_records(const void * base, const uint32_t * idx, void * out,
  * most significant one (0 .. 8*nw-1). For every splitter b and digit d the kernel
  * writes counts[b*256+d] = #local keys <= (prefix_b | d at this byte | 0xff below).
  */
-int mpsk_splitter_count(const uint64_t * skeys, size_t stride, size_t n, uint32_t nw,
+int mpsk_splitter_count(struct mpsk_keyview view, size_t n, uint32_t nw,
         const uint64_t * prefix, int nsplit, int level,
         uint64_t * counts, mpsk_stream_t stream);
 
@@ -79,7 +90,7 @@ int mpsk_splitter_select(const uint64_t * counts, const uint64_t * target,
 
 /* Final local counts for decided splitters: clt[b] = #keys < P_b, cle[b] = #keys <= P_b
  * written to out[0..nsplit) and out[nsplit..2*nsplit). */
-int mpsk_splitter_final(const uint64_t * skeys, size_t stride, size_t n, uint32_t nw,
+int mpsk_splitter_final(struct mpsk_keyview view, size_t n, uint32_t nw,
         const uint64_t * prefix, int nsplit, uint64_t * out, mpsk_stream_t stream);
 
 /* dst[i] += src_k[i] over nsrc sources (u64), for the in-process transport. */
