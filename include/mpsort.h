@@ -182,6 +182,8 @@ struct mpsort_last_stats {
     uint64_t bytes_sent_remote;  /* record bytes that left this GPU             */
     uint32_t second_sort_merge_tiles; /* > 0: SecondSort ran as a p-way merge of this many tiles */
     uint32_t record_mode;        /* 1: 16-byte records were carried through the passes themselves */
+    uint32_t hybrid;             /* 1: four high-digit passes + run fix-up instead of all passes */
+    uint32_t hybrid_long_runs;   /* runs of > 256 equal high parts that were sorted separately */
 };
 void mpsort_comm_last_stats(mpsort_comm_t comm, struct mpsort_last_stats * st,
                             int64_t * sendcounts, int max);

@@ -280,6 +280,58 @@ static int rec16_applicable(size_t elsize, const struct mpsort_radix_desc * d, c
            && ((((uintptr_t) dbase) | ((uintptr_t) dest)) & 15) == 0;
 }
 
+/* P stable passes over the given digits, source `src` (read only unless it is also
+ * the destination), result in `dest`; `Y` and the KB slot are the ping-pong temps */
+static void rec16_passes(struct mpsort_comm * c, const void * src, size_t n, const struct mpsort_radix_desc * desc,
+        void * dest, const int * digits, int P, const uint32_t * bins, void * scratch)
+{
+    const uint64_t flip = desc->is_signed ? (1ULL << 63) : 0ULL;
+    void * Y = mps_arena_get(c, MPS_S_KW, n * 16);
+    int i;
+    for (i = 0; i < P; i++) {
+        const int remaining_after = P - 1 - i;
+        void * tgt = (remaining_after % 2 == 0) ? dest : Y;
+        if (tgt == src) tgt = mps_arena_get(c, MPS_S_KB, n * 16);   /* first pass of an odd in-place chain */
+        KERN_T(c, MPS_K_ONESWEEP_REC, mpsk_onesweep_pass_rec16(src, tgt, n, 8 * digits[i], desc->offset == 8, flip,
+                                                              bins + (size_t) digits[i] * 256, scratch, c->stream));
+        src = tgt;
+    }
+}
+
+#define MPS_HYBRID_MIN_ITEMS ((size_t) 1 << 22)
+#define MPS_HYBRID_SAMPLES 65536u
+#define MPS_HYBRID_MAX_LONG_RUNS 64u
+
+static void local_sort(struct mpsort_comm * c, const void * dbase, size_t n, size_t elsize,
+        const struct mpsort_radix_desc * desc, int want_keys, struct sorted_view * out);
+
+/* Does the high part (key >> lobits) look nearly distinct? Sorts 65536 evenly spaced
+ * high parts and counts equal pairs c: E[c] = s^2/(2n) * (mean length of the run a
+ * random record sits in). The run fix-up costs that many comparisons per record, so
+ * the hybrid is taken while the estimate stays below 16. */
+static int hybrid_predictor(struct mpsort_comm * c, const void * dbase, size_t n,
+        const struct mpsort_radix_desc * desc, uint32_t lobits)
+{
+    const uint64_t flip = desc->is_signed ? (1ULL << 63) : 0ULL;
+    const uint32_t s = MPS_HYBRID_SAMPLES;
+    uint64_t * samp = (uint64_t *) mps_arena_get(c, MPS_S_MERGE_SAMP, (size_t) s * sizeof(uint64_t));
+    uint64_t * dcount = (uint64_t *) mps_arena_get(c, MPS_S_MISC, 256);
+    const int saved = c->kt.force_cls;
+    c->kt.force_cls = MPS_K_HYBRID;
+    KERN_T(c, MPS_K_HYBRID, mpsk_sample_prefix_rec16(dbase, n, s, desc->offset == 8, flip, lobits, samp, c->stream));
+    struct sorted_view sv;
+    const struct mpsort_radix_desc sdesc = { 0, 8, 1, 0, 0 };
+    local_sort(c, samp, s, sizeof(uint64_t), &sdesc, 1, &sv);
+    CUDA_OK(c, cudaMemsetAsync(dcount, 0, sizeof(uint64_t), c->stream));
+    KERN_T(c, MPS_K_HYBRID, mpsk_count_equal_pairs(sv.skeys, s, dcount, c->stream));
+    c->kt.force_cls = saved;
+    uint64_t * h = (uint64_t *) mps_host_stage(c, sizeof(uint64_t));
+    CUDA_OK(c, cudaMemcpyAsync(h, dcount, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    const double limit = 8.0 * (double) s * (double) s / (double) n;
+    return (double) *h <= (limit < 8.0 ? 8.0 : limit);
+}
+
 static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t n,
         const struct mpsort_radix_desc * desc, void * dest, struct sorted_view * out)
 {
@@ -315,17 +367,58 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
         if (dest != dbase) CUDA_OK(c, cudaMemcpyAsync(dest, dbase, n * 16, cudaMemcpyDeviceToDevice, c->stream));
         return;
     }
-    void * Y = mps_arena_get(c, MPS_S_KW, n * 16);
-    const void * src = dbase;
-    int i;
-    for (i = 0; i < P; i++) {
-        const int remaining_after = P - 1 - i;
-        void * tgt = (remaining_after % 2 == 0) ? dest : Y;
-        if (tgt == src) tgt = mps_arena_get(c, MPS_S_KB, n * 16);   /* first pass of an odd in-place chain */
-        KERN_T(c, MPS_K_ONESWEEP_REC, mpsk_onesweep_pass_rec16(src, tgt, n, 8 * digits[i], desc->offset == 8, flip,
-                                                              bins + (size_t) digits[i] * 256, scratch, c->stream));
-        src = tgt;
+
+    /* ---- hybrid: four passes over the most significant digits + run fix-up */
+    if (P >= 6 && n >= MPS_HYBRID_MIN_ITEMS && !getenv("MPSORT_NO_HYBRID")) {
+        const uint32_t lobits = 8u * (uint32_t) digits[P - 4];
+        uint32_t hsave[8 * 256];
+        memcpy(hsave, hhist, sizeof(hsave));
+        const int yes = hybrid_predictor(c, dbase, n, desc, lobits);
+        {
+            /* the predictor's sample sort reused the histogram slot and the host stage:
+             * put the big array's histograms and scanned bins back */
+            uint32_t * hs = (uint32_t *) mps_host_stage(c, sizeof(hsave));
+            memcpy(hs, hsave, sizeof(hsave));
+            CUDA_OK(c, cudaMemcpyAsync(hist, hs, sizeof(hsave), cudaMemcpyHostToDevice, c->stream));
+            KERN_T(c, MPS_K_EXTRACT, mpsk_scan_histograms(hist, bins, 8, c->stream));
+            CUDA_OK(c, cudaStreamSynchronize(c->stream));   /* the stage is reused below */
+        }
+        if (yes) {
+            rec16_passes(c, dbase, n, desc, dest, digits + (P - 4), 4, bins, scratch);
+            uint32_t * wl = (uint32_t *) mps_arena_get(c, MPS_S_MERGE_CUT, (2 * MPS_HYBRID_MAX_LONG_RUNS + 64) * sizeof(uint32_t));
+            uint32_t * nwork = wl + 2 * MPS_HYBRID_MAX_LONG_RUNS;
+            CUDA_OK(c, cudaMemsetAsync(nwork, 0, sizeof(uint32_t), c->stream));
+            KERN_T(c, MPS_K_HYBRID, mpsk_fixup_rec16(dest, n, desc->offset == 8, flip, lobits, wl, nwork, MPS_HYBRID_MAX_LONG_RUNS, c->stream));
+            uint32_t * h = (uint32_t *) mps_host_stage(c, (2 * MPS_HYBRID_MAX_LONG_RUNS + 1) * sizeof(uint32_t));
+            CUDA_OK(c, cudaMemcpyAsync(h, nwork, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_OK(c, cudaStreamSynchronize(c->stream));
+            const uint32_t nlong = h[0];
+            out->npasses = 4;
+            c->stats.hybrid = 1;
+            c->stats.hybrid_long_runs = nlong;
+            if (nlong > MPS_HYBRID_MAX_LONG_RUNS) {
+                /* the predictor was wrong: finish with a full stable LSD of what we have
+                 * (a permutation of the input in which equal keys kept their order) */
+                rec16_passes(c, dest, n, desc, dest, digits, P, bins, scratch);
+                out->npasses = 4 + (uint32_t) P;
+            } else if (nlong > 0) {
+                uint32_t starts[MPS_HYBRID_MAX_LONG_RUNS], lens[MPS_HYBRID_MAX_LONG_RUNS], e;
+                KERN_T(c, MPS_K_HYBRID, mpsk_fixup_extents(dest, n, desc->offset == 8, flip, lobits, wl, nlong, wl + MPS_HYBRID_MAX_LONG_RUNS, c->stream));
+                CUDA_OK(c, cudaMemcpyAsync(h, wl, 2 * MPS_HYBRID_MAX_LONG_RUNS * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+                CUDA_OK(c, cudaStreamSynchronize(c->stream));
+                for (e = 0; e < nlong; e++) { starts[e] = h[e]; lens[e] = h[MPS_HYBRID_MAX_LONG_RUNS + e]; }
+                for (e = 0; e < nlong; e++) {
+                    /* a long run is a contiguous array whose high digits are constant: an
+                     * ordinary in-place record sort of it runs the low passes only */
+                    struct sorted_view sub;
+                    char * p0 = (char *) dest + (size_t) starts[e] * 16;
+                    local_sort_rec16(c, p0, lens[e], desc, p0, &sub);
+                }
+            }
+            return;
+        }
     }
+    rec16_passes(c, dbase, n, desc, dest, digits, P, bins, scratch);
 }
 
 /* ------------------------------------------------------------------------- */

@@ -65,7 +65,7 @@ struct mps_timers {
 /* per-kernel-class timing (bench.py's roofline numbers): CUDA events around every
  * launch of a class on the communicator's stream, summed after the stream sync */
 enum mps_kclass { MPS_K_EXTRACT = 0, MPS_K_ONESWEEP, MPS_K_ONESWEEP_REC, MPS_K_GATHER_KEYS, MPS_K_GATHER_RECORDS,
-                  MPS_K_SPLITTER, MPS_K_CHECKSUM, MPS_K_EXCHANGE, MPS_K_MERGE, MPS_NKCLASS };
+                  MPS_K_SPLITTER, MPS_K_CHECKSUM, MPS_K_EXCHANGE, MPS_K_MERGE, MPS_K_HYBRID, MPS_NKCLASS };
 #define MPS_KT_MAX 512
 struct mps_ktimes {
     int on;

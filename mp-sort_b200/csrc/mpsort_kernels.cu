@@ -734,6 +734,183 @@ extern "C" int mpsk_onesweep_pass_rec16(const void * in, void * out, size_t n, i
     return 0;
 }
 
+/* ------------------------------------------------------------------------- */
+/* hybrid sort: LSD over the four most significant non-constant digits, then the   */
+/* runs of equal high part are ordered by their low part in place                  */
+/*
+ * For keys whose high 32 significant bits are (nearly) distinct -- random 64-bit ids,
+ * hashes -- four passes already put almost every record in its final place: what is
+ * left are short runs of records that agree in the high part. Inside a run records
+ * are still in input order (the passes are stable), so ordering a run stably by the
+ * low part gives exactly the order of the full eight-pass sort.
+ *
+ * fixup_rec16_kernel: one CTA per tile of FIX_T records (+ FIX_HALO look-ahead).
+ * A run belongs to the tile that holds its head. Runs of 2..FIX_HALO records are
+ * ranked by counting (O(L^2), L is tiny) and rewritten in place; longer runs are
+ * appended to a work list and sorted by the host with ordinary passes.
+ * Safe in place: a CTA rewrites only runs it owns, and what other CTAs read of those
+ * records (the high part, for head detection) does not change when a run is permuted.
+ */
+#define FIX_T 2048
+#define FIX_HALO 256
+#define FIX_THREADS 256
+
+__device__ __forceinline__ u64 rec_key(const uint4 & it, u32 khi, u64 flip)
+{
+    return (khi ? (((u64) it.w << 32) | it.z) : (((u64) it.y << 32) | it.x)) ^ flip;
+}
+
+__global__ void __launch_bounds__(FIX_THREADS)
+fixup_rec16_kernel(uint4 * __restrict__ recs, u32 n, u32 khi, u64 flip, u32 lobits,
+                   u32 * __restrict__ worklist, u32 * __restrict__ nwork, u32 cap)
+{
+    constexpr int CAP = FIX_T + FIX_HALO;
+    constexpr int WORDS = (CAP + 31) / 32 + 1;
+    __shared__ uint4 s_rec[CAP];
+    __shared__ u32 s_head[WORDS];
+    __shared__ u32 s_target[CAP];
+
+    const u32 tid = threadIdx.x;
+    const size_t t0 = (size_t) blockIdx.x * FIX_T;
+    const u32 avail = (u32) ((size_t) n - t0);
+    const u32 cnt = avail < (u32) CAP ? avail : (u32) CAP;
+    const bool at_end = (t0 + cnt == n);
+    const u64 lomask = lobits >= 64 ? ~0ULL : ((1ULL << lobits) - 1ULL);
+
+    for (u32 i = tid; i < cnt; i += FIX_THREADS) s_rec[i] = recs[t0 + i];
+    __syncthreads();
+    /* head flags: the high part differs from the predecessor's. A warp handles 32
+     * consecutive positions per round, so one ballot is one word of the bit map. */
+    for (u32 i = tid; i < (u32) WORDS * 32; i += FIX_THREADS) {
+        bool head = false;
+        if (i == cnt) head = at_end;                      /* sentinel: the data ends here */
+        else if (i < cnt) {
+            if (i == 0) head = (t0 == 0) || ((rec_key(recs[t0 - 1], khi, flip) >> lobits) != (rec_key(s_rec[0], khi, flip) >> lobits));
+            else head = (rec_key(s_rec[i - 1], khi, flip) >> lobits) != (rec_key(s_rec[i], khi, flip) >> lobits);
+        }
+        const u32 word = __ballot_sync(FULL_MASK, head);
+        if ((tid & 31) == 0) s_head[i >> 5] = word;
+    }
+    __syncthreads();
+    for (u32 i = tid; i < cnt; i += FIX_THREADS) {
+        s_target[i] = 0xffffffffu;
+        /* run start: last head at or before i */
+        int w = (int) (i >> 5);
+        u32 bits = s_head[w] & (0xffffffffu >> (31 - (i & 31)));
+        while (bits == 0 && w > 0) { w--; bits = s_head[w]; }
+        if (bits == 0) continue;                          /* continuation of a run owned by an earlier tile */
+        const u32 rs = (u32) w * 32 + (31 - __clz(bits));
+        if (rs >= (u32) FIX_T) continue;                  /* head lies in the look-ahead: the next tile owns it */
+        /* run end: first head after i (the sentinel counts) */
+        u32 w2 = (i + 1) >> 5;
+        u32 b2 = s_head[w2] & (0xffffffffu << ((i + 1) & 31));
+        while (b2 == 0 && w2 + 1 < (u32) WORDS && (w2 + 1) * 32 <= cnt + 31) { w2++; b2 = s_head[w2]; }
+        const u32 re = b2 ? (w2 * 32 + (__ffs(b2) - 1)) : 0xffffffffu;
+        if (re == 0xffffffffu || re > cnt || re - rs > (u32) FIX_HALO) {
+            /* too long for this kernel: the run head reports it */
+            if (i == rs) {
+                const u32 slot = atomicAdd(nwork, 1u);
+                if (slot < cap) worklist[slot] = (u32) (t0 + rs);
+            }
+            continue;
+        }
+        if (re - rs < 2) continue;
+        const u64 mine = rec_key(s_rec[i], khi, flip) & lomask;
+        u32 rank = 0;
+        for (u32 j = rs; j < re; j++) {
+            const u64 other = rec_key(s_rec[j], khi, flip) & lomask;
+            rank += (other < mine) || (other == mine && j < i);
+        }
+        s_target[i] = rs + rank;
+    }
+    __syncthreads();
+    for (u32 i = tid; i < cnt; i += FIX_THREADS) {
+        const u32 tgt = s_target[i];
+        if (tgt != 0xffffffffu && tgt != i) recs[t0 + tgt] = s_rec[i];
+    }
+}
+
+/* extent of every long run on the work list: first index whose high part differs */
+__global__ void fixup_extent_kernel(const uint4 * __restrict__ recs, u32 n, u32 khi, u64 flip, u32 lobits,
+                                    const u32 * __restrict__ worklist, u32 nwork, u32 * __restrict__ lengths)
+{
+    const u32 e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nwork) return;
+    const u32 start = worklist[e];
+    const u64 hi = rec_key(recs[start], khi, flip) >> lobits;
+    u32 lo = start + 1, hiidx = n;                       /* keys are sorted by the high part */
+    while (lo < hiidx) {
+        const u32 mid = lo + ((hiidx - lo) >> 1);
+        if ((rec_key(recs[mid], khi, flip) >> lobits) <= hi) lo = mid + 1; else hiidx = mid;
+    }
+    lengths[e] = lo - start;
+}
+
+extern "C" int mpsk_fixup_rec16(void * recs, size_t n, int key_in_high, uint64_t flip, uint32_t lobits,
+        uint32_t * worklist, uint32_t * nwork, uint32_t cap, mpsk_stream_t stream)
+{
+    if (n == 0) return 0;
+    const size_t tiles = (n + FIX_T - 1) / FIX_T;
+    fixup_rec16_kernel<<<(unsigned) tiles, FIX_THREADS, 0, (cudaStream_t) stream>>>(
+        (uint4 *) recs, (u32) n, key_in_high ? 1u : 0u, (u64) flip, lobits, worklist, nwork, cap);
+    CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mpsk_fixup_extents(const void * recs, size_t n, int key_in_high, uint64_t flip, uint32_t lobits,
+        const uint32_t * worklist, uint32_t nwork, uint32_t * lengths, mpsk_stream_t stream)
+{
+    if (nwork == 0) return 0;
+    fixup_extent_kernel<<<(nwork + 63) / 64, 64, 0, (cudaStream_t) stream>>>(
+        (const uint4 *) recs, (u32) n, key_in_high ? 1u : 0u, (u64) flip, lobits, worklist, nwork, lengths);
+    CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
+/* predictor: the high parts of `s` evenly spaced records, as bare u64 "records" */
+__global__ void sample_prefix_kernel(const uint4 * __restrict__ recs, size_t n, u32 s, u32 khi, u64 flip, u32 lobits,
+                                     u64 * __restrict__ out)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s) return;
+    const size_t pos = (size_t) (((unsigned __int128) i * n) / s);
+    out[i] = rec_key(recs[pos], khi, flip) >> lobits;
+}
+
+/* number of equal PAIRS in a sorted array: sum over values of k(k-1)/2 */
+__global__ void count_equal_pairs_kernel(const u64 * __restrict__ sorted, u32 s, u64 * __restrict__ count)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    u64 pairs = 0;
+    if (i < s) {
+        const u64 v = sorted[i];
+        u32 lo = 0, hi = i;                               /* first index holding v */
+        while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (sorted[mid] < v) lo = mid + 1; else hi = mid; }
+        pairs = i - lo;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pairs += __shfl_xor_sync(FULL_MASK, pairs, o);
+    if ((threadIdx.x & 31) == 0 && pairs) atomicAdd(count, pairs);
+}
+
+extern "C" int mpsk_sample_prefix_rec16(const void * recs, size_t n, uint32_t s, int key_in_high, uint64_t flip,
+        uint32_t lobits, uint64_t * out, mpsk_stream_t stream)
+{
+    if (s == 0) return 0;
+    sample_prefix_kernel<<<(s + 255) / 256, 256, 0, (cudaStream_t) stream>>>(
+        (const uint4 *) recs, n, s, key_in_high ? 1u : 0u, (u64) flip, lobits, (u64 *) out);
+    CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mpsk_count_equal_pairs(const uint64_t * sorted, uint32_t s, uint64_t * count, mpsk_stream_t stream)
+{
+    if (s == 0) return 0;
+    count_equal_pairs_kernel<<<(s + 255) / 256, 256, 0, (cudaStream_t) stream>>>((const u64 *) sorted, s, (u64 *) count);
+    CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
 /* ========================================================================= */
 /* gathers                                                                   */
 /* ========================================================================= */

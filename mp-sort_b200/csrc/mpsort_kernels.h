@@ -56,6 +56,23 @@ int mpsk_onesweep_pass(const uint64_t * kin, const uint32_t * vin,
 int mpsk_onesweep_pass_rec16(const void * in, void * out, size_t n, int shift,
         int key_in_high, uint64_t flip, const uint32_t * bins, void * scratch, mpsk_stream_t stream);
 
+/* Hybrid sort support (record mode). After stable passes over the high digits only,
+ * records that agree in (key ^ flip) >> lobits form runs that are still in input
+ * order; mpsk_fixup_rec16 orders every run of <= 256 records by the low `lobits`
+ * bits in place and appends the start index of every longer run to worklist
+ * (*nwork counts them, also beyond cap; both device memory, *nwork zeroed by the
+ * caller). mpsk_fixup_extents turns starts into lengths. */
+int mpsk_fixup_rec16(void * recs, size_t n, int key_in_high, uint64_t flip, uint32_t lobits,
+        uint32_t * worklist, uint32_t * nwork, uint32_t cap, mpsk_stream_t stream);
+int mpsk_fixup_extents(const void * recs, size_t n, int key_in_high, uint64_t flip, uint32_t lobits,
+        const uint32_t * worklist, uint32_t nwork, uint32_t * lengths, mpsk_stream_t stream);
+/* predictor of the hybrid sort: high parts of s evenly spaced records (as u64), and
+ * the number of equal pairs (sum of k(k-1)/2 over values) of a sorted u64 array, added
+ * to *count. */
+int mpsk_sample_prefix_rec16(const void * recs, size_t n, uint32_t s, int key_in_high, uint64_t flip,
+        uint32_t lobits, uint64_t * out, mpsk_stream_t stream);
+int mpsk_count_equal_pairs(const uint64_t * sorted, uint32_t s, uint64_t * count, mpsk_stream_t stream);
+
 /* dst[i] = src[idx[i]] for 64-bit words (key words of multi-word keys). If hist is
  * non-NULL nothing is accumulated (histograms are permutation invariant). */
 int mpsk_gather_u64(const uint64_t * src, const uint32_t * idx, uint64_t * dst,

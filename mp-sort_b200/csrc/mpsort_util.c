@@ -153,7 +153,7 @@ void mpsort_util_mem_info(int device, size_t * free_bytes, size_t * total_bytes)
 }
 
 static const char * kclass_names[MPS_NKCLASS] = {
-    "extract_hist", "onesweep_pass", "onesweep_pass_rec16", "gather_keys", "gather_records", "splitter", "checksum", "exchange", "merge_runs"
+    "extract_hist", "onesweep_pass", "onesweep_pass_rec16", "gather_keys", "gather_records", "splitter", "checksum", "exchange", "merge_runs", "hybrid_fixup"
 };
 
 void mpsort_util_kernel_timing(mpsort_comm_t c, int on)

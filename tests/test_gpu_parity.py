@@ -105,6 +105,87 @@ def test_sorted_reverse_and_constant_inputs():
         assert np.array_equal(got, a[np.argsort(a["key"], kind="stable")])
 
 
+# ------------------------------------------------------------------ record mode + hybrid
+def _sort_single(a, desc):
+    got = a.copy()
+    comm = mpsort.Comm.self(0)
+    lib.mpsort_mpi_desc_impl(got.ctypes.data, len(got), a.dtype.itemsize, ctypes.byref(desc), comm.handle, 0, b"hybrid")
+    st = C.last_stats(comm.handle, 1)
+    comm.destroy()
+    return got, st
+
+
+@pytest.mark.parametrize("keyfield,signed", [("a", 0), ("b", 1)])
+def test_hybrid_sort_uniform_keys(keyfield, signed):
+    """>= 2^22 records with (nearly) distinct high 32 bits: four passes + run fix-up must
+    give the bytes of the full stable sort (key in the low or the high half, signed or not)"""
+    rng = np.random.default_rng(11 + signed)
+    n = (1 << 22) + 12345
+    dt = np.dtype([("a", "i8" if keyfield == "a" and signed else "u8"), ("b", "i8" if keyfield == "b" and signed else "u8")])
+    a = np.zeros(n, dtype=dt)
+    other = "b" if keyfield == "a" else "a"
+    a[keyfield] = rng.integers(0, 1 << 63, size=n, dtype=np.uint64).astype(dt[keyfield]) * 2 + rng.integers(0, 2, size=n).astype(dt[keyfield])
+    # make sure equal high parts and fully equal keys exist: ties must stay in input order
+    a[keyfield][1000:3000] = a[keyfield][0:2000]
+    hi = a[keyfield][5000:9000].view("u8") & np.uint64(0xFFFFFFFF00000000)
+    a[keyfield][9000:13000] = (hi | rng.integers(0, 1 << 32, size=4000, dtype=np.uint64)).view(dt[keyfield])
+    a[other] = np.arange(n)
+    desc = C.RadixDesc(0 if keyfield == "a" else 8, 8, 1, signed, 0)
+    got, st = _sort_single(a, desc)
+    assert st["record_mode"] == 1 and st["hybrid"] == 1 and st["first_sort_passes"] == 4
+    assert np.array_equal(got, a[np.argsort(a[keyfield], kind="stable")])
+
+
+def test_hybrid_sort_long_runs_and_fallback():
+    rng = np.random.default_rng(5)
+    n = 1 << 22
+    dt = np.dtype([("key", "u8"), ("tag", "u8")])
+    for nruns, runlen, expect_fallback in ((3, 3000, False), (100, 400, True)):
+        a = np.zeros(n, dtype=dt)
+        a["key"] = rng.integers(0, 1 << 63, size=n, dtype=np.uint64)
+        pos = rng.permutation(n)[: nruns * runlen].reshape(nruns, runlen)
+        for r in range(nruns):      # runs that share the high 32 bits but differ (with repeats) below
+            a["key"][pos[r]] = (np.uint64(r + 1) << np.uint64(40)) | rng.integers(0, 1000, size=runlen).astype(np.uint64)
+        a["tag"] = np.arange(n)
+        got, st = _sort_single(a, C.RadixDesc(0, 8, 1, 0, 0))
+        assert st["hybrid"] == 1 and st["hybrid_long_runs"] == nruns
+        assert (st["first_sort_passes"] > 4) == expect_fallback
+        assert np.array_equal(got, a[np.argsort(a["key"], kind="stable")])
+
+
+def test_hybrid_declined_for_clustered_keys():
+    """5 % of the records share one key: the predictor must refuse the hybrid"""
+    rng = np.random.default_rng(6)
+    n = 1 << 22
+    dt = np.dtype([("key", "u8"), ("tag", "u8")])
+    a = np.zeros(n, dtype=dt)
+    a["key"] = rng.integers(0, 1 << 63, size=n, dtype=np.uint64)
+    a["key"][rng.random(n) < 0.05] = 77
+    a["tag"] = np.arange(n)
+    got, st = _sort_single(a, C.RadixDesc(0, 8, 1, 0, 0))
+    assert st["record_mode"] == 1 and st["hybrid"] == 0 and st["first_sort_passes"] == 8
+    assert np.array_equal(got, a[np.argsort(a["key"], kind="stable")])
+
+
+def test_record_mode_equals_index_mode():
+    rng = np.random.default_rng(8)
+    dt = np.dtype([("tag", "u8"), ("key", "i8")])
+    for n in (1, 3071, 3072, 3073, 100001):
+        a = np.zeros(n, dtype=dt)
+        a["key"] = rng.integers(-1000, 1000, size=n)
+        a["tag"] = np.arange(n)
+        got, st = _sort_single(a, C.RadixDesc(8, 8, 1, 1, 0))
+        assert st["record_mode"] == 1
+        os.environ["MPSORT_NO_REC16"] = "1"
+        try:
+            got2, st2 = _sort_single(a, C.RadixDesc(8, 8, 1, 1, 0))
+        finally:
+            del os.environ["MPSORT_NO_REC16"]
+        assert st2["record_mode"] == 0
+        exp = a[np.argsort(a["key"], kind="stable")]
+        assert np.array_equal(got, exp) and np.array_equal(got2, exp)
+
+
 # ------------------------------------------------------------------ golden vectors
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 @pytest.mark.parametrize("tuning", TUNINGS)
