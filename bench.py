@@ -39,24 +39,34 @@ def peaks():
 
 
 class Clocks(object):
-    """nvidia-smi sampling during the timed region"""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampling: started early (it takes ~0.2 s to come up), sampled every
+    20 ms with timestamps; only samples inside [mark_start, mark_stop] are used."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.t0 = self.t1 = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_stop(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -64,25 +74,28 @@ class Clocks(object):
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in self.f.read().splitlines():
             t = [x.strip() for x in line.split(",")]
             if len(t) < 9:
                 continue
             try:
-                sm.append(float(t[1]))
-                mx.append(float(t[2]))
+                ts = datetime.datetime.strptime(t[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(t[1]), float(t[2]), [nm for k, nm in enumerate(names) if t[5 + k].lower().startswith("active")]))
             except ValueError:
                 continue
-            for k, nm in enumerate(names):
-                if t[5 + k].lower().startswith("active"):
-                    reasons.add(nm)
         self.f.close()
         os.unlink(self.f.name)
-        if sm:
-            sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.02 <= r[0] <= self.t1 + 0.02]
+        use = inside if inside else rows[-3:]
+        if use:
+            sm = sorted(r[1] for r in use)
+            reasons = set()
+            for r in use:
+                reasons.update(r[3])
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(r[2] for r in use), reasons=sorted(reasons),
+                       samples=len(use), samples_in_timed_region=len(inside))
         return out
 
 
@@ -162,6 +175,7 @@ def main():
 
     comm = mpsort.Comm.from_env()
     dev = comm.device
+    clocks = Clocks(dev) if comm.rank == 0 else None
     kind, E, signed = KINDS[args.workload]
     n = 1 << args.log2n
     desc = C.RadixDesc(0, 8, 1, signed, 0)
@@ -186,14 +200,17 @@ def main():
     e1 = lib.mpsort_util_event_create(comm.handle)
     lib.mpsort_util_kernel_timing(comm.handle, 1)
     lib.mpsort_util_launch_count(1)
-    clocks = Clocks(dev) if comm.rank == 0 else None
     comm.barrier()
     lib.mpsort_util_stream_sync(comm.handle)
+    if clocks:
+        clocks.mark_start()
     lib.mpsort_util_event_record(comm.handle, e0)
     for _ in range(K):
         step()
     lib.mpsort_util_event_record(comm.handle, e1)
     lib.mpsort_util_stream_sync(comm.handle)
+    if clocks:
+        clocks.mark_stop()
     comm.barrier()
     ms_total = maxall(lib.mpsort_util_event_elapsed_ms(comm.handle, e0, e1))
     clk = clocks.stop() if clocks else None

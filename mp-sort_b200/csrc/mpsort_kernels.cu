@@ -760,15 +760,18 @@ __device__ __forceinline__ u64 rec_key(const uint4 & it, u32 khi, u64 flip)
     return (khi ? (((u64) it.w << 32) | it.z) : (((u64) it.y << 32) | it.x)) ^ flip;
 }
 
+template <bool KHI>
 __global__ void __launch_bounds__(FIX_THREADS)
-fixup_rec16_kernel(uint4 * __restrict__ recs, u32 n, u32 khi, u64 flip, u32 lobits,
+fixup_rec16_kernel(uint4 * __restrict__ recs, u32 n, u64 flip, u32 lobits,
                    u32 * __restrict__ worklist, u32 * __restrict__ nwork, u32 cap)
 {
     constexpr int CAP = FIX_T + FIX_HALO;
     constexpr int WORDS = (CAP + 31) / 32 + 1;
-    __shared__ uint4 s_rec[CAP];
+    constexpr int NLD = CAP / FIX_THREADS;
+    static_assert(CAP % FIX_THREADS == 0, "tile + halo must be a multiple of the block size");
+    /* only the keys are staged: the few records that move are re-read from global */
+    __shared__ u64 s_key[CAP + 1];            /* [0] = key of the record before the tile */
     __shared__ u32 s_head[WORDS];
-    __shared__ u32 s_target[CAP];
 
     const u32 tid = threadIdx.x;
     const size_t t0 = (size_t) blockIdx.x * FIX_T;
@@ -776,24 +779,66 @@ fixup_rec16_kernel(uint4 * __restrict__ recs, u32 n, u32 khi, u64 flip, u32 lobi
     const u32 cnt = avail < (u32) CAP ? avail : (u32) CAP;
     const bool at_end = (t0 + cnt == n);
     const u64 lomask = lobits >= 64 ? ~0ULL : ((1ULL << lobits) - 1ULL);
+    const u64 * keys = (const u64 *) recs + (KHI ? 1 : 0);       /* key of record i at keys[2*i] */
 
-    for (u32 i = tid; i < cnt; i += FIX_THREADS) s_rec[i] = recs[t0 + i];
+    {
+        u64 tmp[NLD];
+#pragma unroll
+        for (int k = 0; k < NLD; k++) {
+            const u32 i = tid + k * FIX_THREADS;
+            if (i < cnt) tmp[k] = keys[2 * (t0 + i)];
+        }
+#pragma unroll
+        for (int k = 0; k < NLD; k++) {
+            const u32 i = tid + k * FIX_THREADS;
+            if (i < cnt) s_key[i + 1] = tmp[k] ^ flip;
+        }
+        if (tid == 0) s_key[0] = t0 ? (keys[2 * (t0 - 1)] ^ flip) : 0ULL;
+    }
     __syncthreads();
     /* head flags: the high part differs from the predecessor's. A warp handles 32
      * consecutive positions per round, so one ballot is one word of the bit map. */
-    for (u32 i = tid; i < (u32) WORDS * 32; i += FIX_THREADS) {
-        bool head = false;
-        if (i == cnt) head = at_end;                      /* sentinel: the data ends here */
-        else if (i < cnt) {
-            if (i == 0) head = (t0 == 0) || ((rec_key(recs[t0 - 1], khi, flip) >> lobits) != (rec_key(s_rec[0], khi, flip) >> lobits));
-            else head = (rec_key(s_rec[i - 1], khi, flip) >> lobits) != (rec_key(s_rec[i], khi, flip) >> lobits);
+#pragma unroll
+    for (int k = 0; k < (WORDS * 32 + FIX_THREADS - 1) / FIX_THREADS; k++) {
+        const u32 i = tid + k * FIX_THREADS;
+        if (i < (u32) WORDS * 32) {
+            bool head = false;
+            if (i == cnt) head = at_end;                      /* sentinel: the data ends here */
+            else if (i < cnt) head = ((s_key[i] >> lobits) != (s_key[i + 1] >> lobits)) || (i == 0 && t0 == 0);
+            const u32 word = __ballot_sync(FULL_MASK, head);
+            if ((tid & 31) == 0) s_head[i >> 5] = word;
         }
-        const u32 word = __ballot_sync(FULL_MASK, head);
-        if ((tid & 31) == 0) s_head[i >> 5] = word;
     }
     __syncthreads();
-    for (u32 i = tid; i < cnt; i += FIX_THREADS) {
-        s_target[i] = 0xffffffffu;
+    /* ---- compact the positions that are NOT a run of their own (6 % for random keys):
+     * the expensive part below then runs with full warps */
+    __shared__ u32 s_list[CAP];
+    __shared__ u32 s_nlist;
+    if (tid == 0) s_nlist = 0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NLD; k++) {
+        const u32 i = tid + k * FIX_THREADS;
+        const bool single = (i >= cnt) ||
+            (((s_head[i >> 5] >> (i & 31)) & 1u) && ((s_head[(i + 1) >> 5] >> ((i + 1) & 31)) & 1u));
+        const u32 votes = __ballot_sync(FULL_MASK, !single);
+        if (votes) {
+            u32 base = 0;
+            if ((tid & 31) == 0) base = atomicAdd(&s_nlist, (u32) __popc(votes));
+            base = __shfl_sync(FULL_MASK, base, 0);
+            if (!single) s_list[base + __popc(votes & lanemask_lt())] = i;
+        }
+    }
+    __syncthreads();
+    const u32 nlist = s_nlist;
+    uint4 moved[NLD];
+    u32 tgts[NLD];
+#pragma unroll
+    for (int k = 0; k < NLD; k++) {
+        tgts[k] = 0xffffffffu;
+        const u32 e = tid + k * FIX_THREADS;
+        if (e >= nlist) continue;
+        const u32 i = s_list[e];
         /* run start: last head at or before i */
         int w = (int) (i >> 5);
         u32 bits = s_head[w] & (0xffffffffu >> (31 - (i & 31)));
@@ -815,19 +860,21 @@ fixup_rec16_kernel(uint4 * __restrict__ recs, u32 n, u32 khi, u64 flip, u32 lobi
             continue;
         }
         if (re - rs < 2) continue;
-        const u64 mine = rec_key(s_rec[i], khi, flip) & lomask;
+        const u64 mine = s_key[i + 1] & lomask;
         u32 rank = 0;
         for (u32 j = rs; j < re; j++) {
-            const u64 other = rec_key(s_rec[j], khi, flip) & lomask;
+            const u64 other = s_key[j + 1] & lomask;
             rank += (other < mine) || (other == mine && j < i);
         }
-        s_target[i] = rs + rank;
+        if (rs + rank != i) {
+            tgts[k] = rs + rank;
+            moved[k] = recs[t0 + i];                      /* read before anyone of this CTA writes */
+        }
     }
     __syncthreads();
-    for (u32 i = tid; i < cnt; i += FIX_THREADS) {
-        const u32 tgt = s_target[i];
-        if (tgt != 0xffffffffu && tgt != i) recs[t0 + tgt] = s_rec[i];
-    }
+#pragma unroll
+    for (int k = 0; k < NLD; k++)
+        if (tgts[k] != 0xffffffffu) recs[t0 + tgts[k]] = moved[k];
 }
 
 /* extent of every long run on the work list: first index whose high part differs */
@@ -851,8 +898,12 @@ extern "C" int mpsk_fixup_rec16(void * recs, size_t n, int key_in_high, uint64_t
 {
     if (n == 0) return 0;
     const size_t tiles = (n + FIX_T - 1) / FIX_T;
-    fixup_rec16_kernel<<<(unsigned) tiles, FIX_THREADS, 0, (cudaStream_t) stream>>>(
-        (uint4 *) recs, (u32) n, key_in_high ? 1u : 0u, (u64) flip, lobits, worklist, nwork, cap);
+    if (key_in_high)
+        fixup_rec16_kernel<true><<<(unsigned) tiles, FIX_THREADS, 0, (cudaStream_t) stream>>>(
+            (uint4 *) recs, (u32) n, (u64) flip, lobits, worklist, nwork, cap);
+    else
+        fixup_rec16_kernel<false><<<(unsigned) tiles, FIX_THREADS, 0, (cudaStream_t) stream>>>(
+            (uint4 *) recs, (u32) n, (u64) flip, lobits, worklist, nwork, cap);
     CUDA_LAUNCH_CHECK();
     return 0;
 }
