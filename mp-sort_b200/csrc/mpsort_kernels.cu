@@ -1303,16 +1303,22 @@ merge_bounds_kernel(const unsigned char * __restrict__ recv, KeyDesc d, bool fas
     }
 }
 
+/* shared-memory index with one pad slot per 8 items: a thread's 8 consecutive outputs
+ * are 64 bytes apart from its neighbour's, which would be a 16-way bank conflict */
+#define MPD(i) ((i) + ((i) >> 3))
+#define MPSK_MERGE_PADDED (MPSK_MERGE_TILE + MPSK_MERGE_TILE / 8)
+
 template <typename V>
 __global__ void __launch_bounds__(MPSK_MERGE_THREADS, 2)
 merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, bool fast8, MergeRuns m,
                   const u32 * __restrict__ cut, unsigned char * __restrict__ out, u32 * __restrict__ overflow)
 {
+    constexpr int VT = MPSK_MERGE_TILE / MPSK_MERGE_THREADS;      /* items per thread */
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 * kA = (u64 *) smem_raw;
-    u64 * kB = kA + MPSK_MERGE_TILE;
-    u32 * sA = (u32 *) (kB + MPSK_MERGE_TILE);
-    u32 * sB = sA + MPSK_MERGE_TILE;
+    u64 * kB = kA + MPSK_MERGE_PADDED;
+    u32 * sA = (u32 *) (kB + MPSK_MERGE_PADDED);
+    u32 * sB = sA + MPSK_MERGE_PADDED;
     __shared__ u32 seqoff[MPSK_MERGE_MAX_RUNS + 1];
     __shared__ u32 srcbase[MPSK_MERGE_MAX_RUNS];
     __shared__ u32 s_outstart;
@@ -1336,37 +1342,67 @@ merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, bool fast8
         if (tid == 0) atomicAdd(overflow, 1u);
         return;
     }
-    /* ---- load keys of the p sub-ranges, run-major */
-    for (u32 i = tid; i < cnt; i += MPSK_MERGE_THREADS) {
-        u32 r = 0;
-        while (i >= seqoff[r + 1]) r++;
-        const u32 src = srcbase[r] + (i - seqoff[r]);
-        kA[i] = load_key_any(recv + (size_t) src * d.elsize, d, fast8);
-        sA[i] = src;
+    /* ---- load the keys of the p sub-ranges, run-major; all loads of a thread in flight */
+    {
+        u32 src[VT];
+        u64 key[VT];
+#pragma unroll
+        for (int k = 0; k < VT; k++) {
+            const u32 i = tid + k * MPSK_MERGE_THREADS;
+            src[k] = 0;
+            if (i < cnt) {
+                u32 r = 0;
+                while (i >= seqoff[r + 1]) r++;
+                src[k] = srcbase[r] + (i - seqoff[r]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < VT; k++) {
+            const u32 i = tid + k * MPSK_MERGE_THREADS;
+            if (i < cnt) key[k] = load_key_any(recv + (size_t) src[k] * d.elsize, d, fast8);
+        }
+#pragma unroll
+        for (int k = 0; k < VT; k++) {
+            const u32 i = tid + k * MPSK_MERGE_THREADS;
+            if (i < cnt) { kA[MPD(i)] = key[k]; sA[MPD(i)] = src[k]; }
+        }
     }
     __syncthreads();
-    /* ---- pairwise merge rounds over groups of w runs */
+    /* ---- pairwise merge rounds over groups of w runs: every thread produces VT
+     * consecutive outputs, starting from its merge-path intersection (one binary
+     * search per thread and pair instead of one per item). Ties take from A, the
+     * lower runs: stable. */
     for (u32 w = 1; w < p; w <<= 1) {
-        for (u32 i = tid; i < cnt; i += MPSK_MERGE_THREADS) {
-            u32 g = 0;
-            while ((g + 1) * w < p && i >= seqoff[(g + 1) * w]) g++;
-            const u32 ga = g & ~1u;
-            const u32 a0 = seqoff[ga * w];
-            const u32 a1 = seqoff[min((ga + 1) * w, p)];
-            const u32 b1 = seqoff[min((ga + 2) * w, p)];
-            const u64 key = kA[i];
-            u32 pos;
-            if (g == ga) {                      /* A side: count of B keys < key */
-                u32 lo = a1, hi = b1;
-                while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (kA[mid] < key) lo = mid + 1; else hi = mid; }
-                pos = i + (lo - a1);
-            } else {                            /* B side: count of A keys <= key */
-                u32 lo = a0, hi = a1;
-                while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (kA[mid] <= key) lo = mid + 1; else hi = mid; }
-                pos = a0 + (lo - a0) + (i - a1);
+        u32 o = tid * VT;
+        const u32 end = min(o + (u32) VT, cnt);
+        u32 g = 0;                                  /* pair index: groups 2g and 2g+1 */
+        while (o < end) {
+            while (seqoff[min((2 * g + 2) * w, p)] <= o) g++;
+            const u32 a0 = seqoff[min(2 * g * w, p)];
+            const u32 a1 = seqoff[min((2 * g + 1) * w, p)];
+            const u32 b1 = seqoff[min((2 * g + 2) * w, p)];
+            const u32 lenA = a1 - a0, lenB = b1 - a1;
+            const u32 seg_end = min(end, b1);
+            const u32 diag = o - a0;
+            u32 lo = diag > lenB ? diag - lenB : 0, hi = min(diag, lenA);
+            while (lo < hi) {
+                const u32 mid = (lo + hi) >> 1;
+                if (kA[MPD(a0 + mid)] <= kA[MPD(a1 + diag - 1 - mid)]) lo = mid + 1; else hi = mid;
             }
-            kB[pos] = key;
-            sB[pos] = sA[i];
+            u32 ai = lo, bi = diag - lo;
+            u64 ka = ai < lenA ? kA[MPD(a0 + ai)] : 0, kb = bi < lenB ? kA[MPD(a1 + bi)] : 0;
+            for (; o < seg_end; o++) {
+                const bool takeA = (bi >= lenB) || (ai < lenA && ka <= kb);
+                if (takeA) {
+                    kB[MPD(o)] = ka; sB[MPD(o)] = sA[MPD(a0 + ai)];
+                    ai++;
+                    if (ai < lenA) ka = kA[MPD(a0 + ai)];
+                } else {
+                    kB[MPD(o)] = kb; sB[MPD(o)] = sA[MPD(a1 + bi)];
+                    bi++;
+                    if (bi < lenB) kb = kA[MPD(a1 + bi)];
+                }
+            }
         }
         __syncthreads();
         u64 * tk = kA; kA = kB; kB = tk;
@@ -1377,9 +1413,21 @@ merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, bool fast8
     const V * in = (const V *) recv;
     V * o = (V *) out + (size_t) s_outstart * lpr;
     const u32 totalv = cnt * lpr;
-    for (u32 x = tid; x < totalv; x += MPSK_MERGE_THREADS) {
-        const u32 i = x / lpr, part = x - i * lpr;
-        o[x] = in[(size_t) sA[i] * lpr + part];
+    for (u32 x0 = 0; x0 < totalv; x0 += VT * MPSK_MERGE_THREADS) {
+        V v[VT];
+#pragma unroll
+        for (int k = 0; k < VT; k++) {
+            const u32 x = x0 + tid + k * MPSK_MERGE_THREADS;
+            if (x < totalv) {
+                const u32 i = x / lpr, part = x - i * lpr;
+                v[k] = in[(size_t) sA[MPD(i)] * lpr + part];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < VT; k++) {
+            const u32 x = x0 + tid + k * MPSK_MERGE_THREADS;
+            if (x < totalv) o[x] = v[k];
+        }
     }
 }
 
@@ -1407,7 +1455,7 @@ template <typename V>
 static int launch_merge_tiles(const void * recv, KeyDesc d, bool fast8, const MergeRuns & m, const u32 * cut,
                               void * out, u32 * overflow, u32 ntiles, cudaStream_t stream)
 {
-    const int smem = MPSK_MERGE_TILE * (8 + 8 + 4 + 4);
+    const int smem = MPSK_MERGE_PADDED * (8 + 8 + 4 + 4);
     auto kern = merge_tile_kernel<V>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int) e;
