@@ -294,6 +294,95 @@ __device__ __forceinline__ u32 match_digit(u32 digit)
 #endif
 }
 
+
+/*
+ * Decoupled look-back of one (tile, digit): exclusive count of the digit over all
+ * earlier tiles, two levels deep.
+ *
+ * With a flat look-back every in-flight predecessor only has a PARTIAL count until
+ * its own walk ends, and with ~450 small tiles resident the walk was ~160 entries
+ * deep: ncu showed 25 % of all instructions of a pass in this loop
+ * (profiles/r01_ncu_rec16_flat_lookback.txt). Tiles are therefore grouped in blocks
+ * of LB_BLOCK consecutive tiles. Every tile also adds its count to its block's total
+ * with ONE atomic that carries an arrival counter in the top bits
+ * ({arrivals:6, count:26}), so a complete block is a single self-describing word.
+ * A walk covers at most LB_BLOCK-1 tiles of its own block and then whole blocks.
+ * All waits are on tiles with smaller tickets, which are running or done.
+ */
+#ifndef MPSK_LB_DEPTH
+#define MPSK_LB_DEPTH 4
+#endif
+#ifndef MPSK_LB_BLOCK
+#define MPSK_LB_BLOCK 32
+#endif
+constexpr int LB_BLOCK = MPSK_LB_BLOCK;
+constexpr u32 LB_TOTAL_SHIFT = 26;
+constexpr u32 LB_TOTAL_MASK = (1u << LB_TOTAL_SHIFT) - 1u;
+
+struct LookbackBufs { u32 * tiles; u32 * blktotal; u32 * blkincl; };
+
+__device__ __forceinline__ void lookback_publish_partial(const LookbackBufs & lb, u32 tile, u32 digit, u32 count)
+{
+    st_relaxed_u32(&lb.tiles[(size_t) tile * 256 + digit], (tile == 0 ? LB_INCL : LB_PART) | count);
+    atomicAdd(&lb.blktotal[(size_t) (tile / LB_BLOCK) * 256 + digit], (1u << LB_TOTAL_SHIFT) | count);
+}
+
+/* walk the tile entries t, t-1, ..., t_first (MPSK_LB_DEPTH polled per round trip);
+ * true when an INCLUSIVE entry ended the walk */
+__device__ __forceinline__ bool lookback_walk(const u32 * tiles, int t, const int t_first, const u32 digit, u32 & acc)
+{
+    while (t >= t_first) {
+        u32 s[MPSK_LB_DEPTH];
+#pragma unroll
+        for (int k = 0; k < MPSK_LB_DEPTH; k++)
+            s[k] = (t - k >= t_first) ? ld_relaxed_u32(&tiles[(size_t) (t - k) * 256 + digit]) : 0u;
+        int used = 0;
+#pragma unroll
+        for (int k = 0; k < MPSK_LB_DEPTH; k++) {
+            if (used == k && t - k >= t_first) {
+                if (s[k] & LB_INCL) { acc += s[k] & LB_MASK; return true; }
+                if (s[k] & LB_PART) { acc += s[k] & LB_MASK; used++; }
+            }
+        }
+        t -= used;                     /* entries not yet published are polled again */
+    }
+    return false;
+}
+
+__device__ __forceinline__ u32 lookback_exclusive(const LookbackBufs & lb, u32 tile, u32 digit)
+{
+    const u32 b = tile / LB_BLOCK;
+    u32 excl = 0;
+    /* 1: the earlier tiles of my own block */
+    if (lookback_walk(lb.tiles, (int) tile - 1, (int) (b * LB_BLOCK), digit, excl)) return excl;
+    if (b == 0) return excl;
+    /* 2: whole blocks, newest first */
+    u32 e2 = 0;
+    int bb = (int) b - 1;
+    for (;;) {
+        const u32 wi = ld_relaxed_u32(&lb.blkincl[(size_t) bb * 256 + digit]);
+        const u32 wt = ld_relaxed_u32(&lb.blktotal[(size_t) bb * 256 + digit]);
+        if (wi & LB_INCL) { e2 += wi & LB_MASK; break; }
+        if ((wt >> LB_TOTAL_SHIFT) == (u32) LB_BLOCK) {
+            e2 += wt & LB_TOTAL_MASK;
+        } else {
+            /* some tile of that block has not ranked yet: take its tiles one by one */
+            if (lookback_walk(lb.tiles, (bb + 1) * LB_BLOCK - 1, bb * LB_BLOCK, digit, e2)) break;
+        }
+        if (bb == 0) break;
+        bb--;
+    }
+    /* e2 is the inclusive prefix through block b-1: later walks stop here */
+    st_relaxed_u32(&lb.blkincl[(size_t) (b - 1) * 256 + digit], LB_INCL | e2);
+    return excl + e2;
+}
+
+__host__ __device__ __forceinline__ size_t lookback_words(size_t ntiles)
+{
+    const size_t nblk = (ntiles + LB_BLOCK - 1) / LB_BLOCK;
+    return 64 + ntiles * 256 + 2 * nblk * 256;
+}
+
 template <int THREADS, int IPT>
 struct SweepCfg {
     static constexpr int TILE = THREADS * IPT;
@@ -320,7 +409,7 @@ __global__ void __launch_bounds__(THREADS, MPSK_SWEEP_MINBLOCKS)
 onesweep_kernel(const u64 * __restrict__ kin, const u32 * __restrict__ vin,
                 u64 * __restrict__ kout, u32 * __restrict__ vout,
                 u32 n, u32 shift, const u32 * __restrict__ bins,
-                u32 * lookback, u32 * ticket)
+                LookbackBufs lb, u32 * ticket)
 {
     typedef SweepCfg<THREADS, IPT> Cfg;
     constexpr int TILE = Cfg::TILE;
@@ -397,8 +486,7 @@ onesweep_kernel(const u64 * __restrict__ kin, const u32 * __restrict__ vin,
         cnt_full = run;
         cnt_valid = run;
         if (tid == 255) cnt_valid -= ((u32) TILE - valid);
-        st_relaxed_u32(&lookback[(size_t) tile * 256 + tid],
-                       (tile == 0 ? LB_INCL : LB_PART) | cnt_valid);
+        lookback_publish_partial(lb, tile, tid, cnt_valid);
         /* digit scan, warp part */
         u32 incl = cnt_full;
 #pragma unroll
@@ -451,22 +539,8 @@ onesweep_kernel(const u64 * __restrict__ kin, const u32 * __restrict__ vin,
     if (tid < 256) {
         u32 excl = 0;
         if (tile > 0) {
-            int t = (int) tile - 1;
-            bool done = false;
-            while (!done) {
-                u32 s[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    s[k] = (t - k >= 0) ? ld_relaxed_u32(&lookback[(size_t) (t - k) * 256 + tid]) : LB_INCL;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (done) break;
-                    if (s[k] & LB_INCL) { excl += s[k] & LB_MASK; done = true; }
-                    else if (s[k] & LB_PART) { excl += s[k] & LB_MASK; t--; }
-                    else break;          /* not published yet: poll again from here */
-                }
-            }
-            st_relaxed_u32(&lookback[(size_t) tile * 256 + tid], LB_INCL | (excl + cnt_valid));
+            excl = lookback_exclusive(lb, tile, tid);
+            st_relaxed_u32(&lb.tiles[(size_t) tile * 256 + tid], LB_INCL | (excl + cnt_valid));
         }
         s_gofs[tid] = bins[tid] + excl - s_local[tid];
     }
@@ -497,7 +571,7 @@ extern "C" size_t mpsk_onesweep_scratch_bytes(size_t n)
     /* enough for the smallest tile of any pass flavour (record passes use 3072) */
     const size_t tile = 2048;
     const size_t ntiles = (n + tile - 1) / tile;
-    return (ntiles * 256 + 64) * sizeof(u32);
+    return lookback_words(ntiles) * sizeof(u32);
 }
 
 extern "C" int mpsk_onesweep_pass(const uint64_t * kin, const uint32_t * vin,
@@ -508,23 +582,26 @@ extern "C" int mpsk_onesweep_pass(const uint64_t * kin, const uint32_t * vin,
     if (n > MPSK_MAX_ITEMS) return (int) cudaErrorInvalidValue;
     cudaStream_t stream = (cudaStream_t) stream_;
     const size_t ntiles = (n + TheSweep::TILE - 1) / TheSweep::TILE;
-    cudaError_t e = cudaMemsetAsync(scratch, 0, (ntiles * 256 + 64) * sizeof(u32), stream);
+    cudaError_t e = cudaMemsetAsync(scratch, 0, lookback_words(ntiles) * sizeof(u32), stream);
     if (e != cudaSuccess) return (int) e;
     u32 * ticket = (u32 *) scratch;
-    u32 * lookback = ticket + 64;
+    LookbackBufs lb;
+    lb.tiles = ticket + 64;
+    lb.blktotal = lb.tiles + ntiles * 256;
+    lb.blkincl = lb.blktotal + ((ntiles + LB_BLOCK - 1) / LB_BLOCK) * 256;
     /* the attribute is per device: set it on every launch (local groups span devices) */
     if (vin == NULL) {
         auto kern = onesweep_kernel<MPSK_SWEEP_THREADS, MPSK_SWEEP_IPT, true>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TheSweep::SMEM);
         if (e != cudaSuccess) return (int) e;
         kern<<<(unsigned) ntiles, MPSK_SWEEP_THREADS, TheSweep::SMEM, stream>>>(
-            (const u64 *) kin, vin, (u64 *) kout, vout, (u32) n, (u32) shift, bins, lookback, ticket);
+            (const u64 *) kin, vin, (u64 *) kout, vout, (u32) n, (u32) shift, bins, lb, ticket);
     } else {
         auto kern = onesweep_kernel<MPSK_SWEEP_THREADS, MPSK_SWEEP_IPT, false>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TheSweep::SMEM);
         if (e != cudaSuccess) return (int) e;
         kern<<<(unsigned) ntiles, MPSK_SWEEP_THREADS, TheSweep::SMEM, stream>>>(
-            (const u64 *) kin, vin, (u64 *) kout, vout, (u32) n, (u32) shift, bins, lookback, ticket);
+            (const u64 *) kin, vin, (u64 *) kout, vout, (u32) n, (u32) shift, bins, lb, ticket);
     }
     CUDA_LAUNCH_CHECK();
     return 0;
@@ -567,7 +644,7 @@ template <int THREADS, int IPT>
 __global__ void __launch_bounds__(THREADS, MPSK_REC_MINBLOCKS)
 onesweep_rec16_kernel(const uint4 * __restrict__ in, uint4 * __restrict__ out,
                       u32 n, u32 shift, u32 khi, u64 flip, const u32 * __restrict__ bins,
-                      u32 * lookback, u32 * ticket)
+                      LookbackBufs lb, u32 * ticket)
 {
     typedef RecCfg<THREADS, IPT> Cfg;
     constexpr int TILE = Cfg::TILE;
@@ -646,8 +723,7 @@ onesweep_rec16_kernel(const uint4 * __restrict__ in, uint4 * __restrict__ out,
         cnt_full = run;
         cnt_valid = run;
         if (tid == 255) cnt_valid -= ((u32) TILE - valid);
-        st_relaxed_u32(&lookback[(size_t) tile * 256 + tid],
-                       (tile == 0 ? LB_INCL : LB_PART) | cnt_valid);
+        lookback_publish_partial(lb, tile, tid, cnt_valid);
         u32 incl = cnt_full;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -679,22 +755,8 @@ onesweep_rec16_kernel(const uint4 * __restrict__ in, uint4 * __restrict__ out,
     if (tid < 256) {
         u32 excl = 0;
         if (tile > 0) {
-            int t = (int) tile - 1;
-            bool done = false;
-            while (!done) {
-                u32 s[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    s[k] = (t - k >= 0) ? ld_relaxed_u32(&lookback[(size_t) (t - k) * 256 + tid]) : LB_INCL;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (done) break;
-                    if (s[k] & LB_INCL) { excl += s[k] & LB_MASK; done = true; }
-                    else if (s[k] & LB_PART) { excl += s[k] & LB_MASK; t--; }
-                    else break;
-                }
-            }
-            st_relaxed_u32(&lookback[(size_t) tile * 256 + tid], LB_INCL | (excl + cnt_valid));
+            excl = lookback_exclusive(lb, tile, tid);
+            st_relaxed_u32(&lb.tiles[(size_t) tile * 256 + tid], LB_INCL | (excl + cnt_valid));
         }
         s_gofs[tid] = bins[tid] + excl - s_local[tid];
     }
@@ -720,16 +782,19 @@ extern "C" int mpsk_onesweep_pass_rec16(const void * in, void * out, size_t n, i
     if (n > MPSK_MAX_ITEMS) return (int) cudaErrorInvalidValue;
     cudaStream_t stream = (cudaStream_t) stream_;
     const size_t ntiles = (n + TheRec::TILE - 1) / TheRec::TILE;
-    cudaError_t e = cudaMemsetAsync(scratch, 0, (ntiles * 256 + 64) * sizeof(u32), stream);
+    cudaError_t e = cudaMemsetAsync(scratch, 0, lookback_words(ntiles) * sizeof(u32), stream);
     if (e != cudaSuccess) return (int) e;
     u32 * ticket = (u32 *) scratch;
-    u32 * lookback = ticket + 64;
+    LookbackBufs lb;
+    lb.tiles = ticket + 64;
+    lb.blktotal = lb.tiles + ntiles * 256;
+    lb.blkincl = lb.blktotal + ((ntiles + LB_BLOCK - 1) / LB_BLOCK) * 256;
     auto kern = onesweep_rec16_kernel<MPSK_REC_THREADS, MPSK_REC_IPT>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TheRec::SMEM);
     if (e != cudaSuccess) return (int) e;
     kern<<<(unsigned) ntiles, MPSK_REC_THREADS, TheRec::SMEM, stream>>>(
         (const uint4 *) in, (uint4 *) out, (u32) n, (u32) shift, key_in_high ? 1u : 0u, (u64) flip,
-        bins, lookback, ticket);
+        bins, lb, ticket);
     CUDA_LAUNCH_CHECK();
     return 0;
 }
