@@ -117,28 +117,11 @@ __device__ __forceinline__ u64 load_key_fast8(const unsigned char * rec, size_t 
     return (*(const u64 *) (rec + offset)) ^ flip;
 }
 
-__device__ __forceinline__ void hist8_add(u32 * sh, u64 k, bool warp_full)
-{
-#pragma unroll
-    for (int d = 0; d < 8; d++) {
-        const u32 digit = (u32) (k >> (8 * d)) & 255u;
-        u32 * slot = &sh[d * 256 + digit];
-        if (warp_full) {
-            /* constant digits (small ids, zero high bytes) would serialise 32 same
-             * address atomics: one lane adds 32 instead */
-            int all_same;
-            __match_all_sync(FULL_MASK, digit, &all_same);
-            if (all_same) {
-                if ((threadIdx.x & 31) == 0) atomicAdd(slot, 32u);
-            } else {
-                atomicAdd(slot, 1u);
-            }
-        } else {
-            atomicAdd(slot, 1u);
-        }
-    }
-}
-
+/* Four keys per thread and iteration. Digits that are equal over all 128 keys of the
+ * warp's batch (small ids, zero high bytes, sorted input) would serialise same-address
+ * shared atomics: one OR-reduction of the pairwise differences per batch finds them,
+ * lane 0 adds 128 for those, everyone adds 1 per key for the rest. */
+#define EXTRACT_BATCH 4
 template <bool FAST8>
 __global__ void __launch_bounds__(512)
 extract_kernel(const unsigned char * __restrict__ base, size_t n, KeyDesc d,
@@ -149,18 +132,50 @@ extract_kernel(const unsigned char * __restrict__ base, size_t n, KeyDesc d,
     __syncthreads();
 
     const u64 flip = (d.is_signed ? (1ULL << 63) : 0ULL);
-    const size_t nthreads = (size_t) gridDim.x * blockDim.x;
-    const size_t nround = (n + 31) & ~(size_t) 31;
-    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += nthreads) {
-        const bool valid = i < n;
-        const bool warp_full = __all_sync(FULL_MASK, valid);
-        if (valid) {
-            const unsigned char * rec = base + i * d.elsize;
-            u64 k;
-            if (FAST8) k = load_key_fast8(rec, d.offset, flip);
-            else k = pack_key_word(rec, d);
-            if (kout) kout[i] = k;
-            hist8_add(sh, k, warp_full);
+    const size_t per_block = (size_t) blockDim.x * EXTRACT_BATCH;
+    const size_t nblocks_total = (n + per_block - 1) / per_block;
+    const bool lane0 = (threadIdx.x & 31) == 0;
+    for (size_t blk = blockIdx.x; blk < nblocks_total; blk += gridDim.x) {
+        const size_t i0 = blk * per_block + threadIdx.x;
+        u64 k[EXTRACT_BATCH];
+        bool valid[EXTRACT_BATCH];
+#pragma unroll
+        for (int j = 0; j < EXTRACT_BATCH; j++) {
+            const size_t i = i0 + (size_t) j * blockDim.x;
+            valid[j] = i < n;
+            k[j] = 0;
+            if (valid[j]) {
+                const unsigned char * rec = base + i * d.elsize;
+                if (FAST8) k[j] = load_key_fast8(rec, d.offset, flip);
+                else k[j] = pack_key_word(rec, d);
+                if (kout) kout[i] = k[j];
+            }
+        }
+        /* the last lane's last key is the first to fall off the end */
+        const bool full = __all_sync(FULL_MASK, valid[EXTRACT_BATCH - 1]);
+        u32 same = 0;
+        if (full) {
+            const u64 k0 = __shfl_sync(FULL_MASK, k[0], 0);
+            u64 diff = 0;
+#pragma unroll
+            for (int j = 0; j < EXTRACT_BATCH; j++) diff |= k[j] ^ k0;
+            const u32 dlo = __reduce_or_sync(FULL_MASK, (u32) diff);
+            const u32 dhi = __reduce_or_sync(FULL_MASK, (u32) (diff >> 32));
+#pragma unroll
+            for (int dd = 0; dd < 4; dd++) {
+                if (((dlo >> (8 * dd)) & 255u) == 0) same |= 1u << dd;
+                if (((dhi >> (8 * dd)) & 255u) == 0) same |= 1u << (dd + 4);
+            }
+        }
+#pragma unroll
+        for (int dd = 0; dd < 8; dd++) {
+            if (same & (1u << dd)) {
+                if (lane0) atomicAdd(&sh[dd * 256 + ((u32) (k[0] >> (8 * dd)) & 255u)], 32u * EXTRACT_BATCH);
+            } else {
+#pragma unroll
+                for (int j = 0; j < EXTRACT_BATCH; j++)
+                    if (valid[j]) atomicAdd(&sh[dd * 256 + ((u32) (k[j] >> (8 * dd)) & 255u)], 1u);
+            }
         }
     }
     __syncthreads();
@@ -179,7 +194,7 @@ extern "C" int mpsk_extract_keys(const void * base, size_t n, size_t elsize,
     d.elsize = elsize; d.offset = offset; d.width = width; d.nwords = nwords;
     d.is_signed = is_signed; d.g = g;
     const int threads = 512;
-    size_t blocks = (n + threads - 1) / threads;
+    size_t blocks = (n + (size_t) threads * EXTRACT_BATCH - 1) / ((size_t) threads * EXTRACT_BATCH);
     const size_t maxb = (size_t) num_sms() * 8;
     if (blocks > maxb) blocks = maxb;
     const bool fast8 = (width == 8) && (nwords >= 1) && (elsize % 8 == 0)
