@@ -434,9 +434,9 @@ static int merge_received_runs(struct mpsort_comm * c, const void * recvbuf, con
         void * dout, size_t outn, size_t elsize, const struct mpsort_radix_desc * desc)
 {
     const int p = c->size;
-    const size_t T = mpsk_merge_tile_items();
+    const size_t T = mpsk_merge_tile_items_for(recvbuf, dout, elsize, desc->offset, desc->width, desc->nwords, (uint32_t) p);
     int r;
-    if (key_words(desc) != 1 || p > 32 || p < 2 || outn < 4 * T || outn > 0xfffffff0u) return 1;
+    if (key_words(desc) != 1 || p > 32 || p < 2 || outn < 4 * mpsk_merge_tile_items() || outn > 0xfffffff0u) return 1;
     if (getenv("MPSORT_NO_MERGE")) return 1;
     /* (k + p) * S <= T with k = 3p: S = T / (4p) rounded down to a power of two */
     uint32_t S = 1;

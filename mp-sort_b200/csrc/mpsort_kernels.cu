@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "mpsort_kernels.h"
 
@@ -1315,7 +1316,9 @@ extern "C" int mpsk_sum_u64(uint64_t * dst, const uint64_t * const * srcs, int n
  */
 #define MPSK_MERGE_MAX_RUNS 32
 #define MPSK_MERGE_TILE 4096
+#ifndef MPSK_MERGE_THREADS
 #define MPSK_MERGE_THREADS 512
+#endif
 
 struct MergeRuns {
     u32 p;
@@ -1511,6 +1514,125 @@ merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, bool fast8
     }
 }
 
+/* ---- the same merge for 16-byte records {u64 key, u64 other}: the records themselves
+ * are staged and merged in shared memory, so every record is read once and written
+ * once with coalesced 16-byte accesses (no key pre-read, no gather by index). */
+#define MPSK_MERGE16_TILE 2048
+#define MPSK_MERGE16_THREADS 512
+#define MPSK_MERGE16_PADDED (MPSK_MERGE16_TILE + MPSK_MERGE16_TILE / 8)
+
+template <bool KHI>
+__global__ void __launch_bounds__(MPSK_MERGE16_THREADS, 3)
+merge_tile_rec16_kernel(const uint4 * __restrict__ recv, u64 flip, MergeRuns m,
+                        const u32 * __restrict__ cut, uint4 * __restrict__ out, u32 * __restrict__ overflow)
+{
+    constexpr int VT = MPSK_MERGE16_TILE / MPSK_MERGE16_THREADS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4 * A = (uint4 *) smem_raw;
+    uint4 * B = A + MPSK_MERGE16_PADDED;
+    __shared__ u32 seqoff[MPSK_MERGE_MAX_RUNS + 1];
+    __shared__ u32 srcbase[MPSK_MERGE_MAX_RUNS];
+    __shared__ u32 s_outstart;
+
+    const u32 t = blockIdx.x, p = m.p, tid = threadIdx.x;
+    if (tid == 0) {
+        u32 acc = 0, ostart = 0;
+        for (u32 r = 0; r < p; r++) {
+            const u32 c0 = cut[t * p + r], c1 = cut[(t + 1) * p + r];
+            seqoff[r] = acc;
+            srcbase[r] = m.rdispl[r] + c0;
+            acc += c1 - c0;
+            ostart += c0;
+        }
+        seqoff[p] = acc;
+        s_outstart = ostart;
+    }
+    __syncthreads();
+    const u32 cnt = seqoff[p];
+    if (cnt > MPSK_MERGE16_TILE) {
+        if (tid == 0) atomicAdd(overflow, 1u);
+        return;
+    }
+    {
+        uint4 rec[VT];
+#pragma unroll
+        for (int k = 0; k < VT; k++) {
+            const u32 i = tid + k * MPSK_MERGE16_THREADS;
+            if (i < cnt) {
+                u32 r = 0;
+                while (i >= seqoff[r + 1]) r++;
+                rec[k] = recv[srcbase[r] + (i - seqoff[r])];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < VT; k++) {
+            const u32 i = tid + k * MPSK_MERGE16_THREADS;
+            if (i < cnt) A[MPD(i)] = rec[k];
+        }
+    }
+    __syncthreads();
+#define KEY16(arr, i) (((const u64 *) &(arr)[MPD(i)])[KHI ? 1 : 0] ^ flip)
+    for (u32 w = 1; w < p; w <<= 1) {
+        u32 o = tid * VT;
+        const u32 end = min(o + (u32) VT, cnt);
+        u32 g = 0;
+        while (o < end) {
+            while (seqoff[min((2 * g + 2) * w, p)] <= o) g++;
+            const u32 a0 = seqoff[min(2 * g * w, p)];
+            const u32 a1 = seqoff[min((2 * g + 1) * w, p)];
+            const u32 b1 = seqoff[min((2 * g + 2) * w, p)];
+            const u32 lenA = a1 - a0, lenB = b1 - a1;
+            const u32 seg_end = min(end, b1);
+            const u32 diag = o - a0;
+            u32 lo = diag > lenB ? diag - lenB : 0, hi = min(diag, lenA);
+            while (lo < hi) {
+                const u32 mid = (lo + hi) >> 1;
+                if (KEY16(A, a0 + mid) <= KEY16(A, a1 + diag - 1 - mid)) lo = mid + 1; else hi = mid;
+            }
+            u32 ai = lo, bi = diag - lo;
+            u64 ka = ai < lenA ? KEY16(A, a0 + ai) : 0, kb = bi < lenB ? KEY16(A, a1 + bi) : 0;
+            for (; o < seg_end; o++) {
+                const bool takeA = (bi >= lenB) || (ai < lenA && ka <= kb);
+                if (takeA) {
+                    B[MPD(o)] = A[MPD(a0 + ai)];
+                    ai++;
+                    if (ai < lenA) ka = KEY16(A, a0 + ai);
+                } else {
+                    B[MPD(o)] = A[MPD(a1 + bi)];
+                    bi++;
+                    if (bi < lenB) kb = KEY16(A, a1 + bi);
+                }
+            }
+        }
+        __syncthreads();
+        uint4 * tmp = A; A = B; B = tmp;
+    }
+#undef KEY16
+    uint4 * o = out + s_outstart;
+#pragma unroll
+    for (int k = 0; k < VT; k++) {
+        const u32 i = tid + k * MPSK_MERGE16_THREADS;
+        if (i < cnt) o[i] = A[MPD(i)];
+    }
+}
+
+static bool merge_rec16_ok(const void * recv, const void * out, size_t elsize, size_t offset, uint32_t width, uint32_t nwords)
+{
+    static int disabled = -1;
+    if (disabled < 0) disabled = getenv("MPSORT_NO_MERGE16") ? 1 : 0;
+    if (disabled) return false;
+    return elsize == 16 && width == 8 && nwords == 1 && (offset == 0 || offset == 8)
+           && ((((uintptr_t) recv) | ((uintptr_t) out)) & 15) == 0;
+}
+
+/* the record-staging kernel wins for two runs (one merge round); with more rounds the
+ * (key, index) kernel moves fewer bytes per round (profiles/r01_merge_kernels.log) */
+extern "C" size_t mpsk_merge_tile_items_for(const void * recv, const void * out, size_t elsize, size_t offset,
+        uint32_t width, uint32_t nwords, uint32_t p)
+{
+    return (p == 2 && merge_rec16_ok(recv, out, elsize, offset, width, nwords)) ? MPSK_MERGE16_TILE : MPSK_MERGE_TILE;
+}
+
 extern "C" size_t mpsk_merge_tile_items(void) { return MPSK_MERGE_TILE; }
 
 extern "C" int mpsk_merge_samples(const void * recv, size_t elsize, size_t offset, uint32_t width,
@@ -1562,6 +1684,24 @@ extern "C" int mpsk_merge_runs(const void * recv, void * out, size_t elsize, siz
     merge_bounds_kernel<<<blocks, 256, 0, stream>>>((const unsigned char *) recv, d, fast8, m,
                                                     (const u64 *) sorted_skeys, sorted_sid, ntiles, cut);
     CUDA_LAUNCH_CHECK();
+    if (p == 2 && merge_rec16_ok(recv, out, elsize, offset, width, nwords)) {
+        const int smem = MPSK_MERGE16_PADDED * 16 * 2;
+        const u64 flip = is_signed ? (1ULL << 63) : 0ULL;
+        cudaError_t e;
+        if (offset == 8) {
+            auto kern = merge_tile_rec16_kernel<true>;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return (int) e;
+            kern<<<ntiles, MPSK_MERGE16_THREADS, smem, stream>>>((const uint4 *) recv, flip, m, cut, (uint4 *) out, overflow);
+        } else {
+            auto kern = merge_tile_rec16_kernel<false>;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return (int) e;
+            kern<<<ntiles, MPSK_MERGE16_THREADS, smem, stream>>>((const uint4 *) recv, flip, m, cut, (uint4 *) out, overflow);
+        }
+        CUDA_LAUNCH_CHECK();
+        return 0;
+    }
     const uintptr_t a = ((uintptr_t) recv) | ((uintptr_t) out) | (uintptr_t) elsize;
     if ((a & 15) == 0) return launch_merge_tiles<uint4>(recv, d, fast8, m, cut, out, overflow, ntiles, stream);
     if ((a & 7) == 0) return launch_merge_tiles<u64>(recv, d, fast8, m, cut, out, overflow, ntiles, stream);

@@ -125,6 +125,9 @@ int mpsk_sum_u64(uint64_t * dst, const uint64_t * const * srcs, int nsrc, size_t
  * *overflow (device, zeroed by the caller) counts tiles that exceeded the bound
  * (never happens; such a tile is left unwritten instead of corrupting memory). */
 size_t mpsk_merge_tile_items(void);
+/* tile size the merge will use for these buffers (16-byte records get their own kernel) */
+size_t mpsk_merge_tile_items_for(const void * recv, const void * out, size_t elsize, size_t offset,
+        uint32_t width, uint32_t nwords, uint32_t p);
 int mpsk_merge_samples(const void * recv, size_t elsize, size_t offset, uint32_t width,
         uint32_t nwords, int is_signed, uint32_t p, uint32_t S, uint32_t k,
         const uint32_t * rdispl, const uint32_t * sstart, uint64_t * skeys, mpsk_stream_t stream);

@@ -410,6 +410,36 @@ def test_large_particles48_and_mostly_sorted_by_properties():
     comm.destroy()
 
 
+def test_large_multirank_hybrid_records_by_properties():
+    """4 rank threads x 2^22 uniform 16-byte records: record mode + hybrid FirstSort,
+    exchange, merge; checked by global order, tie order and checksum of checksums"""
+    p, n, E = 4, 1 << 22, 16
+    desc = C.RadixDesc(0, 8, 1, 0, 0)
+    res = [None] * p
+
+    def work(comm):
+        r = comm.rank
+        buf = lib.mpsort_util_dev_malloc(0, n * E)
+        out = lib.mpsort_util_dev_malloc(0, n * E)
+        lib.mpsort_util_generate(comm.handle, buf, n, E, 0, 0x5EED0001)
+        s1 = lib.mpsort_util_checksum(comm.handle, buf, n * E)
+        lib.mpsort_mpi_newarray_desc_impl(buf, n, out, n, E, ctypes.byref(desc), comm.handle, 0, b"multirank16")
+        st = C.last_stats(comm.handle, p)
+        s2 = lib.mpsort_util_checksum(comm.handle, out, n * E)
+        fl = (ctypes.c_uint64 * 2)()
+        bad = lib.mpsort_util_check_sorted(comm.handle, out, n, E, ctypes.byref(desc), 1, 8, fl)
+        lib.mpsort_util_dev_free(0, buf)
+        lib.mpsort_util_dev_free(0, out)
+        res[r] = (s1, s2, bad, fl[0], fl[1], st)
+
+    mpsort.run_local(p, work)
+    mask = (1 << 64) - 1
+    assert sum(x[0] for x in res) & mask == sum(x[1] for x in res) & mask
+    assert all(x[2] == 0 for x in res)
+    assert all(res[r - 1][4] <= res[r][3] for r in range(1, p))
+    assert all(x[5]["record_mode"] == 1 and x[5]["hybrid"] == 1 and x[5]["second_sort_merge_tiles"] > 0 for x in res)
+
+
 def test_large_multirank_by_properties():
     """4 rank threads x 2^22 records with a 5 % equal-key run spanning ranks: global
     order, tie order across rank boundaries, checksum of checksums"""
