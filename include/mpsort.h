@@ -184,6 +184,8 @@ struct mpsort_last_stats {
     uint32_t record_mode;        /* 1: 16-byte records were carried through the passes themselves */
     uint32_t hybrid;             /* 1: four high-digit passes + run fix-up instead of all passes */
     uint32_t hybrid_long_runs;   /* runs of > 256 equal high parts that were sorted separately */
+    uint32_t rebased;            /* 1: keys were sorted relative to their minimum (fewer passes) */
+    uint32_t reserved;
 };
 void mpsort_comm_last_stats(mpsort_comm_t comm, struct mpsort_last_stats * st,
                             int64_t * sendcounts, int max);

@@ -176,8 +176,10 @@ static uint32_t key_words(const struct mpsort_radix_desc * d)
  * the identity permutation): small ids, 4-byte keys and post-exchange key ranges
  * all profit.
  */
+#define MPS_REBASE_MIN_ITEMS ((size_t) 1 << 20)
+
 static void local_sort(struct mpsort_comm * c, const void * dbase, size_t n, size_t elsize,
-        const struct mpsort_radix_desc * desc, int want_keys, struct sorted_view * out)
+        const struct mpsort_radix_desc * desc, int want_keys, int allow_rebase, struct sorted_view * out)
 {
     const uint32_t nw = key_words(desc);
     uint32_t g, d;
@@ -194,30 +196,57 @@ static void local_sort(struct mpsort_comm * c, const void * dbase, size_t n, siz
     uint32_t * ia = (uint32_t *) mps_arena_get(c, MPS_S_IA, n * sizeof(uint32_t));
     uint32_t * ib = (uint32_t *) mps_arena_get(c, MPS_S_IB, n * sizeof(uint32_t));
     const size_t nhist = (size_t) nw * 8;
-    uint32_t * hist = (uint32_t *) mps_arena_get(c, MPS_S_HIST, nhist * 256 * sizeof(uint32_t) * 2);
+    uint32_t * hist = (uint32_t *) mps_arena_get(c, MPS_S_HIST, nhist * 256 * sizeof(uint32_t) * 2 + 64);
     uint32_t * bins = hist + nhist * 256;
+    uint64_t * minmax = (uint64_t *) (bins + nhist * 256);      /* {min, max} of single-word keys */
     void * scratch = mps_arena_get(c, MPS_S_SCRATCH, mpsk_onesweep_scratch_bytes(n));
+    uint64_t add = 0;
 
     CUDA_OK(c, cudaMemsetAsync(hist, 0, nhist * 256 * sizeof(uint32_t), c->stream));
+    {
+        uint64_t * hmm = (uint64_t *) mps_host_stage(c, nhist * 256 * sizeof(uint32_t) + 64) + (nhist * 256 * sizeof(uint32_t)) / 8;
+        hmm[0] = ~0ULL; hmm[1] = 0;
+        CUDA_OK(c, cudaMemcpyAsync(minmax, hmm, 2 * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    }
     for (g = 0; g < nw; g++) {
         KERN_T(c, MPS_K_EXTRACT, mpsk_extract_keys(dbase, n, elsize, desc->offset, desc->width, desc->nwords,
-                                     desc->is_signed, g, kw + (size_t) g * n, hist + (size_t) g * 8 * 256, c->stream));
+                                     desc->is_signed, g, 0, kw + (size_t) g * n, hist + (size_t) g * 8 * 256, (nw == 1 ? minmax : NULL), c->stream));
     }
     KERN_T(c, MPS_K_EXTRACT, mpsk_scan_histograms(hist, bins, (int) nhist, c->stream));
 
-    /* which digits are constant? (one small D2H per sort) */
-    uint32_t * hhist = (uint32_t *) mps_host_stage(c, nhist * 256 * sizeof(uint32_t));
-    CUDA_OK(c, cudaMemcpyAsync(hhist, hist, nhist * 256 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    /* which digits are constant? (one small D2H per sort; bins and min/max ride along) */
+    uint32_t * hhist = (uint32_t *) mps_host_stage(c, nhist * 256 * sizeof(uint32_t) + 64);
     unsigned char skip[MPS_MAX_KEY_WORDS * 8];
     uint32_t todo = 0;
-    for (g = 0; g < nhist; g++) {
-        uint32_t b;
-        skip[g] = 0;
-        for (b = 0; b < 256; b++) {
-            if (hhist[(size_t) g * 256 + b] == (uint32_t) n) { skip[g] = 1; break; }
+    int round;
+    for (round = 0; round < 2; round++) {
+        CUDA_OK(c, cudaMemcpyAsync(hhist, hist, nhist * 256 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(c, cudaMemcpyAsync((char *) hhist + nhist * 256 * sizeof(uint32_t), minmax, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(c, cudaStreamSynchronize(c->stream));
+        todo = 0;
+        for (g = 0; g < nhist; g++) {
+            uint32_t b;
+            skip[g] = 0;
+            for (b = 0; b < 256; b++) {
+                if (hhist[(size_t) g * 256 + b] == (uint32_t) n) { skip[g] = 1; break; }
+            }
+            if (!skip[g]) todo++;
         }
-        if (!skip[g]) todo++;
+        if (round == 1 || !allow_rebase || nw != 1 || n < MPS_REBASE_MIN_ITEMS || getenv("MPSORT_NO_REBASE")) break;
+        /* Range compression: keys that sit in a narrow range far from zero (small signed
+         * ids are 0x7fff.. / 0x8000.. after the sign flip) vary in every byte, yet
+         * key - min needs only ceil(log256(max - min)) passes. One extra 16 B/key pass
+         * rewrites the keys relative to the minimum and recounts the digits. */
+        const uint64_t * mm = (const uint64_t *) ((char *) hhist + nhist * 256 * sizeof(uint32_t));
+        const uint64_t kmin = mm[0], range = mm[1] - mm[0];
+        uint32_t need = 0;
+        while (need < 8 && (range >> (8 * need)) != 0) need++;
+        if (need + 1 > todo) break;                 /* saves less than one pass */
+        add = kmin;
+        CUDA_OK(c, cudaMemsetAsync(hist, 0, nhist * 256 * sizeof(uint32_t), c->stream));
+        KERN_T(c, MPS_K_EXTRACT, mpsk_extract_keys(kw, n, 8, 0, 8, 1, 0, 0, kmin, kw, hist, NULL, c->stream));
+        KERN_T(c, MPS_K_EXTRACT, mpsk_scan_histograms(hist, bins, (int) nhist, c->stream));
+        c->stats.rebased = 1;
     }
     if (todo == 0) { skip[0] = 0; todo = 1; }  /* all keys equal: one pass yields the identity idx */
 
@@ -256,13 +285,13 @@ static void local_sort(struct mpsort_comm * c, const void * dbase, size_t n, siz
     if (want_keys) {
         if (nw == 1) {
             out->skeys = cur_keys;
-            out->kv.base = cur_keys; out->kv.item_stride = 8; out->kv.word_stride = 0; out->kv.flip = 0;
+            out->kv.base = cur_keys; out->kv.item_stride = 8; out->kv.word_stride = 0; out->kv.flip = 0; out->kv.add = add;
         } else {
             uint64_t * sk = (uint64_t *) mps_arena_get(c, MPS_S_SK, (size_t) nw * n * sizeof(uint64_t));
             for (g = 0; g < nw; g++)
                 KERN_T(c, MPS_K_GATHER_KEYS, mpsk_gather_u64(kw + (size_t) g * n, cur_idx, sk + (size_t) g * n, n, c->stream));
             out->skeys = sk;
-            out->kv.base = sk; out->kv.item_stride = 8; out->kv.word_stride = n * sizeof(uint64_t); out->kv.flip = 0;
+            out->kv.base = sk; out->kv.item_stride = 8; out->kv.word_stride = n * sizeof(uint64_t); out->kv.flip = 0; out->kv.add = 0;
         }
     }
 }
@@ -303,7 +332,7 @@ static void rec16_passes(struct mpsort_comm * c, const void * src, size_t n, con
 #define MPS_HYBRID_MAX_LONG_RUNS 64u
 
 static void local_sort(struct mpsort_comm * c, const void * dbase, size_t n, size_t elsize,
-        const struct mpsort_radix_desc * desc, int want_keys, struct sorted_view * out);
+        const struct mpsort_radix_desc * desc, int want_keys, int allow_rebase, struct sorted_view * out);
 
 /* Does the high part (key >> lobits) look nearly distinct? Sorts 65536 evenly spaced
  * high parts and counts equal pairs c: E[c] = s^2/(2n) * (mean length of the run a
@@ -321,7 +350,7 @@ static int hybrid_predictor(struct mpsort_comm * c, const void * dbase, size_t n
     KERN_T(c, MPS_K_HYBRID, mpsk_sample_prefix_rec16(dbase, n, s, desc->offset == 8, flip, lobits, samp, c->stream));
     struct sorted_view sv;
     const struct mpsort_radix_desc sdesc = { 0, 8, 1, 0, 0 };
-    local_sort(c, samp, s, sizeof(uint64_t), &sdesc, 1, &sv);
+    local_sort(c, samp, s, sizeof(uint64_t), &sdesc, 1, 0, &sv);
     CUDA_OK(c, cudaMemsetAsync(dcount, 0, sizeof(uint64_t), c->stream));
     KERN_T(c, MPS_K_HYBRID, mpsk_count_equal_pairs(sv.skeys, s, dcount, c->stream));
     c->kt.force_cls = saved;
@@ -342,7 +371,7 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
     out->stride = n;
     out->sorted_recs = dest;
     out->kv.base = (const char *) dest + desc->offset;
-    out->kv.item_stride = 16; out->kv.word_stride = 0; out->kv.flip = flip;
+    out->kv.item_stride = 16; out->kv.word_stride = 0; out->kv.flip = flip; out->kv.add = 0;
     if (n == 0) return;
     if (n > MPSK_MAX_ITEMS)
         mps_fatal(c, __FILE__, __LINE__, "%zu local items exceed the supported maximum %zu per rank", n, (size_t) MPSK_MAX_ITEMS);
@@ -351,7 +380,7 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
     uint32_t * bins = hist + 8 * 256;
     void * scratch = mps_arena_get(c, MPS_S_SCRATCH, mpsk_onesweep_scratch_bytes(n));
     CUDA_OK(c, cudaMemsetAsync(hist, 0, 8 * 256 * sizeof(uint32_t), c->stream));
-    KERN_T(c, MPS_K_EXTRACT, mpsk_extract_keys(dbase, n, 16, desc->offset, 8, 1, desc->is_signed, 0, NULL, hist, c->stream));
+    KERN_T(c, MPS_K_EXTRACT, mpsk_extract_keys(dbase, n, 16, desc->offset, 8, 1, desc->is_signed, 0, 0, NULL, hist, NULL, c->stream));
     KERN_T(c, MPS_K_EXTRACT, mpsk_scan_histograms(hist, bins, 8, c->stream));
     uint32_t * hhist = (uint32_t *) mps_host_stage(c, 8 * 256 * sizeof(uint32_t));
     CUDA_OK(c, cudaMemcpyAsync(hhist, hist, 8 * 256 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -462,7 +491,7 @@ static int merge_received_runs(struct mpsort_comm * c, const void * recvbuf, con
     struct sorted_view sv;
     const struct mpsort_radix_desc sdesc = { 0, 8, 1, 0, 0 };
     c->kt.force_cls = MPS_K_MERGE;      /* the sample sort is part of the merge, not a full-size pass */
-    local_sort(c, skeys, ns, sizeof(uint64_t), &sdesc, 1, &sv);
+    local_sort(c, skeys, ns, sizeof(uint64_t), &sdesc, 1, 0, &sv);
     c->kt.force_cls = 0;
     KERN_T(c, MPS_K_MERGE, mpsk_merge_runs(recvbuf, dout, elsize, desc->offset, desc->width, desc->nwords, desc->is_signed,
                                            (uint32_t) p, S, k, rd, ss, sv.skeys, sv.idx, ntiles, cut, overflow, c->stream));
@@ -536,7 +565,7 @@ static void gather_sort(struct mpsort_comm * c, const void * dbase, void * dout,
     char * sorted = (char *) mps_arena_get(c, MPS_S_SEND, (size_t) (c->rank == leader ? total : 0) * elsize);
     if (c->rank == leader) {
         struct sorted_view v;
-        local_sort(c, all, (size_t) total, elsize, desc, 0, &v);
+        local_sort(c, all, (size_t) total, elsize, desc, 0, 1, &v);
         KERN_T(c, MPS_K_GATHER_RECORDS, mpsk_gather_records(all, v.idx, sorted, (size_t) total, elsize, c->stream));
         c->stats.first_sort_passes = v.npasses;
     }
@@ -638,7 +667,7 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
         local_sort_rec16(c, dbase, n, desc, sendbuf, &v1);
         c->stats.record_mode = 1;
     } else {
-        local_sort(c, dbase, n, elsize, desc, p > 1, &v1);
+        local_sort(c, dbase, n, elsize, desc, p > 1, 1, &v1);
     }
     c->stats.first_sort_passes = v1.npasses;
     c->stats.key_words = nw;
@@ -671,7 +700,10 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
                                        sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
         }
         CUDA_OK(c, cudaStreamSynchronize(c->stream));
-        for (w = 0; w < (int) nw; w++) { mine.kmin[w] = h[w] ^ v1.kv.flip; mine.kmax[w] = h[MPS_MAX_KEY_WORDS + w] ^ v1.kv.flip; }
+        for (w = 0; w < (int) nw; w++) {
+            mine.kmin[w] = (h[w] ^ v1.kv.flip) + (w == 0 ? v1.kv.add : 0);
+            mine.kmax[w] = (h[MPS_MAX_KEY_WORDS + w] ^ v1.kv.flip) + (w == 0 ? v1.kv.add : 0);
+        }
     }
     mpsort_comm_allgather_host(c, &mine, info, sizeof(mine));
     uint64_t kmin[MPS_MAX_RANKS * MPS_MAX_KEY_WORDS], kmax[MPS_MAX_RANKS * MPS_MAX_KEY_WORDS];
@@ -777,7 +809,7 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
         for (j = 0; j < p; j++) rdispl[j + 1] = rdispl[j] + (cut[(size_t) j * (p + 1) + c->rank + 1] - cut[(size_t) j * (p + 1) + c->rank]);
         if (merge_received_runs(c, recvbuf, rdispl, dout, outn, elsize, desc) != 0) {
             struct sorted_view v2;
-            local_sort(c, recvbuf, outn, elsize, desc, 0, &v2);
+            local_sort(c, recvbuf, outn, elsize, desc, 0, 1, &v2);
             KERN_T(c, MPS_K_GATHER_RECORDS, mpsk_gather_records(recvbuf, v2.idx, dout, outn, elsize, c->stream));
             c->stats.second_sort_passes = v2.npasses;
         }

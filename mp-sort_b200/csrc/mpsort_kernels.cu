@@ -71,6 +71,7 @@ struct KeyDesc {
     u32 nwords;
     int is_signed;
     u32 g;          /* which packed 64-bit word to produce */
+    u64 sub;        /* subtracted from the packed word (range compression); 0 otherwise */
 };
 
 /* little-endian load of `width` bytes, alignment-safe */
@@ -123,10 +124,10 @@ __device__ __forceinline__ u64 load_key_fast8(const unsigned char * rec, size_t 
  * shared atomics: one OR-reduction of the pairwise differences per batch finds them,
  * lane 0 adds 128 for those, everyone adds 1 per key for the rest. */
 #define EXTRACT_BATCH 4
-template <bool FAST8>
+template <bool FAST8, bool MINMAX, bool INPLACE>
 __global__ void __launch_bounds__(512)
 extract_kernel(const unsigned char * __restrict__ base, size_t n, KeyDesc d,
-               u64 * __restrict__ kout, u32 * __restrict__ hist)
+               u64 * kout, u32 * __restrict__ hist, u64 * __restrict__ minmax)
 {
     __shared__ u32 sh[8 * 256];
     for (u32 t = threadIdx.x; t < 8 * 256; t += blockDim.x) sh[t] = 0;
@@ -136,6 +137,7 @@ extract_kernel(const unsigned char * __restrict__ base, size_t n, KeyDesc d,
     const size_t per_block = (size_t) blockDim.x * EXTRACT_BATCH;
     const size_t nblocks_total = (n + per_block - 1) / per_block;
     const bool lane0 = (threadIdx.x & 31) == 0;
+    u64 kmin = ~0ULL, kmax = 0ULL;
     for (size_t blk = blockIdx.x; blk < nblocks_total; blk += gridDim.x) {
         const size_t i0 = blk * per_block + threadIdx.x;
         u64 k[EXTRACT_BATCH];
@@ -147,9 +149,15 @@ extract_kernel(const unsigned char * __restrict__ base, size_t n, KeyDesc d,
             k[j] = 0;
             if (valid[j]) {
                 const unsigned char * rec = base + i * d.elsize;
-                if (FAST8) k[j] = load_key_fast8(rec, d.offset, flip);
+                if (INPLACE) k[j] = kout[i];              /* rebase pass: bare u64 keys, rewritten in place */
+                else if (FAST8) k[j] = load_key_fast8(rec, d.offset, flip);
                 else k[j] = pack_key_word(rec, d);
+                k[j] -= d.sub;
                 if (kout) kout[i] = k[j];
+                if (MINMAX) {
+                    kmin = k[j] < kmin ? k[j] : kmin;
+                    kmax = k[j] > kmax ? k[j] : kmax;
+                }
             }
         }
         /* the last lane's last key is the first to fall off the end */
@@ -184,30 +192,45 @@ extract_kernel(const unsigned char * __restrict__ base, size_t n, KeyDesc d,
         const u32 c = sh[t];
         if (c) atomicAdd(&hist[t], c);
     }
+    if (MINMAX) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const u64 a = __shfl_xor_sync(FULL_MASK, kmin, o), b = __shfl_xor_sync(FULL_MASK, kmax, o);
+            kmin = a < kmin ? a : kmin;
+            kmax = b > kmax ? b : kmax;
+        }
+        if (lane0) { atomicMin(&minmax[0], kmin); atomicMax(&minmax[1], kmax); }
+    }
 }
 
 extern "C" int mpsk_extract_keys(const void * base, size_t n, size_t elsize,
         size_t offset, uint32_t width, uint32_t nwords, int is_signed,
-        uint32_t g, uint64_t * kout, uint32_t * hist, mpsk_stream_t stream)
+        uint32_t g, uint64_t sub, uint64_t * kout, uint32_t * hist, uint64_t * minmax, mpsk_stream_t stream)
 {
     if (n == 0) return 0;
     KeyDesc d;
     d.elsize = elsize; d.offset = offset; d.width = width; d.nwords = nwords;
-    d.is_signed = is_signed; d.g = g;
+    d.is_signed = is_signed; d.g = g; d.sub = sub;
     const int threads = 512;
     size_t blocks = (n + (size_t) threads * EXTRACT_BATCH - 1) / ((size_t) threads * EXTRACT_BATCH);
     const size_t maxb = (size_t) num_sms() * 8;
     if (blocks > maxb) blocks = maxb;
     const bool fast8 = (width == 8) && (nwords >= 1) && (elsize % 8 == 0)
                        && (offset % 8 == 0) && ((((uintptr_t) base) & 7) == 0);
-    if (fast8) {
+    const unsigned grid = (unsigned) blocks;
+    cudaStream_t st = (cudaStream_t) stream;
+    const unsigned char * pb = (const unsigned char *) base;
+    if (base == (const void *) kout && elsize == 8) {
+        /* in-place rebase of bare u64 keys */
+        extract_kernel<true, false, true><<<grid, threads, 0, st>>>(pb, n, d, (u64 *) kout, hist, (u64 *) minmax);
+    } else if (fast8) {
         /* word g of an 8-byte-word key is simply word g */
         d.offset = offset + (size_t) g * 8;
-        extract_kernel<true><<<(unsigned) blocks, threads, 0, (cudaStream_t) stream>>>(
-            (const unsigned char *) base, n, d, (u64 *) kout, hist);
+        if (minmax) extract_kernel<true, true, false><<<grid, threads, 0, st>>>(pb, n, d, (u64 *) kout, hist, (u64 *) minmax);
+        else extract_kernel<true, false, false><<<grid, threads, 0, st>>>(pb, n, d, (u64 *) kout, hist, (u64 *) minmax);
     } else {
-        extract_kernel<false><<<(unsigned) blocks, threads, 0, (cudaStream_t) stream>>>(
-            (const unsigned char *) base, n, d, (u64 *) kout, hist);
+        if (minmax) extract_kernel<false, true, false><<<grid, threads, 0, st>>>(pb, n, d, (u64 *) kout, hist, (u64 *) minmax);
+        else extract_kernel<false, false, false><<<grid, threads, 0, st>>>(pb, n, d, (u64 *) kout, hist, (u64 *) minmax);
     }
     CUDA_LAUNCH_CHECK();
     return 0;
@@ -1162,7 +1185,7 @@ __device__ __forceinline__ int cmp_key(const mpsk_keyview & v, size_t i, const u
 {
     const unsigned char * p = (const unsigned char *) v.base + i * v.item_stride;
     for (int w = (int) nw - 1; w >= 0; w--) {
-        const u64 k = (*(const u64 *) (p + (size_t) w * v.word_stride)) ^ v.flip;
+        const u64 k = ((*(const u64 *) (p + (size_t) w * v.word_stride)) ^ v.flip) + (w == 0 ? v.add : 0ULL);
         if (k < cand[w]) return -1;
         if (k > cand[w]) return 1;
     }
@@ -1644,7 +1667,7 @@ extern "C" int mpsk_merge_samples(const void * recv, size_t elsize, size_t offse
     for (u32 r = 0; r <= p; r++) { m.rdispl[r] = rdispl[r]; m.sstart[r] = sstart[r]; }
     const u32 ns = sstart[p];
     if (ns == 0) return 0;
-    KeyDesc d; d.elsize = elsize; d.offset = offset; d.width = width; d.nwords = nwords; d.is_signed = is_signed; d.g = 0;
+    KeyDesc d; d.elsize = elsize; d.offset = offset; d.width = width; d.nwords = nwords; d.is_signed = is_signed; d.g = 0; d.sub = 0;
     const bool fast8 = (width == 8) && (nwords == 1) && (elsize % 8 == 0) && (offset % 8 == 0) && ((((uintptr_t) recv) & 7) == 0);
     u32 blocks = (ns + 255) / 256;
     if (blocks > (u32) num_sms() * 8) blocks = (u32) num_sms() * 8;
@@ -1677,7 +1700,7 @@ extern "C" int mpsk_merge_runs(const void * recv, void * out, size_t elsize, siz
     cudaStream_t stream = (cudaStream_t) stream_;
     MergeRuns m; m.p = p; m.S = S; m.k = k;
     for (u32 r = 0; r <= p; r++) { m.rdispl[r] = rdispl[r]; m.sstart[r] = sstart[r]; }
-    KeyDesc d; d.elsize = elsize; d.offset = offset; d.width = width; d.nwords = nwords; d.is_signed = is_signed; d.g = 0;
+    KeyDesc d; d.elsize = elsize; d.offset = offset; d.width = width; d.nwords = nwords; d.is_signed = is_signed; d.g = 0; d.sub = 0;
     const bool fast8 = (width == 8) && (nwords == 1) && (elsize % 8 == 0) && (offset % 8 == 0) && ((((uintptr_t) recv) & 7) == 0);
     const u32 total = (ntiles + 1) * p;
     u32 blocks = (total + 255) / 256;
@@ -1877,7 +1900,7 @@ extern "C" int mpsk_check_sorted(const void * base, size_t n, size_t elsize,
     if (n == 0) return 0;
     KeyDesc d;
     d.elsize = elsize; d.offset = offset; d.width = width; d.nwords = nwords;
-    d.is_signed = is_signed; d.g = 0;
+    d.is_signed = is_signed; d.g = 0; d.sub = 0;
     const u32 nw = (u32) (((size_t) width * nwords + 7) / 8);
     size_t blocks = (n + 255) / 256;
     const size_t maxb = (size_t) num_sms() * 16;

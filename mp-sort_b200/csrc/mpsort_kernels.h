@@ -25,11 +25,13 @@ typedef void * mpsk_stream_t; /* cudaStream_t */
  * Packs key bytes [8*g, 8*g+8) of every record (little-endian over the nwords*width
  * key bytes, signed words sign-flipped) into kout[i] and accumulates the eight
  * 8-bit digit histograms of that word into hist[8][256] (must be zeroed by caller).
- * kout may be NULL (histogram only).
+ * kout may be NULL (histogram only). `sub` is subtracted from every packed word before it
+ * is stored and counted (range compression; kout may then alias base for 8-byte records).
+ * minmax (device u64[2], initialised by the caller to {~0, 0}) receives min and max; may be NULL.
  */
 int mpsk_extract_keys(const void * base, size_t n, size_t elsize,
         size_t offset, uint32_t width, uint32_t nwords, int is_signed,
-        uint32_t g, uint64_t * kout, uint32_t * hist, mpsk_stream_t stream);
+        uint32_t g, uint64_t sub, uint64_t * kout, uint32_t * hist, uint64_t * minmax, mpsk_stream_t stream);
 
 /* Exclusive scan of each of `nhist` 256-bin histograms: hist[h][b] -> bins[h][b]. */
 int mpsk_scan_histograms(const uint32_t * hist, uint32_t * bins, int nhist, mpsk_stream_t stream);
@@ -84,9 +86,10 @@ int mpsk_gather_records(const void * base, const uint32_t * idx, void * out,
         size_t n, size_t elsize, mpsk_stream_t stream);
 
 /* How the splitter kernels see the locally sorted keys: word w of key i is the u64
- * at base + i*item_stride + w*word_stride, XOR flip. SoA key arrays of the index
+ * at base + i*item_stride + w*word_stride, XOR flip, plus `add` for word 0 (keys stored
+ * relative to their minimum by the range compression of single-word keys). SoA key arrays of the index
  * sort: {skeys, 8, n*8, 0}; sorted 16-byte records: {recs + offset, 16, 0, signbit}. */
-struct mpsk_keyview { const void * base; size_t item_stride; size_t word_stride; uint64_t flip; };
+struct mpsk_keyview { const void * base; size_t item_stride; size_t word_stride; uint64_t flip; uint64_t add; };
 
 /* K4: splitter counting on the sorted keys. Replaces _histogram/_bsearch_last_lt/le
  * (internal-parallel.h:8-126).

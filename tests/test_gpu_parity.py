@@ -167,6 +167,35 @@ def test_hybrid_declined_for_clustered_keys():
     assert np.array_equal(got, a[np.argsort(a["key"], kind="stable")])
 
 
+def test_range_compression_of_narrow_key_ranges():
+    """index mode, single-word keys in a narrow range far from zero (small signed ids
+    vary in every byte after the sign flip): sorted relative to their minimum with
+    fewer passes; same bytes as without, also across ranks (splitters see real keys)"""
+    rng = np.random.default_rng(77)
+    dt = np.dtype([("key", "i8"), ("tag", "u8"), ("pad", "u8")])         # 24 bytes: index mode
+    n = (1 << 20) + 77
+    a = np.zeros(n, dtype=dt)
+    a["key"] = rng.integers(-(1 << 20), 1 << 24, size=n)
+    a["tag"] = np.arange(n)
+    got, st = _sort_single(a, C.RadixDesc(0, 8, 1, 1, 0))
+    assert st["record_mode"] == 0 and st["rebased"] == 1 and st["first_sort_passes"] == 4
+    exp = a[np.argsort(a["key"], kind="stable")]
+    assert np.array_equal(got, exp)
+    os.environ["MPSORT_NO_REBASE"] = "1"
+    try:
+        got2, st2 = _sort_single(a, C.RadixDesc(0, 8, 1, 1, 0))
+    finally:
+        del os.environ["MPSORT_NO_REBASE"]
+    assert st2["rebased"] == 0 and st2["first_sort_passes"] == 8 and np.array_equal(got2, exp)
+    # 3 ranks, different local minima
+    parts = [a[:400000], a[400000:400000 + (1 << 20) // 2], a[400000 + (1 << 20) // 2:]]
+    parts[1]["key"] += 5000000
+    recs = [O.as_bytes(x) for x in parts]
+    outs = [len(x) for x in parts]
+    out, stats = sort_group(recs, outs, O.Desc(0, 8, 1, 1, 0), C.MPSORT_DISABLE_GATHER_SORT)
+    assert same(out, O.numpy_sort(recs, O.Desc(0, 8, 1, 1, 0), outs))
+
+
 def test_record_mode_equals_index_mode():
     rng = np.random.default_rng(8)
     dt = np.dtype([("tag", "u8"), ("key", "i8")])
