@@ -185,7 +185,7 @@ struct mpsort_last_stats {
     uint32_t hybrid;             /* 1: four high-digit passes + run fix-up instead of all passes */
     uint32_t hybrid_long_runs;   /* runs of > 256 equal high parts that were sorted separately */
     uint32_t rebased;            /* 1: keys were sorted relative to their minimum (fewer passes) */
-    uint32_t reserved;
+    uint32_t p2p_exchange;       /* 1: records moved by peer stores (CUDA IPC), 0: ncclSend/ncclRecv or copies */
 };
 void mpsort_comm_last_stats(mpsort_comm_t comm, struct mpsort_last_stats * st,
                             int64_t * sendcounts, int max);

@@ -84,6 +84,15 @@ void * mps_arena_get(struct mpsort_comm * c, int slot, size_t bytes)
 {
     if (bytes == 0) bytes = 256;
     if (c->slot[slot].cap >= bytes) return c->slot[slot].ptr;
+    if (c->slot[slot].ptr && slot == (c->p2p.pull ? MPS_S_SEND : MPS_S_RECV) && c->kind == MPS_T_NCCL && !c->p2p.disabled && c->p2p.nzombies < 64) {
+        /* peers may still have this buffer mapped (CUDA IPC): it is freed when the
+         * communicator is destroyed, not now. Growth is rare (grow-only, 25 % headroom). */
+        CUDA_OK(c, cudaStreamSynchronize(c->stream));
+        c->p2p.zombies[c->p2p.nzombies++] = c->slot[slot].ptr;
+        c->slot[slot].ptr = NULL;
+        c->slot[slot].cap = 0;
+        bytes += bytes / 4;
+    }
     if (c->slot[slot].ptr) {
         /* buffers may still be in use by work queued on the stream */
         CUDA_OK(c, cudaStreamSynchronize(c->stream));
@@ -209,6 +218,8 @@ mpsort_comm_t mpsort_comm_init_rank(int rank, int size, const void * unique_id, 
     ncclUniqueId uid;
     memcpy(&uid, unique_id, sizeof(uid));
     NCCL_OK(c, ncclCommInitRank(&c->nccl, size, uid, rank));
+    c->p2p.disabled = getenv("MPSORT_NO_P2P") ? 1 : 0;
+    c->p2p.pull = getenv("MPSORT_P2P_PULL") ? 1 : 0;
     return c;
 }
 
@@ -254,8 +265,13 @@ void mpsort_comm_destroy(mpsort_comm_t c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (s = 0; s < c->size && c->kind == MPS_T_NCCL; s++)
+        if (c->p2p.peer_base[s]) cudaIpcCloseMemHandle(c->p2p.peer_base[s]);
+    if (c->kind == MPS_T_NCCL && c->size > 1) mpsort_comm_barrier(c);   /* everyone unmapped before anyone frees */
+    for (s = 0; s < c->p2p.nzombies; s++) cudaFree(c->p2p.zombies[s]);
     for (s = 0; s < MPS_NSLOTS; s++) if (c->slot[s].ptr) cudaFree(c->slot[s].ptr);
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->p2p.d_flag) cudaFree(c->p2p.d_flag);
     if (c->kind == MPS_T_NCCL && c->nccl) ncclCommDestroy(c->nccl);
     if (c->kind == MPS_T_LOCAL && c->grp) {
         int last;
@@ -465,4 +481,117 @@ void mps_comm_alltoallv_dev(struct mpsort_comm * c, const void * sendbuf, void *
     local_barrier(c);   /* sources may reuse their send buffers */
     if (bytes_remote) *bytes_remote = remote;   /* bytes pulled, equals bytes pushed in total */
 #undef CUT
+}
+
+/* ------------------------------------------------------------------------- */
+/* peer-store exchange                                                        */
+
+void mps_comm_recv_info(struct mpsort_comm * c, void * recvbuf, void * sendbuf, struct mps_recv_info * info)
+{
+    memset(info, 0, sizeof(*info));
+    if (c->kind != MPS_T_NCCL || c->p2p.disabled) return;
+    /* pull: peers read my send buffer; push: peers write my receive buffer */
+    void * buf = c->p2p.pull ? sendbuf : recvbuf;
+    info->ptr = (uint64_t) (uintptr_t) buf;
+    info->cap = c->slot[c->p2p.pull ? MPS_S_SEND : MPS_S_RECV].cap;
+    cudaIpcMemHandle_t hdl;
+    if (cudaIpcGetMemHandle(&hdl, buf) != cudaSuccess) {
+        cudaGetLastError();
+        info->ptr = 0;               /* tells everyone: no peer stores */
+        return;
+    }
+    memcpy(info->handle, &hdl, sizeof(hdl) <= sizeof(info->handle) ? sizeof(hdl) : sizeof(info->handle));
+}
+
+int mps_comm_p2p_prepare(struct mpsort_comm * c, const struct mps_recv_info * all)
+{
+    int j, changed = 0, ok = 1;
+    if (c->kind != MPS_T_NCCL || c->p2p.disabled) return 0;
+    for (j = 0; j < c->size; j++) if (all[j].ptr == 0) ok = 0;       /* same table on every rank */
+    if (!ok) { c->p2p.disabled = 1; return 0; }
+    for (j = 0; j < c->size; j++) {
+        /* my own entry counts too: every rank must reach the same verdict */
+        if (c->p2p.peer_ptr[j] == all[j].ptr) continue;
+        changed = 1;
+    }
+    /* every rank sees the same table and has the same history: `changed` agrees everywhere */
+    if (!changed) return 1;
+    int mine_ok = 1;
+    c->p2p.peer_ptr[c->rank] = all[c->rank].ptr;
+    for (j = 0; j < c->size; j++) {
+        if (j == c->rank) continue;
+        if (c->p2p.peer_ptr[j] == all[j].ptr && c->p2p.peer_base[j]) continue;
+        if (c->p2p.peer_base[j]) { cudaIpcCloseMemHandle(c->p2p.peer_base[j]); c->p2p.peer_base[j] = NULL; }
+        cudaIpcMemHandle_t hdl;
+        memcpy(&hdl, all[j].handle, sizeof(hdl));
+        void * p = NULL;
+        if (cudaIpcOpenMemHandle(&p, hdl, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            mine_ok = 0;
+            break;
+        }
+        c->p2p.peer_base[j] = p;
+        c->p2p.peer_ptr[j] = all[j].ptr;
+    }
+    /* collective agreement: one rank that cannot map switches everyone back to NCCL */
+    char flag = (char) mine_ok, flags[MPS_MAX_RANKS];
+    mpsort_comm_allgather_host(c, &flag, flags, 1);
+    for (j = 0; j < c->size; j++) if (!flags[j]) ok = 0;
+    if (!ok) {
+        for (j = 0; j < c->size; j++) if (c->p2p.peer_base[j]) { cudaIpcCloseMemHandle(c->p2p.peer_base[j]); c->p2p.peer_base[j] = NULL; }
+        c->p2p.disabled = 1;
+        if (c->rank == 0) fprintf(stderr, "MPSort: CUDA IPC mapping of peer buffers failed; exchanging with ncclSend/ncclRecv\n");
+        return 0;
+    }
+    return 1;
+}
+
+void mps_comm_alltoallv_p2p(struct mpsort_comm * c, const void * sendbuf, void * recvbuf,
+        const int64_t * cut, size_t elsize, uint64_t * bytes_remote)
+{
+    const int p = c->size, me = c->rank;
+    int k, j;
+    const void * src[MPS_MAX_RANKS];
+    void * dst[MPS_MAX_RANKS];
+    uint64_t bytes[MPS_MAX_RANKS], remote = 0;
+    unsigned char isremote[MPS_MAX_RANKS];
+#define CUT(j, k) cut[(size_t) (j) * (p + 1) + (k)]
+    if (!c->p2p.d_flag) {
+        CUDA_OK(c, cudaMalloc((void **) &c->p2p.d_flag, 256));
+        CUDA_OK(c, cudaMemsetAsync(c->p2p.d_flag, 0, 256, c->stream));
+    }
+    if (c->p2p.pull) {
+        /* every rank's send buffer must be complete before anyone reads it */
+        NCCL_OK(c, ncclAllReduce(c->p2p.d_flag, c->p2p.d_flag, 1, ncclInt32, ncclSum, c->nccl, c->stream));
+        int64_t rd = 0;
+        for (k = 0; k < p; k++) {
+            /* rank k's slice for me, read from its (mapped) send buffer */
+            const int64_t cnt = CUT(k, me + 1) - CUT(k, me);
+            src[k] = (const char *) (k == me ? sendbuf : c->p2p.peer_base[k]) + (size_t) CUT(k, me) * elsize;
+            dst[k] = (char *) recvbuf + (size_t) rd * elsize;
+            bytes[k] = (uint64_t) cnt * elsize;
+            isremote[k] = (unsigned char) (k != me);
+            rd += cnt;
+            if (k != me) remote += (uint64_t) (CUT(me, k + 1) - CUT(me, k)) * elsize;
+        }
+    } else {
+        for (k = 0; k < p; k++) {
+            /* where my slice lands in rank k's receive buffer: after the slices of ranks < me */
+            int64_t rd = 0;
+            for (j = 0; j < me; j++) rd += CUT(j, k + 1) - CUT(j, k);
+            const int64_t cnt = CUT(me, k + 1) - CUT(me, k);
+            src[k] = (const char *) sendbuf + (size_t) CUT(me, k) * elsize;
+            dst[k] = (char *) (k == me ? recvbuf : c->p2p.peer_base[k]) + (size_t) rd * elsize;
+            bytes[k] = (uint64_t) cnt * elsize;
+            isremote[k] = (unsigned char) (k != me);
+            if (k != me) remote += bytes[k];
+        }
+    }
+#undef CUT
+    KERN_OK(c, mpsk_p2p_alltoallv(src, dst, bytes, isremote, p, c->stream));
+    /* push: all stores into my buffer are complete when everyone's kernel is; pull: nobody
+     * may reuse its send buffer before everyone has read it. A one-word all-reduce on the
+     * stream is the barrier (stream ordered, no host involvement). */
+    NCCL_OK(c, ncclAllReduce(c->p2p.d_flag, c->p2p.d_flag, 1, ncclInt32, ncclSum, c->nccl, c->stream));
+    if (bytes_remote) *bytes_remote = remote;
 }

@@ -754,13 +754,26 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
 
     /* ---- LayDistr: all-gather the local rows (replaces the 8-byte Alltoalls :450-456) */
     int64_t * rows = (int64_t *) malloc(sizeof(int64_t) * 2 * (size_t) ns * p);
+    void * recvbuf = mps_arena_get(c, MPS_S_RECV, outn * elsize);
+    int use_p2p = 0;
     {
+        /* one message per rank: its (CLT, CLE) row and how to reach its receive buffer */
+        struct lay_msg { int64_t row[2 * MPS_MAX_RANKS]; struct mps_recv_info recv; };
+        struct lay_msg mymsg, * allmsg = (struct lay_msg *) malloc(sizeof(struct lay_msg) * (size_t) p);
+        struct mps_recv_info * allrecv = (struct mps_recv_info *) malloc(sizeof(struct mps_recv_info) * (size_t) p);
         int64_t * h = (int64_t *) mps_host_stage(c, 2 * (size_t) ns * sizeof(int64_t));
         CUDA_OK(c, cudaMemcpyAsync(h, d_final, 2 * (size_t) ns * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
         CUDA_OK(c, cudaStreamSynchronize(c->stream));
-        int64_t myrow[2 * MPS_MAX_RANKS];
-        memcpy(myrow, h, 2 * (size_t) ns * sizeof(int64_t));
-        mpsort_comm_allgather_host(c, myrow, rows, 2 * (size_t) ns * sizeof(int64_t));
+        memset(&mymsg, 0, sizeof(mymsg));
+        memcpy(mymsg.row, h, 2 * (size_t) ns * sizeof(int64_t));
+        mps_comm_recv_info(c, recvbuf, sendbuf, &mymsg.recv);
+        mpsort_comm_allgather_host(c, &mymsg, allmsg, sizeof(mymsg));
+        for (j = 0; j < p; j++) {
+            memcpy(rows + (size_t) j * 2 * ns, allmsg[j].row, 2 * (size_t) ns * sizeof(int64_t));
+            allrecv[j] = allmsg[j].recv;
+        }
+        use_p2p = mps_comm_p2p_prepare(c, allrecv);
+        free(allmsg); free(allrecv);
     }
     timer_mark(c, "LayDistr");
 
@@ -789,7 +802,6 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
     /* ---- Exchange: pack (payload gather into destination-contiguous order; the
      * destinations are contiguous slices of the sorted order, SendDispl[i] == myC[i]
      * :483-501) then grouped send/recv */
-    void * recvbuf = mps_arena_get(c, MPS_S_RECV, outn * elsize);
     if (v1.sorted_recs != sendbuf)
         KERN_T(c, MPS_K_GATHER_RECORDS, mpsk_gather_records(dbase, v1.idx, sendbuf, n, elsize, c->stream));
     timer_mark(c, "Pack");
@@ -797,8 +809,10 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
                       && !mpsort_mpi_has_options(MPSORT_REQUIRE_SPARSE_ALLTOALLV);
     c->stats.dense_exchange = (uint32_t) dense;
     mps_kt_begin(c, MPS_K_EXCHANGE);
-    mps_comm_alltoallv_dev(c, sendbuf, recvbuf, cut, elsize, dense, &c->stats.bytes_sent_remote);
+    if (use_p2p) mps_comm_alltoallv_p2p(c, sendbuf, recvbuf, cut, elsize, &c->stats.bytes_sent_remote);
+    else mps_comm_alltoallv_dev(c, sendbuf, recvbuf, cut, elsize, dense, &c->stats.bytes_sent_remote);
     mps_kt_end(c);
+    c->stats.p2p_exchange = (uint32_t) use_p2p;
     timer_mark(c, "Exchange");
 
     /* ---- SecondSort: the received buffer is p sorted runs in source-rank order;

@@ -95,7 +95,25 @@ struct mpsort_comm {
     struct mpsort_last_stats stats;
     int64_t sendcounts[MPS_MAX_RANKS];
     struct mps_ktimes kt;
+
+    /* peer-store exchange (NCCL transport only): every rank's receive buffer mapped here */
+    struct {
+        int disabled;                          /* env MPSORT_NO_P2P, or a mapping failed somewhere */
+        int pull;                              /* 1: read peers' send buffers, 0: write peers' receive buffers */
+        void * peer_base[MPS_MAX_RANKS];       /* my mapping of rank j's exchange buffer */
+        uint64_t peer_ptr[MPS_MAX_RANKS];      /* rank j's own pointer the mapping belongs to */
+        void * zombies[64];                    /* my old receive buffers peers may still have mapped */
+        int nzombies;
+        int * d_flag;                          /* device word for the completion all-reduce */
+    } p2p;
 };
+
+/* what every rank tells the others about its receive buffer during LayDistr */
+struct mps_recv_info { uint64_t ptr; uint64_t cap; unsigned char handle[64]; };
+void mps_comm_recv_info(struct mpsort_comm * c, void * recvbuf, void * sendbuf, struct mps_recv_info * info);
+/* after the all-gather: (re)map peers whose buffer changed; returns 1 if the peer-store
+ * exchange can be used by ALL ranks this call (collective decision) */
+int mps_comm_p2p_prepare(struct mpsort_comm * c, const struct mps_recv_info * all);
 
 void mps_kt_begin(struct mpsort_comm * c, int cls);
 void mps_kt_end(struct mpsort_comm * c);
@@ -126,6 +144,9 @@ void mps_comm_allreduce_u64_dev(struct mpsort_comm * c, uint64_t * dptr, size_t 
  * goes to rank k (full matrix, known on every rank) */
 void mps_comm_alltoallv_dev(struct mpsort_comm * c, const void * sendbuf, void * recvbuf,
         const int64_t * cut, size_t elsize, int dense, uint64_t * bytes_remote);
+/* the same exchange as peer stores; valid only after mps_comm_p2p_prepare returned 1 */
+void mps_comm_alltoallv_p2p(struct mpsort_comm * c, const void * sendbuf, void * recvbuf,
+        const int64_t * cut, size_t elsize, uint64_t * bytes_remote);
 
 /* ---- layout solver (mpsort_layout.c; pure host arithmetic, unit-testable) ---- */
 /* C[p+1] desired cumulative output counts; clt/cle[j*(p-1) + b] local counts of rank j

@@ -140,6 +140,14 @@ int mpsk_merge_runs(const void * recv, void * out, size_t elsize, size_t offset,
         const uint64_t * sorted_skeys, const uint32_t * sorted_sid, uint32_t ntiles,
         uint32_t * cut, uint32_t * overflow, mpsk_stream_t stream);
 
+/* K6: the record exchange as peer stores (replaces MPI_Alltoallv and its sparse variant,
+ * mp-mpiu.c:69-236, inside one box): segment k copies bytes[k] from src[k] (local) to
+ * dst[k] (a peer's receive buffer mapped with CUDA IPC, or local memory); empty segments
+ * are skipped; remote[k] != 0 marks peer destinations. One kernel, CTAs dealt to segments
+ * by their expected time. */
+int mpsk_p2p_alltoallv(const void * const * src, void * const * dst, const uint64_t * bytes,
+        const unsigned char * remote, int nseg, mpsk_stream_t stream);
+
 /* K8: reference checksum (mpsort-mpi.c:148-159): sum of all bytes as SIGNED chars,
  * wrapping in 64 bits; accumulated (atomicAdd) into *sum which the caller zeroes. */
 int mpsk_checksum(const void * base, size_t nbytes, uint64_t * sum, mpsk_stream_t stream);
