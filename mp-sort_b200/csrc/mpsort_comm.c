@@ -218,7 +218,10 @@ mpsort_comm_t mpsort_comm_init_rank(int rank, int size, const void * unique_id, 
     ncclUniqueId uid;
     memcpy(&uid, unique_id, sizeof(uid));
     NCCL_OK(c, ncclCommInitRank(&c->nccl, size, uid, rank));
-    c->p2p.disabled = getenv("MPSORT_NO_P2P") ? 1 : 0;
+    /* peer stores beat NCCL send/recv at 2 GPUs (590 vs 543 GB/s) but not at 4 and 8
+     * (570 vs 619 GB/s at 8; profiles/r01_p2p_exchange.log): default on for pairs only,
+     * MPSORT_P2P=1 forces them for any size, MPSORT_NO_P2P=1 turns them off */
+    c->p2p.disabled = (getenv("MPSORT_NO_P2P") || (size > 2 && !getenv("MPSORT_P2P"))) ? 1 : 0;
     c->p2p.pull = getenv("MPSORT_P2P_PULL") ? 1 : 0;
     return c;
 }
@@ -588,7 +591,18 @@ void mps_comm_alltoallv_p2p(struct mpsort_comm * c, const void * sendbuf, void *
         }
     }
 #undef CUT
-    KERN_OK(c, mpsk_p2p_alltoallv(src, dst, bytes, isremote, p, c->stream));
+    {
+        /* segments in shifted order: me+1, me+2, ..., me (self last) */
+        const void * rsrc[MPS_MAX_RANKS];
+        void * rdst[MPS_MAX_RANKS];
+        uint64_t rbytes[MPS_MAX_RANKS];
+        unsigned char rrem[MPS_MAX_RANKS];
+        for (k = 0; k < p; k++) {
+            const int q = (me + 1 + k) % p;
+            rsrc[k] = src[q]; rdst[k] = dst[q]; rbytes[k] = bytes[q]; rrem[k] = isremote[q];
+        }
+        KERN_OK(c, mpsk_p2p_alltoallv(rsrc, rdst, rbytes, rrem, p, c->stream));
+    }
     /* push: all stores into my buffer are complete when everyone's kernel is; pull: nobody
      * may reuse its send buffer before everyone has read it. A one-word all-reduce on the
      * stream is the barrier (stream ordered, no host involvement). */

@@ -1776,13 +1776,38 @@ p2p_copy_kernel(P2PPlan plan)
     __threadfence_system();        /* peer stores performed before the kernel is seen as done */
 }
 
+/* the same copy with the whole grid on ONE segment at a time, segments in the caller's
+ * order (rotated by rank: the classic shifted all-to-all schedule, every GPU sends to
+ * one peer and receives from one peer at a time) */
+template <typename V>
+__global__ void __launch_bounds__(512)
+p2p_copy_seq_kernel(P2PPlan plan)
+{
+    constexpr int U = 4;
+    const size_t stride = (size_t) gridDim.x * blockDim.x * U;
+    for (int k = 0; k < plan.nseg; k++) {
+        const V * __restrict__ src = (const V *) plan.src[k];
+        V * __restrict__ dst = (V *) plan.dst[k];
+        const size_t nv = plan.bytes[k] / sizeof(V);
+        for (size_t i0 = ((size_t) blockIdx.x * blockDim.x) * U + threadIdx.x; i0 < nv; i0 += stride) {
+            V v[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) { const size_t i = i0 + (size_t) u * blockDim.x; if (i < nv) v[u] = src[i]; }
+#pragma unroll
+            for (int u = 0; u < U; u++) { const size_t i = i0 + (size_t) u * blockDim.x; if (i < nv) dst[i] = v[u]; }
+        }
+    }
+    __threadfence_system();
+}
+
 extern "C" int mpsk_p2p_alltoallv(const void * const * src, void * const * dst, const uint64_t * bytes,
         const unsigned char * remote, int nseg, mpsk_stream_t stream)
 {
     /* CTAs are dealt by bytes; weighting remote bytes higher did not help (profiles/r01_p2p_exchange.log) */
-    static int wremote = -1, cta_mult = -1;
+    static int wremote = -1, cta_mult = -1, sequential = -1;
+    if (sequential < 0) sequential = getenv("MPSORT_P2P_SEQUENTIAL") ? 1 : 0;
     if (wremote < 0) { const char * e = getenv("MPSORT_P2P_REMOTE_WEIGHT"); wremote = e ? atoi(e) : 1; }
-    if (cta_mult < 0) { const char * e = getenv("MPSORT_P2P_CTAS_PER_SM"); cta_mult = e ? atoi(e) : 4; }
+    if (cta_mult < 0) { const char * e = getenv("MPSORT_P2P_CTAS_PER_SM"); cta_mult = e ? atoi(e) : (nseg > 2 ? 1 : 4); }
     double weight[MPSK_P2P_MAX_SEGS];
     if (nseg > MPSK_P2P_MAX_SEGS) return (int) cudaErrorInvalidValue;
     P2PPlan plan;
@@ -1811,6 +1836,14 @@ extern "C" int mpsk_p2p_alltoallv(const void * const * src, void * const * dst, 
     }
     plan.cta_begin[n] = acc;
     cudaStream_t st = (cudaStream_t) stream;
+    if (sequential) {
+        if ((align & 15) == 0) p2p_copy_seq_kernel<uint4><<<G, 512, 0, st>>>(plan);
+        else if ((align & 7) == 0) p2p_copy_seq_kernel<u64><<<G, 512, 0, st>>>(plan);
+        else if ((align & 3) == 0) p2p_copy_seq_kernel<u32><<<G, 512, 0, st>>>(plan);
+        else p2p_copy_seq_kernel<unsigned char><<<G, 512, 0, st>>>(plan);
+        CUDA_LAUNCH_CHECK();
+        return 0;
+    }
     if ((align & 15) == 0) p2p_copy_kernel<uint4><<<acc, 512, 0, st>>>(plan);
     else if ((align & 7) == 0) p2p_copy_kernel<u64><<<acc, 512, 0, st>>>(plan);
     else if ((align & 3) == 0) p2p_copy_kernel<u32><<<acc, 512, 0, st>>>(plan);
