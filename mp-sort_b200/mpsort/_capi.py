@@ -16,6 +16,13 @@ if not os.path.exists(LIB_PATH):
         "`python -c 'import __graft_entry__ as g; g.build()'`); there is no CPU fallback."
         % (LIB_PATH, os.path.dirname(_HERE)))
 
+# libmpsort-b200.so links libnccl.so.2 dynamically. A process that ALSO imports PyTorch must
+# end up with one NCCL: either import torch first (its bundled, newer NCCL is then shared), or
+# point MPSORT_NCCL_LIB at the libnccl.so.2 to preload (e.g. site-packages/nvidia/nccl/lib/).
+_nccl = os.environ.get("MPSORT_NCCL_LIB")
+if _nccl:
+    ctypes.CDLL(_nccl, mode=ctypes.RTLD_GLOBAL)
+
 lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
 
 c_void_p = ctypes.c_void_p

@@ -75,7 +75,9 @@ def _worker(rank, world, port, distinct, q):
 
 @pytest.mark.parametrize("world,distinct", [(2, None), (2, 3), (3, 5)])
 def test_layout_and_exchange_over_gloo(world, distinct):
-    import torch.multiprocessing as mp
+    # stdlib multiprocessing: the parent must not import torch (it may already hold the
+    # system NCCL through libmpsort-b200.so; torch wants its own newer one)
+    import multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29600 + world * 7 + (distinct or 0)
