@@ -494,10 +494,13 @@ onesweep_kernel(const u64 * __restrict__ kin, const u32 * __restrict__ vin,
     u32 rank[IPT];
     u32 * my_hist = s_whist + warp * 256;
     const u32 lt = lanemask_lt();
+    u32 peers_of[IPT];                 /* all ballots first: off the serial histogram chain */
+#pragma unroll
+    for (int j = 0; j < IPT; j++) peers_of[j] = match_digit((u32) (key[j] >> shift) & 255u);
 #pragma unroll
     for (int j = 0; j < IPT; j++) {
         const u32 digit = (u32) (key[j] >> shift) & 255u;
-        const u32 peers = match_digit(digit);
+        const u32 peers = peers_of[j];
         const u32 leader = __ffs(peers) - 1;
         u32 c = 0;
         if (lane == leader) {
@@ -727,14 +730,18 @@ onesweep_rec16_kernel(const uint4 * __restrict__ in, uint4 * __restrict__ out,
         }
     }
 
-    /* ---- rank inside (warp, digit) */
+    /* ---- rank inside (warp, digit). The eight ballots of every row are independent of
+     * the serial histogram update below: issue them all first so their latency overlaps. */
     u32 rank[IPT];
     u32 * my_hist = s_whist + warp * 256;
     const u32 lt = lanemask_lt();
+    u32 peers_of[IPT];
+#pragma unroll
+    for (int j = 0; j < IPT; j++) peers_of[j] = match_digit(rec_digit(it[j], khi, flip, shift));
 #pragma unroll
     for (int j = 0; j < IPT; j++) {
         const u32 digit = rec_digit(it[j], khi, flip, shift);
-        const u32 peers = match_digit(digit);
+        const u32 peers = peers_of[j];
         const u32 leader = __ffs(peers) - 1;
         u32 c = 0;
         if (lane == leader) {
