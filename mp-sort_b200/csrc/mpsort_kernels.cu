@@ -1502,19 +1502,22 @@ merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, bool fast8
                 const u32 mid = (lo + hi) >> 1;
                 if (kA[MPD(a0 + mid)] <= kA[MPD(a1 + diag - 1 - mid)]) lo = mid + 1; else hi = mid;
             }
-            u32 ai = lo, bi = diag - lo;
-            u64 ka = ai < lenA ? kA[MPD(a0 + ai)] : 0, kb = bi < lenB ? kA[MPD(a1 + bi)] : 0;
+            /* branch-free sequential merge: both candidates (key, source) live in registers,
+             * the one taken is replaced by its successor (index clamped at the sequence end) */
+            u32 ai = a0 + lo, bi = a1 + (diag - lo);            /* absolute positions */
+            u64 ka = kA[MPD(min(ai, b1 - 1))], kb = kA[MPD(min(bi, b1 - 1))];
+            u32 sa = sA[MPD(min(ai, b1 - 1))], sb = sA[MPD(min(bi, b1 - 1))];
             for (; o < seg_end; o++) {
-                const bool takeA = (bi >= lenB) || (ai < lenA && ka <= kb);
-                if (takeA) {
-                    kB[MPD(o)] = ka; sB[MPD(o)] = sA[MPD(a0 + ai)];
-                    ai++;
-                    if (ai < lenA) ka = kA[MPD(a0 + ai)];
-                } else {
-                    kB[MPD(o)] = kb; sB[MPD(o)] = sA[MPD(a1 + bi)];
-                    bi++;
-                    if (bi < lenB) kb = kA[MPD(a1 + bi)];
-                }
+                const bool takeA = (bi >= b1) || (ai < a1 && ka <= kb);
+                kB[MPD(o)] = takeA ? ka : kb;
+                sB[MPD(o)] = takeA ? sa : sb;
+                ai += takeA ? 1u : 0u;
+                bi += takeA ? 0u : 1u;
+                const u32 nxt = min(takeA ? ai : bi, b1 - 1);
+                const u64 nk = kA[MPD(nxt)];
+                const u32 ns = sA[MPD(nxt)];
+                ka = takeA ? nk : ka; sa = takeA ? ns : sa;
+                kb = takeA ? kb : nk; sb = takeA ? sb : ns;
             }
         }
         __syncthreads();
