@@ -1459,12 +1459,12 @@ merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, bool fast8
     {
         u32 src[VT];
         u64 key[VT];
+        u32 r = 0;                                  /* a thread's positions increase: the run index only moves up */
 #pragma unroll
         for (int k = 0; k < VT; k++) {
             const u32 i = tid + k * MPSK_MERGE_THREADS;
             src[k] = 0;
             if (i < cnt) {
-                u32 r = 0;
                 while (i >= seqoff[r + 1]) r++;
                 src[k] = srcbase[r] + (i - seqoff[r]);
             }
