@@ -305,23 +305,25 @@ static void local_sort(struct mpsort_comm * c, const void * dbase, size_t n, siz
 static int rec16_applicable(size_t elsize, const struct mpsort_radix_desc * d, const void * dbase, const void * dest)
 {
     if (getenv("MPSORT_NO_REC16")) return 0;
-    return elsize == 16 && d->nwords == 1 && d->width == 8 && (d->offset == 0 || d->offset == 8)
-           && ((((uintptr_t) dbase) | ((uintptr_t) dest)) & 15) == 0;
+    if (d->nwords != 1 || d->width != 8) return 0;
+    if (elsize == 16) return (d->offset == 0 || d->offset == 8) && ((((uintptr_t) dbase) | ((uintptr_t) dest)) & 15) == 0;
+    if (elsize == 8) return d->offset == 0 && ((((uintptr_t) dbase) | ((uintptr_t) dest)) & 7) == 0;   /* bare keys */
+    return 0;
 }
 
 /* P stable passes over the given digits, source `src` (read only unless it is also
  * the destination), result in `dest`; `Y` and the KB slot are the ping-pong temps */
-static void rec16_passes(struct mpsort_comm * c, const void * src, size_t n, const struct mpsort_radix_desc * desc,
+static void rec16_passes(struct mpsort_comm * c, const void * src, size_t n, size_t E, const struct mpsort_radix_desc * desc,
         void * dest, const int * digits, int P, const uint32_t * bins, void * scratch)
 {
     const uint64_t flip = desc->is_signed ? (1ULL << 63) : 0ULL;
-    void * Y = mps_arena_get(c, MPS_S_KW, n * 16);
+    void * Y = mps_arena_get(c, MPS_S_KW, n * E);
     int i;
     for (i = 0; i < P; i++) {
         const int remaining_after = P - 1 - i;
         void * tgt = (remaining_after % 2 == 0) ? dest : Y;
-        if (tgt == src) tgt = mps_arena_get(c, MPS_S_KB, n * 16);   /* first pass of an odd in-place chain */
-        KERN_T(c, MPS_K_ONESWEEP_REC, mpsk_onesweep_pass_rec16(src, tgt, n, 8 * digits[i], desc->offset == 8, flip,
+        if (tgt == src) tgt = mps_arena_get(c, MPS_S_KB, n * E);   /* first pass of an odd in-place chain */
+        KERN_T(c, MPS_K_ONESWEEP_REC, mpsk_onesweep_pass_rec(src, tgt, n, E, 8 * digits[i], desc->offset == 8, flip,
                                                               bins + (size_t) digits[i] * 256, scratch, c->stream));
         src = tgt;
     }
@@ -338,7 +340,7 @@ static void local_sort(struct mpsort_comm * c, const void * dbase, size_t n, siz
  * high parts and counts equal pairs c: E[c] = s^2/(2n) * (mean length of the run a
  * random record sits in). The run fix-up costs that many comparisons per record, so
  * the hybrid is taken while the estimate stays below 16. */
-static int hybrid_predictor(struct mpsort_comm * c, const void * dbase, size_t n,
+static int hybrid_predictor(struct mpsort_comm * c, const void * dbase, size_t n, size_t E,
         const struct mpsort_radix_desc * desc, uint32_t lobits)
 {
     const uint64_t flip = desc->is_signed ? (1ULL << 63) : 0ULL;
@@ -347,7 +349,7 @@ static int hybrid_predictor(struct mpsort_comm * c, const void * dbase, size_t n
     uint64_t * dcount = (uint64_t *) mps_arena_get(c, MPS_S_MISC, 256);
     const int saved = c->kt.force_cls;
     c->kt.force_cls = MPS_K_HYBRID;
-    KERN_T(c, MPS_K_HYBRID, mpsk_sample_prefix_rec16(dbase, n, s, desc->offset == 8, flip, lobits, samp, c->stream));
+    KERN_T(c, MPS_K_HYBRID, mpsk_sample_prefix_rec(dbase, n, E, s, desc->offset == 8, flip, lobits, samp, c->stream));
     struct sorted_view sv;
     const struct mpsort_radix_desc sdesc = { 0, 8, 1, 0, 0 };
     local_sort(c, samp, s, sizeof(uint64_t), &sdesc, 1, 0, &sv);
@@ -361,7 +363,7 @@ static int hybrid_predictor(struct mpsort_comm * c, const void * dbase, size_t n
     return (double) *h <= (limit < 8.0 ? 8.0 : limit);
 }
 
-static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t n,
+static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t n, size_t E,
         const struct mpsort_radix_desc * desc, void * dest, struct sorted_view * out)
 {
     const uint64_t flip = desc->is_signed ? (1ULL << 63) : 0ULL;
@@ -371,7 +373,7 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
     out->stride = n;
     out->sorted_recs = dest;
     out->kv.base = (const char *) dest + desc->offset;
-    out->kv.item_stride = 16; out->kv.word_stride = 0; out->kv.flip = flip; out->kv.add = 0;
+    out->kv.item_stride = E; out->kv.word_stride = 0; out->kv.flip = flip; out->kv.add = 0;
     if (n == 0) return;
     if (n > MPSK_MAX_ITEMS)
         mps_fatal(c, __FILE__, __LINE__, "%zu local items exceed the supported maximum %zu per rank", n, (size_t) MPSK_MAX_ITEMS);
@@ -380,7 +382,7 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
     uint32_t * bins = hist + 8 * 256;
     void * scratch = mps_arena_get(c, MPS_S_SCRATCH, mpsk_onesweep_scratch_bytes(n));
     CUDA_OK(c, cudaMemsetAsync(hist, 0, 8 * 256 * sizeof(uint32_t), c->stream));
-    KERN_T(c, MPS_K_EXTRACT, mpsk_extract_keys(dbase, n, 16, desc->offset, 8, 1, desc->is_signed, 0, 0, NULL, hist, NULL, c->stream));
+    KERN_T(c, MPS_K_EXTRACT, mpsk_extract_keys(dbase, n, E, desc->offset, 8, 1, desc->is_signed, 0, 0, NULL, hist, NULL, c->stream));
     KERN_T(c, MPS_K_EXTRACT, mpsk_scan_histograms(hist, bins, 8, c->stream));
     uint32_t * hhist = (uint32_t *) mps_host_stage(c, 8 * 256 * sizeof(uint32_t));
     CUDA_OK(c, cudaMemcpyAsync(hhist, hist, 8 * 256 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -393,7 +395,7 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
     }
     out->npasses = (uint32_t) P;
     if (P == 0) {
-        if (dest != dbase) CUDA_OK(c, cudaMemcpyAsync(dest, dbase, n * 16, cudaMemcpyDeviceToDevice, c->stream));
+        if (dest != dbase) CUDA_OK(c, cudaMemcpyAsync(dest, dbase, n * E, cudaMemcpyDeviceToDevice, c->stream));
         return;
     }
 
@@ -402,7 +404,7 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
         const uint32_t lobits = 8u * (uint32_t) digits[P - 4];
         uint32_t hsave[8 * 256];
         memcpy(hsave, hhist, sizeof(hsave));
-        const int yes = hybrid_predictor(c, dbase, n, desc, lobits);
+        const int yes = hybrid_predictor(c, dbase, n, E, desc, lobits);
         {
             /* the predictor's sample sort reused the histogram slot and the host stage:
              * put the big array's histograms and scanned bins back */
@@ -413,11 +415,11 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
             CUDA_OK(c, cudaStreamSynchronize(c->stream));   /* the stage is reused below */
         }
         if (yes) {
-            rec16_passes(c, dbase, n, desc, dest, digits + (P - 4), 4, bins, scratch);
+            rec16_passes(c, dbase, n, E, desc, dest, digits + (P - 4), 4, bins, scratch);
             uint32_t * wl = (uint32_t *) mps_arena_get(c, MPS_S_MERGE_CUT, (2 * MPS_HYBRID_MAX_LONG_RUNS + 64) * sizeof(uint32_t));
             uint32_t * nwork = wl + 2 * MPS_HYBRID_MAX_LONG_RUNS;
             CUDA_OK(c, cudaMemsetAsync(nwork, 0, sizeof(uint32_t), c->stream));
-            KERN_T(c, MPS_K_HYBRID, mpsk_fixup_rec16(dest, n, desc->offset == 8, flip, lobits, wl, nwork, MPS_HYBRID_MAX_LONG_RUNS, c->stream));
+            KERN_T(c, MPS_K_HYBRID, mpsk_fixup_rec(dest, n, E, desc->offset == 8, flip, lobits, wl, nwork, MPS_HYBRID_MAX_LONG_RUNS, c->stream));
             uint32_t * h = (uint32_t *) mps_host_stage(c, (2 * MPS_HYBRID_MAX_LONG_RUNS + 1) * sizeof(uint32_t));
             CUDA_OK(c, cudaMemcpyAsync(h, nwork, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
             CUDA_OK(c, cudaStreamSynchronize(c->stream));
@@ -428,11 +430,11 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
             if (nlong > MPS_HYBRID_MAX_LONG_RUNS) {
                 /* the predictor was wrong: finish with a full stable LSD of what we have
                  * (a permutation of the input in which equal keys kept their order) */
-                rec16_passes(c, dest, n, desc, dest, digits, P, bins, scratch);
+                rec16_passes(c, dest, n, E, desc, dest, digits, P, bins, scratch);
                 out->npasses = 4 + (uint32_t) P;
             } else if (nlong > 0) {
                 uint32_t starts[MPS_HYBRID_MAX_LONG_RUNS], lens[MPS_HYBRID_MAX_LONG_RUNS], e;
-                KERN_T(c, MPS_K_HYBRID, mpsk_fixup_extents(dest, n, desc->offset == 8, flip, lobits, wl, nlong, wl + MPS_HYBRID_MAX_LONG_RUNS, c->stream));
+                KERN_T(c, MPS_K_HYBRID, mpsk_fixup_extents(dest, n, E, desc->offset == 8, flip, lobits, wl, nlong, wl + MPS_HYBRID_MAX_LONG_RUNS, c->stream));
                 CUDA_OK(c, cudaMemcpyAsync(h, wl, 2 * MPS_HYBRID_MAX_LONG_RUNS * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
                 CUDA_OK(c, cudaStreamSynchronize(c->stream));
                 for (e = 0; e < nlong; e++) { starts[e] = h[e]; lens[e] = h[MPS_HYBRID_MAX_LONG_RUNS + e]; }
@@ -440,14 +442,14 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
                     /* a long run is a contiguous array whose high digits are constant: an
                      * ordinary in-place record sort of it runs the low passes only */
                     struct sorted_view sub;
-                    char * p0 = (char *) dest + (size_t) starts[e] * 16;
-                    local_sort_rec16(c, p0, lens[e], desc, p0, &sub);
+                    char * p0 = (char *) dest + (size_t) starts[e] * E;
+                    local_sort_rec16(c, p0, lens[e], E, desc, p0, &sub);
                 }
             }
             return;
         }
     }
-    rec16_passes(c, dbase, n, desc, dest, digits, P, bins, scratch);
+    rec16_passes(c, dbase, n, E, desc, dest, digits, P, bins, scratch);
 }
 
 /* ------------------------------------------------------------------------- */
@@ -653,7 +655,7 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
     void * sendbuf = NULL;
     if (p == 1 && rec16_applicable(elsize, desc, dbase, dout)) {
         /* one rank, record mode: the passes leave the sorted records in the output */
-        local_sort_rec16(c, dbase, n, desc, dout, &v1);
+        local_sort_rec16(c, dbase, n, elsize, desc, dout, &v1);
         c->stats.first_sort_passes = v1.npasses;
         c->stats.record_mode = 1;
         c->sendcounts[0] = (int64_t) n;
@@ -664,7 +666,7 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
     }
     if (p > 1) sendbuf = mps_arena_get(c, MPS_S_SEND, n * elsize);
     if (p > 1 && rec16_applicable(elsize, desc, dbase, sendbuf)) {
-        local_sort_rec16(c, dbase, n, desc, sendbuf, &v1);
+        local_sort_rec16(c, dbase, n, elsize, desc, sendbuf, &v1);
         c->stats.record_mode = 1;
     } else {
         local_sort(c, dbase, n, elsize, desc, p > 1, 1, &v1);

@@ -669,33 +669,41 @@ extern "C" int mpsk_onesweep_pass(const uint64_t * kin, const uint32_t * vin,
 #define MPSK_REC_MINBLOCKS 3
 #endif
 
-template <int THREADS, int IPT>
+template <int THREADS, int IPT, int ITEMBYTES>
 struct RecCfg {
     static constexpr int TILE = THREADS * IPT;
     static constexpr int WARPS = THREADS / 32;
-    static constexpr int SMEM = TILE * 16 + WARPS * 256 * 4 + 256 * 4 * 2 + 64;
+    static constexpr int SMEM = TILE * ITEMBYTES + WARPS * 256 * 4 + 256 * 4 * 2 + 64;
 };
 
+/* an item is a whole record: uint4 = {u64, u64} with the key in either half, or a bare u64 key */
 __device__ __forceinline__ u32 rec_digit(const uint4 & it, u32 khi, u64 flip, u32 shift)
 {
     const u64 k = (khi ? (((u64) it.w << 32) | it.z) : (((u64) it.y << 32) | it.x)) ^ flip;
     return (u32) (k >> shift) & 255u;
 }
+__device__ __forceinline__ u32 rec_digit(const u64 & it, u32 khi, u64 flip, u32 shift)
+{
+    (void) khi;
+    return (u32) ((it ^ flip) >> shift) & 255u;
+}
+__device__ __forceinline__ void rec_pad(uint4 & it, u64 padk) { it = make_uint4((u32) padk, (u32) (padk >> 32), (u32) padk, (u32) (padk >> 32)); }
+__device__ __forceinline__ void rec_pad(u64 & it, u64 padk) { it = padk; }
 
-template <int THREADS, int IPT>
+template <int THREADS, int IPT, typename ITEM>
 __global__ void __launch_bounds__(THREADS, MPSK_REC_MINBLOCKS)
-onesweep_rec16_kernel(const uint4 * __restrict__ in, uint4 * __restrict__ out,
+onesweep_rec_kernel(const ITEM * __restrict__ in, ITEM * __restrict__ out,
                       u32 n, u32 shift, u32 khi, u64 flip, const u32 * __restrict__ bins,
                       LookbackBufs lb, u32 * ticket)
 {
-    typedef RecCfg<THREADS, IPT> Cfg;
+    typedef RecCfg<THREADS, IPT, (int) sizeof(ITEM)> Cfg;
     constexpr int TILE = Cfg::TILE;
     constexpr int WARPS = Cfg::WARPS;
     static_assert(THREADS >= 256, "one thread per digit needs >= 256 threads");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint4 * s_items = (uint4 *) smem_raw;
-    u32 * s_whist = (u32 *) (smem_raw + TILE * 16);     /* [WARPS][256] */
+    ITEM * s_items = (ITEM *) smem_raw;
+    u32 * s_whist = (u32 *) (smem_raw + TILE * sizeof(ITEM));     /* [WARPS][256] */
     u32 * s_local = s_whist + WARPS * 256;
     u32 * s_gofs = s_local + 256;
     u32 * s_misc = s_gofs + 256;
@@ -715,14 +723,14 @@ onesweep_rec16_kernel(const uint4 * __restrict__ in, uint4 * __restrict__ out,
     const u32 wbase = tile_base + warp * (IPT * 32) + lane;
 
     /* ---- load records, warp-striped: each load instruction covers 512 contiguous bytes */
-    uint4 it[IPT];
+    ITEM it[IPT];
     if (valid == (u32) TILE) {
 #pragma unroll
         for (int j = 0; j < IPT; j++) it[j] = in[wbase + j * 32];
     } else {
         /* padding must rank last in bin 255: (key ^ flip) == ~0 */
-        const u64 padk = ~flip;
-        const uint4 pad = make_uint4((u32) padk, (u32) (padk >> 32), (u32) padk, (u32) (padk >> 32));
+        ITEM pad;
+        rec_pad(pad, ~flip);
 #pragma unroll
         for (int j = 0; j < IPT; j++) {
             const u32 pos = wbase + j * 32;
@@ -813,21 +821,18 @@ onesweep_rec16_kernel(const uint4 * __restrict__ in, uint4 * __restrict__ out,
     for (int k = 0; k < IPT; k++) {
         const u32 s = tid + k * THREADS;
         if (s < valid) {
-            const uint4 v = s_items[s];
+            const ITEM v = s_items[s];
             out[s_gofs[rec_digit(v, khi, flip, shift)] + s] = v;
         }
     }
 }
 
-typedef RecCfg<MPSK_REC_THREADS, MPSK_REC_IPT> TheRec;
-
-extern "C" int mpsk_onesweep_pass_rec16(const void * in, void * out, size_t n, int shift,
-        int key_in_high, uint64_t flip, const uint32_t * bins, void * scratch, mpsk_stream_t stream_)
+template <typename ITEM>
+static int launch_rec_pass(const void * in, void * out, size_t n, int shift, int key_in_high, uint64_t flip,
+                           const uint32_t * bins, void * scratch, cudaStream_t stream)
 {
-    if (n == 0) return 0;
-    if (n > MPSK_MAX_ITEMS) return (int) cudaErrorInvalidValue;
-    cudaStream_t stream = (cudaStream_t) stream_;
-    const size_t ntiles = (n + TheRec::TILE - 1) / TheRec::TILE;
+    typedef RecCfg<MPSK_REC_THREADS, MPSK_REC_IPT, (int) sizeof(ITEM)> Cfg;
+    const size_t ntiles = (n + Cfg::TILE - 1) / Cfg::TILE;
     cudaError_t e = cudaMemsetAsync(scratch, 0, lookback_words(ntiles) * sizeof(u32), stream);
     if (e != cudaSuccess) return (int) e;
     u32 * ticket = (u32 *) scratch;
@@ -835,14 +840,25 @@ extern "C" int mpsk_onesweep_pass_rec16(const void * in, void * out, size_t n, i
     lb.tiles = ticket + 64;
     lb.blktotal = lb.tiles + ntiles * 256;
     lb.blkincl = lb.blktotal + ((ntiles + LB_BLOCK - 1) / LB_BLOCK) * 256;
-    auto kern = onesweep_rec16_kernel<MPSK_REC_THREADS, MPSK_REC_IPT>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TheRec::SMEM);
+    auto kern = onesweep_rec_kernel<MPSK_REC_THREADS, MPSK_REC_IPT, ITEM>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return (int) e;
-    kern<<<(unsigned) ntiles, MPSK_REC_THREADS, TheRec::SMEM, stream>>>(
-        (const uint4 *) in, (uint4 *) out, (u32) n, (u32) shift, key_in_high ? 1u : 0u, (u64) flip,
+    kern<<<(unsigned) ntiles, MPSK_REC_THREADS, Cfg::SMEM, stream>>>(
+        (const ITEM *) in, (ITEM *) out, (u32) n, (u32) shift, key_in_high ? 1u : 0u, (u64) flip,
         bins, lb, ticket);
     CUDA_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int mpsk_onesweep_pass_rec(const void * in, void * out, size_t n, size_t elsize, int shift,
+        int key_in_high, uint64_t flip, const uint32_t * bins, void * scratch, mpsk_stream_t stream_)
+{
+    if (n == 0) return 0;
+    if (n > MPSK_MAX_ITEMS) return (int) cudaErrorInvalidValue;
+    cudaStream_t stream = (cudaStream_t) stream_;
+    if (elsize == 16) return launch_rec_pass<uint4>(in, out, n, shift, key_in_high, flip, bins, scratch, stream);
+    if (elsize == 8) return launch_rec_pass<u64>(in, out, n, shift, 0, flip, bins, scratch, stream);
+    return (int) cudaErrorInvalidValue;
 }
 
 /* ------------------------------------------------------------------------- */
@@ -871,9 +887,9 @@ __device__ __forceinline__ u64 rec_key(const uint4 & it, u32 khi, u64 flip)
     return (khi ? (((u64) it.w << 32) | it.z) : (((u64) it.y << 32) | it.x)) ^ flip;
 }
 
-template <bool KHI>
+template <typename ITEM, bool KHI>
 __global__ void __launch_bounds__(FIX_THREADS)
-fixup_rec16_kernel(uint4 * __restrict__ recs, u32 n, u64 flip, u32 lobits,
+fixup_rec_kernel(ITEM * __restrict__ recs, u32 n, u64 flip, u32 lobits,
                    u32 * __restrict__ worklist, u32 * __restrict__ nwork, u32 cap)
 {
     constexpr int CAP = FIX_T + FIX_HALO;
@@ -890,21 +906,22 @@ fixup_rec16_kernel(uint4 * __restrict__ recs, u32 n, u64 flip, u32 lobits,
     const u32 cnt = avail < (u32) CAP ? avail : (u32) CAP;
     const bool at_end = (t0 + cnt == n);
     const u64 lomask = lobits >= 64 ? ~0ULL : ((1ULL << lobits) - 1ULL);
-    const u64 * keys = (const u64 *) recs + (KHI ? 1 : 0);       /* key of record i at keys[2*i] */
+    constexpr u32 W = sizeof(ITEM) / 8;                            /* u64 words per record */
+    const u64 * keys = (const u64 *) recs + (KHI ? 1 : 0);       /* key of record i at keys[W*i] */
 
     {
         u64 tmp[NLD];
 #pragma unroll
         for (int k = 0; k < NLD; k++) {
             const u32 i = tid + k * FIX_THREADS;
-            if (i < cnt) tmp[k] = keys[2 * (t0 + i)];
+            if (i < cnt) tmp[k] = keys[W * (t0 + i)];
         }
 #pragma unroll
         for (int k = 0; k < NLD; k++) {
             const u32 i = tid + k * FIX_THREADS;
             if (i < cnt) s_key[i + 1] = tmp[k] ^ flip;
         }
-        if (tid == 0) s_key[0] = t0 ? (keys[2 * (t0 - 1)] ^ flip) : 0ULL;
+        if (tid == 0) s_key[0] = t0 ? (keys[W * (t0 - 1)] ^ flip) : 0ULL;
     }
     __syncthreads();
     /* head flags: the high part differs from the predecessor's. A warp handles 32
@@ -942,7 +959,7 @@ fixup_rec16_kernel(uint4 * __restrict__ recs, u32 n, u64 flip, u32 lobits,
     }
     __syncthreads();
     const u32 nlist = s_nlist;
-    uint4 moved[NLD];
+    ITEM moved[NLD];
     u32 tgts[NLD];
 #pragma unroll
     for (int k = 0; k < NLD; k++) {
@@ -989,54 +1006,62 @@ fixup_rec16_kernel(uint4 * __restrict__ recs, u32 n, u64 flip, u32 lobits,
 }
 
 /* extent of every long run on the work list: first index whose high part differs */
-__global__ void fixup_extent_kernel(const uint4 * __restrict__ recs, u32 n, u32 khi, u64 flip, u32 lobits,
+__device__ __forceinline__ u64 rec_key_at(const u64 * words, size_t i, u32 W, u32 khi, u64 flip)
+{
+    return words[W * i + khi] ^ flip;
+}
+
+__global__ void fixup_extent_kernel(const u64 * __restrict__ recs, u32 W, u32 n, u32 khi, u64 flip, u32 lobits,
                                     const u32 * __restrict__ worklist, u32 nwork, u32 * __restrict__ lengths)
 {
     const u32 e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nwork) return;
     const u32 start = worklist[e];
-    const u64 hi = rec_key(recs[start], khi, flip) >> lobits;
+    const u64 hi = rec_key_at(recs, start, W, khi, flip) >> lobits;
     u32 lo = start + 1, hiidx = n;                       /* keys are sorted by the high part */
     while (lo < hiidx) {
         const u32 mid = lo + ((hiidx - lo) >> 1);
-        if ((rec_key(recs[mid], khi, flip) >> lobits) <= hi) lo = mid + 1; else hiidx = mid;
+        if ((rec_key_at(recs, mid, W, khi, flip) >> lobits) <= hi) lo = mid + 1; else hiidx = mid;
     }
     lengths[e] = lo - start;
 }
 
-extern "C" int mpsk_fixup_rec16(void * recs, size_t n, int key_in_high, uint64_t flip, uint32_t lobits,
+extern "C" int mpsk_fixup_rec(void * recs, size_t n, size_t elsize, int key_in_high, uint64_t flip, uint32_t lobits,
         uint32_t * worklist, uint32_t * nwork, uint32_t cap, mpsk_stream_t stream)
 {
     if (n == 0) return 0;
     const size_t tiles = (n + FIX_T - 1) / FIX_T;
-    if (key_in_high)
-        fixup_rec16_kernel<true><<<(unsigned) tiles, FIX_THREADS, 0, (cudaStream_t) stream>>>(
+    if (elsize == 8)
+        fixup_rec_kernel<u64, false><<<(unsigned) tiles, FIX_THREADS, 0, (cudaStream_t) stream>>>(
+            (u64 *) recs, (u32) n, (u64) flip, lobits, worklist, nwork, cap);
+    else if (key_in_high)
+        fixup_rec_kernel<uint4, true><<<(unsigned) tiles, FIX_THREADS, 0, (cudaStream_t) stream>>>(
             (uint4 *) recs, (u32) n, (u64) flip, lobits, worklist, nwork, cap);
     else
-        fixup_rec16_kernel<false><<<(unsigned) tiles, FIX_THREADS, 0, (cudaStream_t) stream>>>(
+        fixup_rec_kernel<uint4, false><<<(unsigned) tiles, FIX_THREADS, 0, (cudaStream_t) stream>>>(
             (uint4 *) recs, (u32) n, (u64) flip, lobits, worklist, nwork, cap);
     CUDA_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int mpsk_fixup_extents(const void * recs, size_t n, int key_in_high, uint64_t flip, uint32_t lobits,
+extern "C" int mpsk_fixup_extents(const void * recs, size_t n, size_t elsize, int key_in_high, uint64_t flip, uint32_t lobits,
         const uint32_t * worklist, uint32_t nwork, uint32_t * lengths, mpsk_stream_t stream)
 {
     if (nwork == 0) return 0;
     fixup_extent_kernel<<<(nwork + 63) / 64, 64, 0, (cudaStream_t) stream>>>(
-        (const uint4 *) recs, (u32) n, key_in_high ? 1u : 0u, (u64) flip, lobits, worklist, nwork, lengths);
+        (const u64 *) recs, (u32) (elsize / 8), (u32) n, (key_in_high && elsize == 16) ? 1u : 0u, (u64) flip, lobits, worklist, nwork, lengths);
     CUDA_LAUNCH_CHECK();
     return 0;
 }
 
 /* predictor: the high parts of `s` evenly spaced records, as bare u64 "records" */
-__global__ void sample_prefix_kernel(const uint4 * __restrict__ recs, size_t n, u32 s, u32 khi, u64 flip, u32 lobits,
+__global__ void sample_prefix_kernel(const u64 * __restrict__ recs, u32 W, size_t n, u32 s, u32 khi, u64 flip, u32 lobits,
                                      u64 * __restrict__ out)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= s) return;
     const size_t pos = (size_t) (((unsigned __int128) i * n) / s);
-    out[i] = rec_key(recs[pos], khi, flip) >> lobits;
+    out[i] = rec_key_at(recs, pos, W, khi, flip) >> lobits;
 }
 
 /* number of equal PAIRS in a sorted array: sum over values of k(k-1)/2 */
@@ -1055,12 +1080,12 @@ __global__ void count_equal_pairs_kernel(const u64 * __restrict__ sorted, u32 s,
     if ((threadIdx.x & 31) == 0 && pairs) atomicAdd(count, pairs);
 }
 
-extern "C" int mpsk_sample_prefix_rec16(const void * recs, size_t n, uint32_t s, int key_in_high, uint64_t flip,
+extern "C" int mpsk_sample_prefix_rec(const void * recs, size_t n, size_t elsize, uint32_t s, int key_in_high, uint64_t flip,
         uint32_t lobits, uint64_t * out, mpsk_stream_t stream)
 {
     if (s == 0) return 0;
     sample_prefix_kernel<<<(s + 255) / 256, 256, 0, (cudaStream_t) stream>>>(
-        (const uint4 *) recs, n, s, key_in_high ? 1u : 0u, (u64) flip, lobits, (u64 *) out);
+        (const u64 *) recs, (u32) (elsize / 8), n, s, (key_in_high && elsize == 16) ? 1u : 0u, (u64) flip, lobits, (u64 *) out);
     CUDA_LAUNCH_CHECK();
     return 0;
 }

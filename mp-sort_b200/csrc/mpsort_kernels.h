@@ -52,26 +52,26 @@ int mpsk_onesweep_pass(const uint64_t * kin, const uint32_t * vin,
         uint64_t * kout, uint32_t * vout, size_t n, int shift,
         const uint32_t * bins, void * scratch, mpsk_stream_t stream);
 
-/* The same pass over whole 16-byte records {u64 key, u64 other} (key in the low or
- * the high half; `flip` is XORed onto the key before the digit is taken, i.e. the
- * sign bit for signed keys). in/out 16-byte aligned. */
-int mpsk_onesweep_pass_rec16(const void * in, void * out, size_t n, int shift,
+/* The same pass over whole records: elsize 16 = {u64 key, u64 other} (key in the low or
+ * the high half), elsize 8 = a bare u64 key. `flip` is XORed onto the key before the
+ * digit is taken (the sign bit for signed keys). in/out aligned to elsize. */
+int mpsk_onesweep_pass_rec(const void * in, void * out, size_t n, size_t elsize, int shift,
         int key_in_high, uint64_t flip, const uint32_t * bins, void * scratch, mpsk_stream_t stream);
 
 /* Hybrid sort support (record mode). After stable passes over the high digits only,
  * records that agree in (key ^ flip) >> lobits form runs that are still in input
- * order; mpsk_fixup_rec16 orders every run of <= 256 records by the low `lobits`
+ * order; mpsk_fixup_rec orders every run of <= 256 records by the low `lobits`
  * bits in place and appends the start index of every longer run to worklist
  * (*nwork counts them, also beyond cap; both device memory, *nwork zeroed by the
  * caller). mpsk_fixup_extents turns starts into lengths. */
-int mpsk_fixup_rec16(void * recs, size_t n, int key_in_high, uint64_t flip, uint32_t lobits,
+int mpsk_fixup_rec(void * recs, size_t n, size_t elsize, int key_in_high, uint64_t flip, uint32_t lobits,
         uint32_t * worklist, uint32_t * nwork, uint32_t cap, mpsk_stream_t stream);
-int mpsk_fixup_extents(const void * recs, size_t n, int key_in_high, uint64_t flip, uint32_t lobits,
+int mpsk_fixup_extents(const void * recs, size_t n, size_t elsize, int key_in_high, uint64_t flip, uint32_t lobits,
         const uint32_t * worklist, uint32_t nwork, uint32_t * lengths, mpsk_stream_t stream);
 /* predictor of the hybrid sort: high parts of s evenly spaced records (as u64), and
  * the number of equal pairs (sum of k(k-1)/2 over values) of a sorted u64 array, added
  * to *count. */
-int mpsk_sample_prefix_rec16(const void * recs, size_t n, uint32_t s, int key_in_high, uint64_t flip,
+int mpsk_sample_prefix_rec(const void * recs, size_t n, size_t elsize, uint32_t s, int key_in_high, uint64_t flip,
         uint32_t lobits, uint64_t * out, mpsk_stream_t stream);
 int mpsk_count_equal_pairs(const uint64_t * sorted, uint32_t s, uint64_t * count, mpsk_stream_t stream);
 

@@ -136,6 +136,33 @@ def test_hybrid_sort_uniform_keys(keyfield, signed):
     assert np.array_equal(got, a[np.argsort(a[keyfield], kind="stable")])
 
 
+@pytest.mark.parametrize("signed", [0, 1])
+def test_record_mode_bare_8_byte_keys(signed):
+    """elsize 8 = the reference's own bench-mpi workload (bare int64 items,
+    bench-mpi.c:13-15): keys are carried through the passes, hybrid for >= 2^22"""
+    rng = np.random.default_rng(21 + signed)
+    dt = np.dtype("i8" if signed else "u8")
+    for n, expect_hybrid in (((1 << 22) + 999, 1), (50001, 0)):
+        a = rng.integers(0, 1 << 63, size=n, dtype=np.uint64)
+        a = (a * np.uint64(2) + rng.integers(0, 2, size=n, dtype=np.uint64)).view(dt).copy()
+        a[100:1100] = a[0:1000]                                   # duplicates
+        got = a.copy()
+        comm = mpsort.Comm.self(0)
+        lib.radix_sort_desc(got.ctypes.data, n, 8, ctypes.byref(C.RadixDesc(0, 8, 1, signed, 0)), 0)
+        lib.mpsort_mpi_desc_impl(got.ctypes.data, n, 8, ctypes.byref(C.RadixDesc(0, 8, 1, signed, 0)), comm.handle, 0, b"bare8")
+        st = C.last_stats(comm.handle, 1)
+        comm.destroy()
+        assert st["record_mode"] == 1 and st["hybrid"] == expect_hybrid
+        assert np.array_equal(got, np.sort(a, kind="stable"))
+    # multi-rank: 3 ranks of bare keys
+    recs = [O.as_bytes(rng.integers(0, 1 << 62, size=m, dtype=np.uint64).view(dt)) for m in (70000, 0, 90001)]
+    outs = [60000, 50000, 50001]
+    desc = O.Desc(0, 8, 1, signed, 0)
+    out, stats = sort_group(recs, outs, desc, C.MPSORT_DISABLE_GATHER_SORT)
+    assert same(out, O.numpy_sort(recs, desc, outs))
+    assert all(st["record_mode"] == 1 for st in stats)
+
+
 def test_hybrid_sort_long_runs_and_fallback():
     rng = np.random.default_rng(5)
     n = 1 << 22

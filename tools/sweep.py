@@ -32,7 +32,7 @@ for _ in range(K):
 lib.mpsort_util_event_record(comm, e1)
 ms = lib.mpsort_util_event_elapsed_ms(comm, e0, e1) / K
 kt = C.kernel_times(comm)
-bad = lib.mpsort_util_check_sorted(comm, dout, n, E, ctypes.byref(desc), 1, 8, None)
+bad = lib.mpsort_util_check_sorted(comm, dout, n, E, ctypes.byref(desc), 1 if E >= 16 else 0, 8, None)
 print("%-28s n=2^%d E=%d kind=%d  step %.3f ms  %.2f Grec/s  bad=%d  | " % (
     os.path.basename(os.environ.get("MPSORT_LIB", "default")), log2n, E, kind, ms, n / ms / 1e6, bad) +
     "  ".join("%s %.3f/%d" % (k, v[0] / K, v[1] // K) for k, v in kt.items() if v[1]))
