@@ -275,6 +275,8 @@ void mpsort_comm_destroy(mpsort_comm_t c)
     for (s = 0; s < MPS_NSLOTS; s++) if (c->slot[s].ptr) cudaFree(c->slot[s].ptr);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->p2p.d_flag) cudaFree(c->p2p.d_flag);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
+    if (c->phase_ev_created) { int i; for (i = 0; i <= MPS_MAX_RANKS; i++) cudaEventDestroy(c->phase_ev[i]); }
     if (c->kind == MPS_T_NCCL && c->nccl) ncclCommDestroy(c->nccl);
     if (c->kind == MPS_T_LOCAL && c->grp) {
         int last;
@@ -412,60 +414,60 @@ void mps_comm_allreduce_u64_dev(struct mpsort_comm * c, uint64_t * dptr, size_t 
 }
 
 /*
- * The record exchange. Rank j's sorted records [cut[j][k], cut[j][k+1]) go to rank k
- * and land at item offset sum_{j'<j} count[j'][k] of k's receive buffer, i.e. the
- * receive buffer is laid out in source-rank order exactly like the reference's
- * RecvDispl (mpsort-mpi.c:490-503).
+ * The record exchange (one phase of it). The receive buffer is laid out in source-rank
+ * order exactly like the reference's RecvDispl (mpsort-mpi.c:490-503).
  *
  * dense == 0 (AUTO / REQUIRE_SPARSE): zero-length pairs are skipped, the behaviour
  *   of MPI_Alltoallv_sparse (mp-mpiu.c:184-214). Safe with NCCL because both sides
  *   of every pair hold the same count matrix.
  * dense != 0 (DISABLE_SPARSE): every pair is posted, like MPI_Alltoallv (mp-mpiu.c:140).
  */
-void mps_comm_alltoallv_dev(struct mpsort_comm * c, const void * sendbuf, void * recvbuf,
-        const int64_t * cut, size_t elsize, int dense, uint64_t * bytes_remote)
+static void exchange_p2p(struct mpsort_comm * c, const void * sendbuf, const int64_t * sendoff, const int64_t * sendcnt,
+        void * recvbuf, int64_t recvoff, const int64_t * recvcnt,
+        const int64_t * peer_recvoff, const int64_t * peer_sendoff, size_t elsize, uint64_t * bytes_remote);
+
+void mps_comm_exchange(struct mpsort_comm * c, const void * sendbuf, const int64_t * sendoff, const int64_t * sendcnt,
+        void * recvbuf, int64_t recvoff, const int64_t * recvcnt,
+        const int64_t * peer_recvoff, const int64_t * peer_sendoff,
+        size_t elsize, int dense, int use_p2p, uint64_t * bytes_remote)
 {
     const int p = c->size, me = c->rank;
     int j, k;
     uint64_t remote = 0;
-#define CUT(j, k) cut[(size_t) (j) * (p + 1) + (k)]
-    /* my receive displacement for source j */
     int64_t rdispl[MPS_MAX_RANKS + 1];
-    rdispl[0] = 0;
-    for (j = 0; j < p; j++) rdispl[j + 1] = rdispl[j] + (CUT(j, me + 1) - CUT(j, me));
+    rdispl[0] = recvoff;
+    for (j = 0; j < p; j++) rdispl[j + 1] = rdispl[j] + recvcnt[j];
 
     if (c->kind == MPS_T_SELF) {
-        const int64_t cnt = CUT(0, 1) - CUT(0, 0);
-        if (cnt > 0 && sendbuf != recvbuf)
-            CUDA_OK(c, cudaMemcpyAsync(recvbuf, sendbuf, (size_t) cnt * elsize, cudaMemcpyDeviceToDevice, c->stream));
-        if (bytes_remote) *bytes_remote = 0;
+        if (sendcnt[0] > 0 && (const char *) sendbuf + (size_t) sendoff[0] * elsize != (char *) recvbuf + (size_t) recvoff * elsize)
+            CUDA_OK(c, cudaMemcpyAsync((char *) recvbuf + (size_t) recvoff * elsize, (const char *) sendbuf + (size_t) sendoff[0] * elsize,
+                                       (size_t) sendcnt[0] * elsize, cudaMemcpyDeviceToDevice, c->stream));
+        return;
+    }
+    if (c->kind == MPS_T_NCCL && use_p2p) {
+        exchange_p2p(c, sendbuf, sendoff, sendcnt, recvbuf, recvoff, recvcnt, peer_recvoff, peer_sendoff, elsize, bytes_remote);
         return;
     }
     if (c->kind == MPS_T_NCCL) {
         NCCL_OK(c, ncclGroupStart());
         for (k = 0; k < p; k++) {
             if (k == me) continue;
-            const int64_t scnt = CUT(me, k + 1) - CUT(me, k);
-            const int64_t rcnt = CUT(k, me + 1) - CUT(k, me);
-            if (scnt > 0 || dense) {
-                NCCL_OK(c, ncclSend((const char *) sendbuf + (size_t) CUT(me, k) * elsize,
-                                    (size_t) scnt * elsize, ncclUint8, k, c->nccl, c->stream));
-                remote += (uint64_t) scnt * elsize;
+            if (sendcnt[k] > 0 || dense) {
+                NCCL_OK(c, ncclSend((const char *) sendbuf + (size_t) sendoff[k] * elsize,
+                                    (size_t) sendcnt[k] * elsize, ncclUint8, k, c->nccl, c->stream));
+                remote += (uint64_t) sendcnt[k] * elsize;
             }
-            if (rcnt > 0 || dense) {
+            if (recvcnt[k] > 0 || dense) {
                 NCCL_OK(c, ncclRecv((char *) recvbuf + (size_t) rdispl[k] * elsize,
-                                    (size_t) rcnt * elsize, ncclUint8, k, c->nccl, c->stream));
+                                    (size_t) recvcnt[k] * elsize, ncclUint8, k, c->nccl, c->stream));
             }
         }
         NCCL_OK(c, ncclGroupEnd());
-        {
-            const int64_t cnt = CUT(me, me + 1) - CUT(me, me);
-            if (cnt > 0)
-                CUDA_OK(c, cudaMemcpyAsync((char *) recvbuf + (size_t) rdispl[me] * elsize,
-                                           (const char *) sendbuf + (size_t) CUT(me, me) * elsize,
-                                           (size_t) cnt * elsize, cudaMemcpyDeviceToDevice, c->stream));
-        }
-        if (bytes_remote) *bytes_remote = remote;
+        if (sendcnt[me] > 0)
+            CUDA_OK(c, cudaMemcpyAsync((char *) recvbuf + (size_t) rdispl[me] * elsize,
+                                       (const char *) sendbuf + (size_t) sendoff[me] * elsize,
+                                       (size_t) sendcnt[me] * elsize, cudaMemcpyDeviceToDevice, c->stream));
+        if (bytes_remote) *bytes_remote += remote;
         return;
     }
     /* LOCAL: pull from every source's send buffer */
@@ -473,17 +475,38 @@ void mps_comm_alltoallv_dev(struct mpsort_comm * c, const void * sendbuf, void *
     c->grp->slot2[me] = sendbuf;
     local_barrier(c);
     for (j = 0; j < p; j++) {
-        const int64_t cnt = CUT(j, me + 1) - CUT(j, me);
-        if (cnt <= 0) continue;
-        const char * src = (const char *) c->grp->slot2[j] + (size_t) CUT(j, me) * elsize;
+        if (recvcnt[j] <= 0) continue;
+        const char * src = (const char *) c->grp->slot2[j] + (size_t) peer_sendoff[j] * elsize;
         CUDA_OK(c, cudaMemcpyAsync((char *) recvbuf + (size_t) rdispl[j] * elsize, src,
-                                   (size_t) cnt * elsize, cudaMemcpyDefault, c->stream));
-        if (j != me) remote += (uint64_t) cnt * elsize;
+                                   (size_t) recvcnt[j] * elsize, cudaMemcpyDefault, c->stream));
     }
+    for (k = 0; k < p; k++) if (k != me) remote += (uint64_t) sendcnt[k] * elsize;
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
     local_barrier(c);   /* sources may reuse their send buffers */
-    if (bytes_remote) *bytes_remote = remote;   /* bytes pulled, equals bytes pushed in total */
+    if (bytes_remote) *bytes_remote += remote;
+}
+
+/* whole exchange from the full cut matrix: rank j's sorted records [cut[j][k], cut[j][k+1])
+ * go to rank k (used by the small-input gather path) */
+void mps_comm_alltoallv_dev(struct mpsort_comm * c, const void * sendbuf, void * recvbuf,
+        const int64_t * cut, size_t elsize, int dense, uint64_t * bytes_remote)
+{
+    const int p = c->size, me = c->rank;
+    int j, k;
+    int64_t sendoff[MPS_MAX_RANKS], sendcnt[MPS_MAX_RANKS], recvcnt[MPS_MAX_RANKS];
+    int64_t peer_recvoff[MPS_MAX_RANKS], peer_sendoff[MPS_MAX_RANKS];
+#define CUT(j, k) cut[(size_t) (j) * (p + 1) + (k)]
+    for (k = 0; k < p; k++) {
+        sendoff[k] = CUT(me, k);
+        sendcnt[k] = CUT(me, k + 1) - CUT(me, k);
+        recvcnt[k] = CUT(k, me + 1) - CUT(k, me);
+        peer_sendoff[k] = CUT(k, me);
+        peer_recvoff[k] = 0;
+        for (j = 0; j < me; j++) peer_recvoff[k] += CUT(j, k + 1) - CUT(j, k);
+    }
 #undef CUT
+    if (bytes_remote) *bytes_remote = 0;
+    mps_comm_exchange(c, sendbuf, sendoff, sendcnt, recvbuf, 0, recvcnt, peer_recvoff, peer_sendoff, elsize, dense, 0, bytes_remote);
 }
 
 /* ------------------------------------------------------------------------- */
@@ -549,16 +572,16 @@ int mps_comm_p2p_prepare(struct mpsort_comm * c, const struct mps_recv_info * al
     return 1;
 }
 
-void mps_comm_alltoallv_p2p(struct mpsort_comm * c, const void * sendbuf, void * recvbuf,
-        const int64_t * cut, size_t elsize, uint64_t * bytes_remote)
+static void exchange_p2p(struct mpsort_comm * c, const void * sendbuf, const int64_t * sendoff, const int64_t * sendcnt,
+        void * recvbuf, int64_t recvoff, const int64_t * recvcnt,
+        const int64_t * peer_recvoff, const int64_t * peer_sendoff, size_t elsize, uint64_t * bytes_remote)
 {
     const int p = c->size, me = c->rank;
-    int k, j;
+    int k;
     const void * src[MPS_MAX_RANKS];
     void * dst[MPS_MAX_RANKS];
     uint64_t bytes[MPS_MAX_RANKS], remote = 0;
     unsigned char isremote[MPS_MAX_RANKS];
-#define CUT(j, k) cut[(size_t) (j) * (p + 1) + (k)]
     if (!c->p2p.d_flag) {
         CUDA_OK(c, cudaMalloc((void **) &c->p2p.d_flag, 256));
         CUDA_OK(c, cudaMemsetAsync(c->p2p.d_flag, 0, 256, c->stream));
@@ -566,31 +589,24 @@ void mps_comm_alltoallv_p2p(struct mpsort_comm * c, const void * sendbuf, void *
     if (c->p2p.pull) {
         /* every rank's send buffer must be complete before anyone reads it */
         NCCL_OK(c, ncclAllReduce(c->p2p.d_flag, c->p2p.d_flag, 1, ncclInt32, ncclSum, c->nccl, c->stream));
-        int64_t rd = 0;
+        int64_t rd = recvoff;
         for (k = 0; k < p; k++) {
-            /* rank k's slice for me, read from its (mapped) send buffer */
-            const int64_t cnt = CUT(k, me + 1) - CUT(k, me);
-            src[k] = (const char *) (k == me ? sendbuf : c->p2p.peer_base[k]) + (size_t) CUT(k, me) * elsize;
+            src[k] = (const char *) (k == me ? sendbuf : c->p2p.peer_base[k]) + (size_t) peer_sendoff[k] * elsize;
             dst[k] = (char *) recvbuf + (size_t) rd * elsize;
-            bytes[k] = (uint64_t) cnt * elsize;
+            bytes[k] = (uint64_t) recvcnt[k] * elsize;
             isremote[k] = (unsigned char) (k != me);
-            rd += cnt;
-            if (k != me) remote += (uint64_t) (CUT(me, k + 1) - CUT(me, k)) * elsize;
+            rd += recvcnt[k];
+            if (k != me) remote += (uint64_t) sendcnt[k] * elsize;
         }
     } else {
         for (k = 0; k < p; k++) {
-            /* where my slice lands in rank k's receive buffer: after the slices of ranks < me */
-            int64_t rd = 0;
-            for (j = 0; j < me; j++) rd += CUT(j, k + 1) - CUT(j, k);
-            const int64_t cnt = CUT(me, k + 1) - CUT(me, k);
-            src[k] = (const char *) sendbuf + (size_t) CUT(me, k) * elsize;
-            dst[k] = (char *) (k == me ? recvbuf : c->p2p.peer_base[k]) + (size_t) rd * elsize;
-            bytes[k] = (uint64_t) cnt * elsize;
+            src[k] = (const char *) sendbuf + (size_t) sendoff[k] * elsize;
+            dst[k] = (char *) (k == me ? recvbuf : c->p2p.peer_base[k]) + (size_t) peer_recvoff[k] * elsize;
+            bytes[k] = (uint64_t) sendcnt[k] * elsize;
             isremote[k] = (unsigned char) (k != me);
             if (k != me) remote += bytes[k];
         }
     }
-#undef CUT
     {
         /* segments in shifted order: me+1, me+2, ..., me (self last) */
         const void * rsrc[MPS_MAX_RANKS];
@@ -607,5 +623,5 @@ void mps_comm_alltoallv_p2p(struct mpsort_comm * c, const void * sendbuf, void *
      * may reuse its send buffer before everyone has read it. A one-word all-reduce on the
      * stream is the barrier (stream ordered, no host involvement). */
     NCCL_OK(c, ncclAllReduce(c->p2p.d_flag, c->p2p.d_flag, 1, ncclInt32, ncclSum, c->nccl, c->stream));
-    if (bytes_remote) *bytes_remote = remote;
+    if (bytes_remote) *bytes_remote += remote;
 }

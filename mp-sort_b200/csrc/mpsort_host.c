@@ -503,7 +503,7 @@ static int merge_received_runs(struct mpsort_comm * c, const void * recvbuf, con
         CUDA_OK(c, cudaStreamSynchronize(c->stream));
         if (*h != 0) mps_fatal(c, __FILE__, __LINE__, "serious bug: %u merge tiles exceeded their bound", *h);
     }
-    c->stats.second_sort_merge_tiles = ntiles;
+    c->stats.second_sort_merge_tiles += ntiles;
     return 0;
 }
 
@@ -717,11 +717,35 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
     const int level0 = mpsort_key_range(p, nw, nmemb, kmin, kmax, Pmin, Pmax, prefix0);
     timer_mark(c, "PmaxPmin");
 
-    /* ---- findP: byte-wise descent to the key at global rank C[b]-1 for every
+    /* ---- optional pipelining (MPSORT_EXCHANGE_PHASES=Q): every rank's output is cut into
+     * Q consecutive parts ("virtual ranks", pv = p*Q destinations). The exchange then runs
+     * part by part and the merge of part q overlaps the transfer of part q+1 on a second
+     * stream. The result is the same global stable sort: only more cut points. Off by
+     * default: on B200 the merge kernels starve the concurrent NCCL/peer-store kernels of
+     * SMs and HBM bandwidth, so the overlapped total is no shorter than the sum
+     * (profiles/r01_pipelined_exchange.log). Q is decided from global facts so that every
+     * rank takes the same branch. */
+    int Q = 1;
+    {
+        const char * e = getenv("MPSORT_EXCHANGE_PHASES");
+        const int want = e ? atoi(e) : 1;
+        if (nw == 1 && p <= 32 && want > 1 && total / p >= ((int64_t) 1 << 22)) {
+            Q = want;
+            while (Q > 1 && p * Q > MPS_MAX_RANKS) Q--;
+        }
+    }
+    const int pv = p * Q;
+    int64_t Cv[MPS_MAX_RANKS + 1];
+#define PARTBASE(k, q) ((int64_t) (outnmemb[k] * (int64_t) (q) / Q))
+    Cv[0] = 0;
+    for (j = 0; j < p; j++) for (b = 0; b < Q; b++)
+        Cv[j * Q + b + 1] = Cv[j * Q + b] + (PARTBASE(j, b + 1) - PARTBASE(j, b));
+
+    /* ---- findP: byte-wise descent to the key at global rank Cv[b]-1 for every
      * boundary b. Any exact selection gives the reference's result because a
      * splitter is only accepted when CLT < C <= CLE (internal-parallel.h:234-247),
      * i.e. when it IS that key. */
-    const int ns = p - 1;
+    const int ns = pv - 1;
     const int nlevels = 8 * (int) nw;
     /* layout of the splitter slot: prefix[ns][nw] | target[ns] | counts[ns][256] | final[2*ns] */
     const size_t sp_words = (size_t) ns * nw + ns + (size_t) ns * 256 + 2 * (size_t) ns;
@@ -734,7 +758,7 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
         uint64_t * h = (uint64_t *) mps_host_stage(c, ((size_t) ns * nw + ns) * sizeof(uint64_t));
         for (b = 0; b < ns; b++) {
             for (w = 0; w < (int) nw; w++) h[(size_t) b * nw + w] = prefix0[w];
-            h[(size_t) ns * nw + b] = (uint64_t) C[b + 1];
+            h[(size_t) ns * nw + b] = (uint64_t) Cv[b + 1];
         }
         CUDA_OK(c, cudaMemcpyAsync(d_prefix, h, ((size_t) ns * nw + ns) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
     }
@@ -779,60 +803,102 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
     }
     timer_mark(c, "LayDistr");
 
-    /* ---- LaySolve */
-    int64_t * clt = (int64_t *) malloc(sizeof(int64_t) * (size_t) ns * p);
-    int64_t * cle = (int64_t *) malloc(sizeof(int64_t) * (size_t) ns * p);
-    int64_t * cut = (int64_t *) malloc(sizeof(int64_t) * (size_t) p * (p + 1));
+    /* ---- LaySolve: p sources x pv virtual destinations */
+    int64_t * clt = (int64_t *) malloc(sizeof(int64_t) * (size_t) (ns ? ns : 1) * p);
+    int64_t * cle = (int64_t *) malloc(sizeof(int64_t) * (size_t) (ns ? ns : 1) * p);
+    int64_t * cut = (int64_t *) malloc(sizeof(int64_t) * (size_t) p * (pv + 1));
     for (j = 0; j < p; j++) for (b = 0; b < ns; b++) {
         clt[(size_t) j * ns + b] = rows[(size_t) j * 2 * ns + b];
         cle[(size_t) j * ns + b] = rows[(size_t) j * 2 * ns + ns + b];
     }
     {
-        const int rc = mpsort_solve_layout(p, C, clt, cle, nmemb, cut);
+        const int rc = mpsort_solve_layout2(p, pv, Cv, clt, cle, nmemb, cut);
         if (rc != 0) mps_fatal(c, __FILE__, __LINE__, "serious bug: layout solver failed with code %d", rc);
     }
+#define CUTV(j, v) cut[(size_t) (j) * (pv + 1) + (v)]
     /* consistency checks of mpsort-mpi.c:490-510 */
     {
         int64_t totrecv = 0;
-        for (j = 0; j < p; j++) totrecv += cut[(size_t) j * (p + 1) + c->rank + 1] - cut[(size_t) j * (p + 1) + c->rank];
+        for (j = 0; j < p; j++) totrecv += CUTV(j, (c->rank + 1) * Q) - CUTV(j, c->rank * Q);
         if (totrecv != (int64_t) outn)
             mps_fatal(c, __FILE__, __LINE__, "totrecv = %td, mismatch with %td", (ptrdiff_t) totrecv, (ptrdiff_t) outn);
     }
-    for (j = 0; j < p; j++) c->sendcounts[j] = cut[(size_t) c->rank * (p + 1) + j + 1] - cut[(size_t) c->rank * (p + 1) + j];
+    /* the reference's SendCount row (mpsort-mpi.c:483-485): all parts of a rank together */
+    for (j = 0; j < p; j++) c->sendcounts[j] = CUTV(c->rank, (j + 1) * Q) - CUTV(c->rank, j * Q);
     timer_mark(c, "LaySolve");
 
     /* ---- Exchange: pack (payload gather into destination-contiguous order; the
      * destinations are contiguous slices of the sorted order, SendDispl[i] == myC[i]
-     * :483-501) then grouped send/recv */
+     * :483-501) then, part by part, grouped send/recv or peer stores */
     if (v1.sorted_recs != sendbuf)
         KERN_T(c, MPS_K_GATHER_RECORDS, mpsk_gather_records(dbase, v1.idx, sendbuf, n, elsize, c->stream));
     timer_mark(c, "Pack");
     const int dense = mpsort_mpi_has_options(MPSORT_DISABLE_SPARSE_ALLTOALLV)
                       && !mpsort_mpi_has_options(MPSORT_REQUIRE_SPARSE_ALLTOALLV);
     c->stats.dense_exchange = (uint32_t) dense;
-    mps_kt_begin(c, MPS_K_EXCHANGE);
-    if (use_p2p) mps_comm_alltoallv_p2p(c, sendbuf, recvbuf, cut, elsize, &c->stats.bytes_sent_remote);
-    else mps_comm_alltoallv_dev(c, sendbuf, recvbuf, cut, elsize, dense, &c->stats.bytes_sent_remote);
-    mps_kt_end(c);
     c->stats.p2p_exchange = (uint32_t) use_p2p;
+    c->stats.exchange_phases = (uint32_t) Q;
+    if (!c->phase_ev_created) {
+        for (j = 0; j <= MPS_MAX_RANKS; j++) CUDA_OK(c, cudaEventCreateWithFlags(&c->phase_ev[j], cudaEventDisableTiming));
+        c->phase_ev_created = 1;
+    }
+    if (Q > 1 && !c->stream2) CUDA_OK(c, cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    const int me = c->rank;
+    int64_t (*recvcnt_q)[MPS_MAX_RANKS] = (int64_t (*)[MPS_MAX_RANKS]) malloc(sizeof(int64_t) * MPS_MAX_RANKS * (size_t) Q);
+    int q;
+    for (q = 0; q < Q; q++) {
+        int64_t sendoff[MPS_MAX_RANKS], sendcnt[MPS_MAX_RANKS], peer_recvoff[MPS_MAX_RANKS], peer_sendoff[MPS_MAX_RANKS];
+        int k;
+        for (k = 0; k < p; k++) {
+            const int v = k * Q + q;                   /* part q of rank k */
+            sendoff[k] = CUTV(me, v);
+            sendcnt[k] = CUTV(me, v + 1) - CUTV(me, v);
+            peer_recvoff[k] = PARTBASE(k, q);
+            for (j = 0; j < me; j++) peer_recvoff[k] += CUTV(j, v + 1) - CUTV(j, v);
+            recvcnt_q[q][k] = CUTV(k, me * Q + q + 1) - CUTV(k, me * Q + q);
+            peer_sendoff[k] = CUTV(k, me * Q + q);
+        }
+        mps_kt_begin(c, MPS_K_EXCHANGE);
+        mps_comm_exchange(c, sendbuf, sendoff, sendcnt, recvbuf, PARTBASE(me, q), recvcnt_q[q], peer_recvoff, peer_sendoff,
+                          elsize, dense, use_p2p, &c->stats.bytes_sent_remote);
+        mps_kt_end(c);
+        CUDA_OK(c, cudaEventRecord(c->phase_ev[q], c->stream));
+    }
     timer_mark(c, "Exchange");
 
-    /* ---- SecondSort: the received buffer is p sorted runs in source-rank order;
-     * a stable sort of it restores global order with ties by (source rank, index) */
+    /* ---- SecondSort: every received part is p sorted runs in source-rank order; a stable
+     * merge (or stable re-sort) of it restores global order with ties by (source rank,
+     * index). With Q > 1 the parts are merged on the second stream as they arrive. */
     {
-        int64_t rdispl[MPS_MAX_RANKS + 1];
-        rdispl[0] = 0;
-        for (j = 0; j < p; j++) rdispl[j + 1] = rdispl[j] + (cut[(size_t) j * (p + 1) + c->rank + 1] - cut[(size_t) j * (p + 1) + c->rank]);
-        if (merge_received_runs(c, recvbuf, rdispl, dout, outn, elsize, desc) != 0) {
-            struct sorted_view v2;
-            local_sort(c, recvbuf, outn, elsize, desc, 0, 1, &v2);
-            KERN_T(c, MPS_K_GATHER_RECORDS, mpsk_gather_records(recvbuf, v2.idx, dout, outn, elsize, c->stream));
-            c->stats.second_sort_passes = v2.npasses;
+        cudaStream_t main_stream = c->stream;
+        if (Q > 1) c->stream = c->stream2;
+        for (q = 0; q < Q; q++) {
+            const int64_t base = PARTBASE(me, q), cnt = PARTBASE(me, q + 1) - PARTBASE(me, q);
+            int64_t rdispl[MPS_MAX_RANKS + 1];
+            rdispl[0] = 0;
+            for (j = 0; j < p; j++) rdispl[j + 1] = rdispl[j] + recvcnt_q[q][j];
+            if (Q > 1) CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->phase_ev[q], 0));
+            char * part_in = (char *) recvbuf + (size_t) base * elsize;
+            char * part_out = (char *) dout + (size_t) base * elsize;
+            if (merge_received_runs(c, part_in, rdispl, part_out, (size_t) cnt, elsize, desc) != 0) {
+                struct sorted_view v2;
+                local_sort(c, part_in, (size_t) cnt, elsize, desc, 0, 1, &v2);
+                KERN_T(c, MPS_K_GATHER_RECORDS, mpsk_gather_records(part_in, v2.idx, part_out, (size_t) cnt, elsize, c->stream));
+                c->stats.second_sort_passes = v2.npasses;
+            }
+        }
+        if (Q > 1) {
+            CUDA_OK(c, cudaEventRecord(c->phase_ev[MPS_MAX_RANKS], c->stream));
+            c->stream = main_stream;
+            CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->phase_ev[MPS_MAX_RANKS], 0));
         }
     }
     timer_mark(c, "SecondSort");
     timer_mark(c, "END");
+#undef CUTV
+#undef PARTBASE
 
+    free(recvcnt_q);
     free(rows); free(clt); free(cle); free(cut); free(info);
 }
 

@@ -95,6 +95,9 @@ struct mpsort_comm {
     struct mpsort_last_stats stats;
     int64_t sendcounts[MPS_MAX_RANKS];
     struct mps_ktimes kt;
+    cudaStream_t stream2;                      /* merges of the pipelined exchange run here */
+    cudaEvent_t phase_ev[MPS_MAX_RANKS + 1];
+    int phase_ev_created;
 
     /* peer-store exchange (NCCL transport only): every rank's receive buffer mapped here */
     struct {
@@ -144,15 +147,24 @@ void mps_comm_allreduce_u64_dev(struct mpsort_comm * c, uint64_t * dptr, size_t 
  * goes to rank k (full matrix, known on every rank) */
 void mps_comm_alltoallv_dev(struct mpsort_comm * c, const void * sendbuf, void * recvbuf,
         const int64_t * cut, size_t elsize, int dense, uint64_t * bytes_remote);
-/* the same exchange as peer stores; valid only after mps_comm_p2p_prepare returned 1 */
-void mps_comm_alltoallv_p2p(struct mpsort_comm * c, const void * sendbuf, void * recvbuf,
-        const int64_t * cut, size_t elsize, uint64_t * bytes_remote);
+/* One phase of the exchange, in items of elsize bytes. I send sendcnt[k] items from item
+ * sendoff[k] of sendbuf to rank k; I receive recvcnt[j] items from rank j, stored in
+ * source-rank order from item recvoff of recvbuf. peer_recvoff[k] = item of rank k's
+ * receive buffer where my slice lands (peer stores); peer_sendoff[j] = item of rank j's
+ * send buffer where its slice for me starts (pull transports). use_p2p needs a successful
+ * mps_comm_p2p_prepare. Adds the bytes that left this GPU to *bytes_remote. */
+void mps_comm_exchange(struct mpsort_comm * c, const void * sendbuf, const int64_t * sendoff, const int64_t * sendcnt,
+        void * recvbuf, int64_t recvoff, const int64_t * recvcnt,
+        const int64_t * peer_recvoff, const int64_t * peer_sendoff,
+        size_t elsize, int dense, int use_p2p, uint64_t * bytes_remote);
 
 /* ---- layout solver (mpsort_layout.c; pure host arithmetic, unit-testable) ---- */
 /* C[p+1] desired cumulative output counts; clt/cle[j*(p-1) + b] local counts of rank j
  * for splitter b; nmemb[j]; writes cut[j*(p+1) + k]. Returns 0, or a negative code on
  * the reference's "serious bug" conditions (mpsort-mpi.c:707-716). */
 int mpsort_solve_layout(int p, const int64_t * C, const int64_t * clt, const int64_t * cle,
+        const int64_t * nmemb, int64_t * cut);
+int mpsort_solve_layout2(int psrc, int pdst, const int64_t * C, const int64_t * clt, const int64_t * cle,
         const int64_t * nmemb, int64_t * cut);
 
 #endif

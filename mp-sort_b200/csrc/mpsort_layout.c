@@ -22,37 +22,46 @@
  * cut[j][b] is the resulting first index in rank j's sorted array that goes to
  * rank >= b; cut[j][0] = 0, cut[j][p] = nmemb[j].
  */
-int mpsort_solve_layout(int p, const int64_t * C, const int64_t * clt, const int64_t * cle,
+/* psrc sources, pdst (virtual) destinations: cut[j * (pdst + 1) + b], clt/cle[j * (pdst - 1) + b - 1].
+ * pdst > psrc when every rank's output is split into several consecutive parts so that
+ * the exchange and the merge can be pipelined part by part. */
+int mpsort_solve_layout2(int psrc, int pdst, const int64_t * C, const int64_t * clt, const int64_t * cle,
         const int64_t * nmemb, int64_t * cut)
 {
-    const int ns = p - 1;
+    const int ns = pdst - 1;
     int j, b;
-    for (j = 0; j < p; j++) {
-        cut[(size_t) j * (p + 1) + 0] = 0;
-        cut[(size_t) j * (p + 1) + p] = nmemb[j];
+    for (j = 0; j < psrc; j++) {
+        cut[(size_t) j * (pdst + 1) + 0] = 0;
+        cut[(size_t) j * (pdst + 1) + pdst] = nmemb[j];
     }
-    for (b = 1; b < p; b++) {
+    for (b = 1; b < pdst; b++) {
         int64_t sure = 0;
-        for (j = 0; j < p; j++) sure += clt[(size_t) j * ns + (b - 1)];
+        for (j = 0; j < psrc; j++) sure += clt[(size_t) j * ns + (b - 1)];
         int64_t deficit = C[b] - sure;
         if (deficit < 0) return -1;   /* "more items than there should be" */
-        for (j = 0; j < p; j++) {
+        for (j = 0; j < psrc; j++) {
             const int64_t lt = clt[(size_t) j * ns + (b - 1)];
             const int64_t supply = cle[(size_t) j * ns + (b - 1)] - lt;
             if (supply < 0) return -2; /* "less items than there should be" */
             int64_t take = supply <= deficit ? supply : deficit;
-            cut[(size_t) j * (p + 1) + b] = lt + take;
+            cut[(size_t) j * (pdst + 1) + b] = lt + take;
             deficit -= take;
         }
         if (deficit != 0) return -3;   /* CLE did not bracket C: splitter was wrong */
     }
     /* sanity: cuts must be monotone per source (SendCount >= 0, mpsort-mpi.c:483-485) */
-    for (j = 0; j < p; j++) {
-        for (b = 0; b < p; b++) {
-            if (cut[(size_t) j * (p + 1) + b] > cut[(size_t) j * (p + 1) + b + 1]) return -4;
+    for (j = 0; j < psrc; j++) {
+        for (b = 0; b < pdst; b++) {
+            if (cut[(size_t) j * (pdst + 1) + b] > cut[(size_t) j * (pdst + 1) + b + 1]) return -4;
         }
     }
     return 0;
+}
+
+int mpsort_solve_layout(int p, const int64_t * C, const int64_t * clt, const int64_t * cle,
+        const int64_t * nmemb, int64_t * cut)
+{
+    return mpsort_solve_layout2(p, p, C, clt, cle, nmemb, cut);
 }
 
 /* Desired cumulative output counts, C[0] = 0, C[i+1] = C[i] + outnmemb[i]

@@ -466,9 +466,12 @@ def test_large_particles48_and_mostly_sorted_by_properties():
     comm.destroy()
 
 
-def test_large_multirank_hybrid_records_by_properties():
+@pytest.mark.parametrize("phases", [1, 4])
+def test_large_multirank_hybrid_records_by_properties(phases, monkeypatch):
     """4 rank threads x 2^22 uniform 16-byte records: record mode + hybrid FirstSort,
-    exchange, merge; checked by global order, tie order and checksum of checksums"""
+    exchange (optionally pipelined in 4 parts over virtual ranks), merge; checked by
+    global order, tie order and checksum of checksums"""
+    monkeypatch.setenv("MPSORT_EXCHANGE_PHASES", str(phases))
     p, n, E = 4, 1 << 22, 16
     desc = C.RadixDesc(0, 8, 1, 0, 0)
     res = [None] * p
@@ -494,6 +497,7 @@ def test_large_multirank_hybrid_records_by_properties():
     assert all(x[2] == 0 for x in res)
     assert all(res[r - 1][4] <= res[r][3] for r in range(1, p))
     assert all(x[5]["record_mode"] == 1 and x[5]["hybrid"] == 1 and x[5]["second_sort_merge_tiles"] > 0 for x in res)
+    assert all(x[5]["exchange_phases"] == phases for x in res)
 
 
 def test_large_multirank_by_properties():
