@@ -668,6 +668,9 @@ extern "C" int mpsk_onesweep_pass(const uint64_t * kin, const uint32_t * vin,
 #ifndef MPSK_REC_MINBLOCKS
 #define MPSK_REC_MINBLOCKS 3
 #endif
+#ifndef MPSK_REC8_IPT
+#define MPSK_REC8_IPT 12
+#endif
 
 template <int THREADS, int IPT, int ITEMBYTES>
 struct RecCfg {
@@ -831,7 +834,9 @@ template <typename ITEM>
 static int launch_rec_pass(const void * in, void * out, size_t n, int shift, int key_in_high, uint64_t flip,
                            const uint32_t * bins, void * scratch, cudaStream_t stream)
 {
-    typedef RecCfg<MPSK_REC_THREADS, MPSK_REC_IPT, (int) sizeof(ITEM)> Cfg;
+    /* bare 8-byte keys: 12 per thread is the best of the shapes tried (profiles/r01_sweep5_rec_shapes.log) */
+    constexpr int IPT = sizeof(ITEM) == 8 ? MPSK_REC8_IPT : MPSK_REC_IPT;
+    typedef RecCfg<MPSK_REC_THREADS, IPT, (int) sizeof(ITEM)> Cfg;
     const size_t ntiles = (n + Cfg::TILE - 1) / Cfg::TILE;
     cudaError_t e = cudaMemsetAsync(scratch, 0, lookback_words(ntiles) * sizeof(u32), stream);
     if (e != cudaSuccess) return (int) e;
@@ -840,7 +845,7 @@ static int launch_rec_pass(const void * in, void * out, size_t n, int shift, int
     lb.tiles = ticket + 64;
     lb.blktotal = lb.tiles + ntiles * 256;
     lb.blkincl = lb.blktotal + ((ntiles + LB_BLOCK - 1) / LB_BLOCK) * 256;
-    auto kern = onesweep_rec_kernel<MPSK_REC_THREADS, MPSK_REC_IPT, ITEM>;
+    auto kern = onesweep_rec_kernel<MPSK_REC_THREADS, IPT, ITEM>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return (int) e;
     kern<<<(unsigned) ntiles, MPSK_REC_THREADS, Cfg::SMEM, stream>>>(
