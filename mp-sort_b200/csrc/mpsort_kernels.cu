@@ -1451,9 +1451,11 @@ merge_bounds_kernel(const unsigned char * __restrict__ recv, KeyDesc d, bool fas
 #define MPD(i) ((i) + ((i) >> 3))
 #define MPSK_MERGE_PADDED (MPSK_MERGE_TILE + MPSK_MERGE_TILE / 8)
 
-template <typename V>
+/* FAST8: one aligned 8-byte key word (no generic key packing code in the kernel);
+ * LPR1: a record is exactly one V (no division in the output loop) */
+template <typename V, bool FAST8, bool LPR1>
 __global__ void __launch_bounds__(MPSK_MERGE_THREADS, 2)
-merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, bool fast8, MergeRuns m,
+merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, MergeRuns m,
                   const u32 * __restrict__ cut, unsigned char * __restrict__ out, u32 * __restrict__ overflow)
 {
     constexpr int VT = MPSK_MERGE_TILE / MPSK_MERGE_THREADS;      /* items per thread */
@@ -1467,17 +1469,23 @@ merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, bool fast8
     __shared__ u32 s_outstart;
 
     const u32 t = blockIdx.x, p = m.p, tid = threadIdx.x;
-    if (tid == 0) {
-        u32 acc = 0, ostart = 0;
-        for (u32 r = 0; r < p; r++) {
-            const u32 c0 = cut[t * p + r], c1 = cut[(t + 1) * p + r];
-            seqoff[r] = acc;
-            srcbase[r] = m.rdispl[r] + c0;
-            acc += c1 - c0;
-            ostart += c0;
+    if (tid < 32) {
+        /* one lane per run (p <= 32): the 2p cut words are fetched in parallel, not by one
+         * thread in a dependent loop (that loop alone was ~4 us per tile at p = 8) */
+        u32 c0 = 0, c1 = 0;
+        if (tid < p) { c0 = cut[t * p + tid]; c1 = cut[(t + 1) * p + tid]; }
+        const u32 len = c1 - c0;
+        u32 incl = len, sum0 = c0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 y = __shfl_up_sync(FULL_MASK, incl, o);
+            if (tid >= (u32) o) incl += y;
         }
-        seqoff[p] = acc;
-        s_outstart = ostart;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum0 += __shfl_xor_sync(FULL_MASK, sum0, o);
+        if (tid < p) { seqoff[tid] = incl - len; srcbase[tid] = m.rdispl[tid] + c0; }
+        if (tid == p - 1) seqoff[p] = incl;
+        if (tid == 0) s_outstart = sum0;
     }
     __syncthreads();
     const u32 cnt = seqoff[p];
@@ -1502,7 +1510,7 @@ merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, bool fast8
 #pragma unroll
         for (int k = 0; k < VT; k++) {
             const u32 i = tid + k * MPSK_MERGE_THREADS;
-            if (i < cnt) key[k] = load_key_any(recv + (size_t) src[k] * d.elsize, d, fast8);
+            if (i < cnt) key[k] = load_key_any(recv + (size_t) src[k] * d.elsize, d, FAST8);
         }
 #pragma unroll
         for (int k = 0; k < VT; k++) {
@@ -1555,7 +1563,7 @@ merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, bool fast8
         u32 * ts = sA; sA = sB; sB = ts;
     }
     /* ---- write the records in merged order (lanes of one record move consecutive pieces) */
-    const u32 lpr = (u32) (d.elsize / sizeof(V));
+    const u32 lpr = LPR1 ? 1u : (u32) (d.elsize / sizeof(V));
     const V * in = (const V *) recv;
     V * o = (V *) out + (size_t) s_outstart * lpr;
     const u32 totalv = cnt * lpr;
@@ -1565,8 +1573,12 @@ merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, bool fast8
         for (int k = 0; k < VT; k++) {
             const u32 x = x0 + tid + k * MPSK_MERGE_THREADS;
             if (x < totalv) {
-                const u32 i = x / lpr, part = x - i * lpr;
-                v[k] = in[(size_t) sA[MPD(i)] * lpr + part];
+                if (LPR1) {
+                    v[k] = in[sA[MPD(x)]];
+                } else {
+                    const u32 i = x / lpr, part = x - i * lpr;
+                    v[k] = in[(size_t) sA[MPD(i)] * lpr + part];
+                }
             }
         }
 #pragma unroll
@@ -1598,17 +1610,23 @@ merge_tile_rec16_kernel(const uint4 * __restrict__ recv, u64 flip, MergeRuns m,
     __shared__ u32 s_outstart;
 
     const u32 t = blockIdx.x, p = m.p, tid = threadIdx.x;
-    if (tid == 0) {
-        u32 acc = 0, ostart = 0;
-        for (u32 r = 0; r < p; r++) {
-            const u32 c0 = cut[t * p + r], c1 = cut[(t + 1) * p + r];
-            seqoff[r] = acc;
-            srcbase[r] = m.rdispl[r] + c0;
-            acc += c1 - c0;
-            ostart += c0;
+    if (tid < 32) {
+        /* one lane per run (p <= 32): the 2p cut words are fetched in parallel, not by one
+         * thread in a dependent loop (that loop alone was ~4 us per tile at p = 8) */
+        u32 c0 = 0, c1 = 0;
+        if (tid < p) { c0 = cut[t * p + tid]; c1 = cut[(t + 1) * p + tid]; }
+        const u32 len = c1 - c0;
+        u32 incl = len, sum0 = c0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 y = __shfl_up_sync(FULL_MASK, incl, o);
+            if (tid >= (u32) o) incl += y;
         }
-        seqoff[p] = acc;
-        s_outstart = ostart;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum0 += __shfl_xor_sync(FULL_MASK, sum0, o);
+        if (tid < p) { seqoff[tid] = incl - len; srcbase[tid] = m.rdispl[tid] + c0; }
+        if (tid == p - 1) seqoff[p] = incl;
+        if (tid == 0) s_outstart = sum0;
     }
     __syncthreads();
     const u32 cnt = seqoff[p];
@@ -1721,11 +1739,18 @@ static int launch_merge_tiles(const void * recv, KeyDesc d, bool fast8, const Me
                               void * out, u32 * overflow, u32 ntiles, cudaStream_t stream)
 {
     const int smem = MPSK_MERGE_PADDED * (8 + 8 + 4 + 4);
-    auto kern = merge_tile_kernel<V>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int) e;
-    kern<<<ntiles, MPSK_MERGE_THREADS, smem, stream>>>((const unsigned char *) recv, d, fast8, m, cut,
-                                                       (unsigned char *) out, overflow);
+    const bool lpr1 = d.elsize == sizeof(V);
+#define MERGE_LAUNCH(F8, L1) do { \
+        auto kern = merge_tile_kernel<V, F8, L1>; \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+        if (e != cudaSuccess) return (int) e; \
+        kern<<<ntiles, MPSK_MERGE_THREADS, smem, stream>>>((const unsigned char *) recv, d, m, cut, \
+                                                           (unsigned char *) out, overflow); } while (0)
+    if (fast8 && lpr1) MERGE_LAUNCH(true, true);
+    else if (fast8) MERGE_LAUNCH(true, false);
+    else if (lpr1) MERGE_LAUNCH(false, true);
+    else MERGE_LAUNCH(false, false);
+#undef MERGE_LAUNCH
     CUDA_LAUNCH_CHECK();
     return 0;
 }
