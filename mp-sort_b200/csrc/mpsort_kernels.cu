@@ -671,6 +671,9 @@ extern "C" int mpsk_onesweep_pass(const uint64_t * kin, const uint32_t * vin,
 #ifndef MPSK_REC8_IPT
 #define MPSK_REC8_IPT 12
 #endif
+#ifndef MPSK_REC_TMA_STORE
+#define MPSK_REC_TMA_STORE 1
+#endif
 
 template <int THREADS, int IPT, int ITEMBYTES>
 struct RecCfg {
@@ -807,10 +810,15 @@ onesweep_rec_kernel(const ITEM * __restrict__ in, ITEM * __restrict__ out,
         const u32 digit = rec_digit(it[j], khi, flip, shift);
         s_items[rank[j] + my_hist[digit]] = it[j];
     }
+#if MPSK_REC_TMA_STORE
+    /* the staged tile is read by the bulk-copy engine below: make the generic-proxy
+     * shared-memory writes visible to the async proxy */
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
 
     /* ---- decoupled look-back (see onesweep_kernel) */
+    u32 excl = 0;
     if (tid < 256) {
-        u32 excl = 0;
         if (tile > 0) {
             excl = lookback_exclusive(lb, tile, tid);
             st_relaxed_u32(&lb.tiles[(size_t) tile * 256 + tid], LB_INCL | (excl + cnt_valid));
@@ -819,13 +827,36 @@ onesweep_rec_kernel(const ITEM * __restrict__ in, ITEM * __restrict__ out,
     }
     __syncthreads();
 
-    /* ---- coalesced stores of the digit runs */
+#if MPSK_REC_TMA_STORE
+    /* ---- one bulk copy (TMA, cp.async.bulk shared -> global) per digit run: the run of
+     * digit d is contiguous both in the staged tile and in the output, a multiple of the
+     * record size long and 16-byte aligned on both sides. 256 threads issue 256 copies;
+     * nobody executes a per-record store loop. */
+    if (sizeof(ITEM) == 16) {
+        if (tid < 256) {
+            if (cnt_valid) {
+                const u32 local = s_local[tid];
+                ITEM * dst = out + (bins[tid] + excl);
+                const u32 src = (u32) __cvta_generic_to_shared(&s_items[local]);
+                const u32 bytes = cnt_valid * (u32) sizeof(ITEM);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"(dst), "r"(src), "r"(bytes) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            /* shared memory must stay valid until the engine has read it */
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    } else
+#endif
+    {
+        /* ---- coalesced stores of the digit runs (8-byte items: runs are not multiples of 16 bytes) */
 #pragma unroll
-    for (int k = 0; k < IPT; k++) {
-        const u32 s = tid + k * THREADS;
-        if (s < valid) {
-            const ITEM v = s_items[s];
-            out[s_gofs[rec_digit(v, khi, flip, shift)] + s] = v;
+        for (int k = 0; k < IPT; k++) {
+            const u32 s = tid + k * THREADS;
+            if (s < valid) {
+                const ITEM v = s_items[s];
+                out[s_gofs[rec_digit(v, khi, flip, shift)] + s] = v;
+            }
         }
     }
 }
