@@ -401,10 +401,11 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
 
     /* ---- hybrid: four passes over the most significant digits + run fix-up */
     if (P >= 6 && n >= MPS_HYBRID_MIN_ITEMS && !getenv("MPSORT_NO_HYBRID")) {
-        const uint32_t lobits = 8u * (uint32_t) digits[P - 4];
+        const int H = getenv("MPSORT_HYBRID_PASSES") ? atoi(getenv("MPSORT_HYBRID_PASSES")) : 4;
+        const uint32_t lobits = 8u * (uint32_t) digits[P - H];
         uint32_t hsave[8 * 256];
         memcpy(hsave, hhist, sizeof(hsave));
-        const int yes = hybrid_predictor(c, dbase, n, E, desc, lobits);
+        const int yes = hybrid_predictor(c, dbase, n, E, desc, lobits) || getenv("MPSORT_HYBRID_FORCE");
         {
             /* the predictor's sample sort reused the histogram slot and the host stage:
              * put the big array's histograms and scanned bins back */
@@ -415,7 +416,7 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
             CUDA_OK(c, cudaStreamSynchronize(c->stream));   /* the stage is reused below */
         }
         if (yes) {
-            rec16_passes(c, dbase, n, E, desc, dest, digits + (P - 4), 4, bins, scratch);
+            rec16_passes(c, dbase, n, E, desc, dest, digits + (P - H), H, bins, scratch);
             uint32_t * wl = (uint32_t *) mps_arena_get(c, MPS_S_MERGE_CUT, (2 * MPS_HYBRID_MAX_LONG_RUNS + 64) * sizeof(uint32_t));
             uint32_t * nwork = wl + 2 * MPS_HYBRID_MAX_LONG_RUNS;
             CUDA_OK(c, cudaMemsetAsync(nwork, 0, sizeof(uint32_t), c->stream));
@@ -424,14 +425,14 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
             CUDA_OK(c, cudaMemcpyAsync(h, nwork, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
             CUDA_OK(c, cudaStreamSynchronize(c->stream));
             const uint32_t nlong = h[0];
-            out->npasses = 4;
+            out->npasses = (uint32_t) H;
             c->stats.hybrid = 1;
             c->stats.hybrid_long_runs = nlong;
             if (nlong > MPS_HYBRID_MAX_LONG_RUNS) {
                 /* the predictor was wrong: finish with a full stable LSD of what we have
                  * (a permutation of the input in which equal keys kept their order) */
                 rec16_passes(c, dest, n, E, desc, dest, digits, P, bins, scratch);
-                out->npasses = 4 + (uint32_t) P;
+                out->npasses = (uint32_t) H + (uint32_t) P;
             } else if (nlong > 0) {
                 uint32_t starts[MPS_HYBRID_MAX_LONG_RUNS], lens[MPS_HYBRID_MAX_LONG_RUNS], e;
                 KERN_T(c, MPS_K_HYBRID, mpsk_fixup_extents(dest, n, E, desc->offset == 8, flip, lobits, wl, nlong, wl + MPS_HYBRID_MAX_LONG_RUNS, c->stream));
