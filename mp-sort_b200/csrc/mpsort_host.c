@@ -367,7 +367,7 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
         const struct mpsort_radix_desc * desc, void * dest, struct sorted_view * out)
 {
     const uint64_t flip = desc->is_signed ? (1ULL << 63) : 0ULL;
-    uint32_t d, b;
+    uint32_t d;
     memset(out, 0, sizeof(*out));
     out->nw = 1;
     out->stride = n;
@@ -378,34 +378,65 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
     if (n > MPSK_MAX_ITEMS)
         mps_fatal(c, __FILE__, __LINE__, "%zu local items exceed the supported maximum %zu per rank", n, (size_t) MPSK_MAX_ITEMS);
 
-    uint32_t * hist = (uint32_t *) mps_arena_get(c, MPS_S_HIST, 8 * 256 * sizeof(uint32_t) * 2);
+    uint32_t * hist = (uint32_t *) mps_arena_get(c, MPS_S_HIST, 8 * 256 * sizeof(uint32_t) * 2 + 64);
     uint32_t * bins = hist + 8 * 256;
+    uint64_t * ddiff = (uint64_t *) (bins + 8 * 256);        /* OR of key ^ key[0]: which bytes vary */
     void * scratch = mps_arena_get(c, MPS_S_SCRATCH, mpsk_onesweep_scratch_bytes(n));
+    const int khi = desc->offset == 8;
+    const int hybrid_ok = n >= MPS_HYBRID_MIN_ITEMS && !getenv("MPSORT_NO_HYBRID");
     CUDA_OK(c, cudaMemsetAsync(hist, 0, 8 * 256 * sizeof(uint32_t), c->stream));
-    KERN_T(c, MPS_K_EXTRACT, mpsk_extract_keys(dbase, n, E, desc->offset, 8, 1, desc->is_signed, 0, 0, NULL, hist, NULL, c->stream));
+    CUDA_OK(c, cudaMemsetAsync(ddiff, 0, sizeof(uint64_t), c->stream));
+    /* The hybrid sort only needs the counts of the four most significant digits, and
+     * counting four digits instead of eight makes the histogram pass HBM-bound. A preview
+     * over 4096 evenly spaced keys says whether that is where this input is heading: bytes
+     * that vary in the sample vary in the whole array. */
+    int have_low = 1;
+    if (hybrid_ok && !getenv("MPSORT_NO_HIST4")) {
+        uint64_t * hd = (uint64_t *) mps_host_stage(c, sizeof(uint64_t));
+        KERN_T(c, MPS_K_EXTRACT, mpsk_rec_sample_diff(dbase, n, E, khi, 4096, ddiff, c->stream));
+        CUDA_OK(c, cudaMemcpyAsync(hd, ddiff, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(c, cudaMemsetAsync(ddiff, 0, sizeof(uint64_t), c->stream));
+        CUDA_OK(c, cudaStreamSynchronize(c->stream));
+        int vary = 0, top4 = 1;
+        for (d = 0; d < 8; d++) {
+            const int v = ((*hd >> (8 * d)) & 255u) != 0;
+            vary += v;
+            if (d >= 4 && !v) top4 = 0;
+        }
+        if (top4 && vary >= 6) have_low = 0;
+    }
+    if (have_low) KERN_T(c, MPS_K_EXTRACT, mpsk_rec_histograms(dbase, n, E, khi, flip, 0, 8, hist, ddiff, c->stream));
+    else KERN_T(c, MPS_K_EXTRACT, mpsk_rec_histograms(dbase, n, E, khi, flip, 4, 4, hist, ddiff, c->stream));
     KERN_T(c, MPS_K_EXTRACT, mpsk_scan_histograms(hist, bins, 8, c->stream));
-    uint32_t * hhist = (uint32_t *) mps_host_stage(c, 8 * 256 * sizeof(uint32_t));
+    uint32_t * hhist = (uint32_t *) mps_host_stage(c, 8 * 256 * sizeof(uint32_t) + sizeof(uint64_t));
     CUDA_OK(c, cudaMemcpyAsync(hhist, hist, 8 * 256 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(hhist + 8 * 256, ddiff, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
     int digits[8], P = 0;
-    for (d = 0; d < 8; d++) {
-        int constant = 0;
-        for (b = 0; b < 256; b++) if (hhist[d * 256 + b] == (uint32_t) n) { constant = 1; break; }
-        if (!constant) digits[P++] = (int) d;
+    {
+        uint64_t diff;
+        memcpy(&diff, hhist + 8 * 256, sizeof(diff));
+        for (d = 0; d < 8; d++) if ((diff >> (8 * d)) & 255u) digits[P++] = (int) d;
     }
     out->npasses = (uint32_t) P;
     if (P == 0) {
         if (dest != dbase) CUDA_OK(c, cudaMemcpyAsync(dest, dbase, n * E, cudaMemcpyDeviceToDevice, c->stream));
         return;
     }
+/* counts of the four low digits, when the first histogram pass left them out */
+#define ENSURE_LOW_HISTOGRAMS() do { if (!have_low) { \
+        KERN_T(c, MPS_K_EXTRACT, mpsk_rec_histograms(dbase, n, E, khi, flip, 0, 4, hist, NULL, c->stream)); \
+        KERN_T(c, MPS_K_EXTRACT, mpsk_scan_histograms(hist, bins, 8, c->stream)); \
+        have_low = 1; } } while (0)
 
     /* ---- hybrid: four passes over the most significant digits + run fix-up */
-    if (P >= 6 && n >= MPS_HYBRID_MIN_ITEMS && !getenv("MPSORT_NO_HYBRID")) {
-        const int H = getenv("MPSORT_HYBRID_PASSES") ? atoi(getenv("MPSORT_HYBRID_PASSES")) : 4;
+    if (P >= 6 && hybrid_ok) {
+        const int H = 4;
         const uint32_t lobits = 8u * (uint32_t) digits[P - H];
+        if (digits[P - H] < 4) ENSURE_LOW_HISTOGRAMS();
         uint32_t hsave[8 * 256];
         memcpy(hsave, hhist, sizeof(hsave));
-        const int yes = hybrid_predictor(c, dbase, n, E, desc, lobits) || getenv("MPSORT_HYBRID_FORCE");
+        const int yes = hybrid_predictor(c, dbase, n, E, desc, lobits);
         {
             /* the predictor's sample sort reused the histogram slot and the host stage:
              * put the big array's histograms and scanned bins back */
@@ -431,6 +462,13 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
             if (nlong > MPS_HYBRID_MAX_LONG_RUNS) {
                 /* the predictor was wrong: finish with a full stable LSD of what we have
                  * (a permutation of the input in which equal keys kept their order) */
+                if (!have_low) {
+                    /* (histograms are permutation invariant: counting dest is counting dbase,
+                     * which an in-place sort has already overwritten) */
+                    KERN_T(c, MPS_K_EXTRACT, mpsk_rec_histograms(dest, n, E, khi, flip, 0, 4, hist, NULL, c->stream));
+                    KERN_T(c, MPS_K_EXTRACT, mpsk_scan_histograms(hist, bins, 8, c->stream));
+                    have_low = 1;
+                }
                 rec16_passes(c, dest, n, E, desc, dest, digits, P, bins, scratch);
                 out->npasses = (uint32_t) H + (uint32_t) P;
             } else if (nlong > 0) {
@@ -450,7 +488,9 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
             return;
         }
     }
+    ENSURE_LOW_HISTOGRAMS();
     rec16_passes(c, dbase, n, E, desc, dest, digits, P, bins, scratch);
+#undef ENSURE_LOW_HISTOGRAMS
 }
 
 /* ------------------------------------------------------------------------- */

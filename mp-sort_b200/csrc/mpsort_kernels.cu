@@ -236,6 +236,127 @@ extern "C" int mpsk_extract_keys(const void * base, size_t n, size_t elsize,
     return 0;
 }
 
+/*
+ * Record mode (keys sit in place inside 8- or 16-byte records): digit histograms of NH
+ * consecutive digits d0 .. d0+NH-1 plus the OR of (key ^ key[0]) over all keys. The
+ * OR tells exactly which key bytes vary; the hybrid sort only ever needs the counts of
+ * the four most significant digits, and counting four digits instead of eight takes
+ * the kernel from shared-atomic-bound (1.0 ms per 2^28 keys, ncu: LSU wavefronts 88 %)
+ * to the HBM read time. Same batch trick as extract_kernel for digits that are equal
+ * over a warp's 128 keys.
+ */
+template <int NH>
+__global__ void __launch_bounds__(512)
+rec_hist_kernel(const u64 * __restrict__ words, u32 W, u32 koff, size_t n, u64 flip, u32 d0,
+                u32 * __restrict__ hist, unsigned long long * __restrict__ diff)
+{
+    __shared__ u32 sh[NH * 256];
+    for (u32 t = threadIdx.x; t < NH * 256; t += blockDim.x) sh[t] = 0;
+    __syncthreads();
+    const u64 k0 = words[koff] ^ flip;
+    const size_t per_block = (size_t) blockDim.x * EXTRACT_BATCH;
+    const size_t nblocks_total = (n + per_block - 1) / per_block;
+    const bool lane0 = (threadIdx.x & 31) == 0;
+    const u32 sh0 = 8 * d0;
+    u64 acc = 0;
+    for (size_t blk = blockIdx.x; blk < nblocks_total; blk += gridDim.x) {
+        const size_t i0 = blk * per_block + threadIdx.x;
+        u64 k[EXTRACT_BATCH];
+        bool valid[EXTRACT_BATCH];
+#pragma unroll
+        for (int j = 0; j < EXTRACT_BATCH; j++) {
+            const size_t i = i0 + (size_t) j * blockDim.x;
+            valid[j] = i < n;
+            k[j] = valid[j] ? (words[(size_t) W * i + koff] ^ flip) : k0;
+        }
+        u64 d = 0;
+#pragma unroll
+        for (int j = 0; j < EXTRACT_BATCH; j++) d |= k[j] ^ k0;
+        acc |= d;
+        const bool full = __all_sync(FULL_MASK, valid[EXTRACT_BATCH - 1]);
+        u32 same = 0;
+        if (full) {
+            /* digits equal over the whole batch: compare with the warp's first key */
+            const u64 kw0 = __shfl_sync(FULL_MASK, k[0], 0);
+            u64 dd = 0;
+#pragma unroll
+            for (int j = 0; j < EXTRACT_BATCH; j++) dd |= k[j] ^ kw0;
+            dd >>= sh0;
+            const u32 dlo = __reduce_or_sync(FULL_MASK, (u32) dd);
+            const u32 dhi = NH > 4 ? __reduce_or_sync(FULL_MASK, (u32) (dd >> 32)) : 0u;
+#pragma unroll
+            for (int q = 0; q < NH; q++) {
+                const u32 byte = q < 4 ? ((dlo >> (8 * q)) & 255u) : ((dhi >> (8 * (q - 4))) & 255u);
+                if (byte == 0) same |= 1u << q;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NH; q++) {
+            if (same & (1u << q)) {
+                if (lane0) atomicAdd(&sh[q * 256 + ((u32) (k[0] >> (sh0 + 8 * q)) & 255u)], 32u * EXTRACT_BATCH);
+            } else {
+#pragma unroll
+                for (int j = 0; j < EXTRACT_BATCH; j++)
+                    if (valid[j]) atomicAdd(&sh[q * 256 + ((u32) (k[j] >> (sh0 + 8 * q)) & 255u)], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (u32 t = threadIdx.x; t < NH * 256; t += blockDim.x) {
+        const u32 c = sh[t];
+        if (c) atomicAdd(&hist[d0 * 256 + t], c);
+    }
+    if (diff) {
+        const u32 lo = __reduce_or_sync(FULL_MASK, (u32) acc), hi = __reduce_or_sync(FULL_MASK, (u32) (acc >> 32));
+        if (lane0 && (lo | hi)) atomicOr(diff, ((unsigned long long) hi << 32) | lo);
+    }
+}
+
+/* OR of (key ^ key[0]) over s evenly spaced records: a cheap preview of which key bytes vary */
+__global__ void __launch_bounds__(256)
+rec_sample_diff_kernel(const u64 * __restrict__ words, u32 W, u32 koff, size_t n, u32 s, unsigned long long * __restrict__ diff)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    u64 acc = 0;
+    if (i < s) {
+        const size_t pos = (size_t) (((unsigned __int128) i * n) / s);
+        acc = words[(size_t) W * pos + koff] ^ words[koff];
+    }
+    const u32 lo = __reduce_or_sync(FULL_MASK, (u32) acc), hi = __reduce_or_sync(FULL_MASK, (u32) (acc >> 32));
+    if ((threadIdx.x & 31) == 0 && (lo | hi)) atomicOr(diff, ((unsigned long long) hi << 32) | lo);
+}
+
+extern "C" int mpsk_rec_histograms(const void * recs, size_t n, size_t elsize, int key_in_high, uint64_t flip,
+        uint32_t d0, uint32_t nh, uint32_t * hist, uint64_t * diff, mpsk_stream_t stream)
+{
+    if (n == 0) return 0;
+    if ((elsize != 8 && elsize != 16) || (nh != 4 && nh != 8) || d0 + nh > 8) return (int) cudaErrorInvalidValue;
+    const int threads = 512;
+    size_t blocks = (n + (size_t) threads * EXTRACT_BATCH - 1) / ((size_t) threads * EXTRACT_BATCH);
+    const size_t maxb = (size_t) num_sms() * 8;
+    if (blocks > maxb) blocks = maxb;
+    const u32 W = (u32) (elsize / 8), koff = (key_in_high && elsize == 16) ? 1u : 0u;
+    if (nh == 4)
+        rec_hist_kernel<4><<<(unsigned) blocks, threads, 0, (cudaStream_t) stream>>>(
+            (const u64 *) recs, W, koff, n, (u64) flip, d0, hist, (unsigned long long *) diff);
+    else
+        rec_hist_kernel<8><<<(unsigned) blocks, threads, 0, (cudaStream_t) stream>>>(
+            (const u64 *) recs, W, koff, n, (u64) flip, d0, hist, (unsigned long long *) diff);
+    CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mpsk_rec_sample_diff(const void * recs, size_t n, size_t elsize, int key_in_high, uint32_t s,
+        uint64_t * diff, mpsk_stream_t stream)
+{
+    if (n == 0 || s == 0) return 0;
+    if (elsize != 8 && elsize != 16) return (int) cudaErrorInvalidValue;
+    rec_sample_diff_kernel<<<(s + 255) / 256, 256, 0, (cudaStream_t) stream>>>(
+        (const u64 *) recs, (u32) (elsize / 8), (key_in_high && elsize == 16) ? 1u : 0u, n, s, (unsigned long long *) diff);
+    CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
 /* exclusive scan of nhist 256-bin histograms, one warp-synchronous block each */
 __global__ void __launch_bounds__(256)
 scan_hist_kernel(const u32 * __restrict__ hist, u32 * __restrict__ bins)
@@ -980,17 +1101,22 @@ fixup_rec_kernel(ITEM * __restrict__ recs, u32 n, u64 flip, u32 lobits,
     __shared__ u32 s_nlist;
     if (tid == 0) s_nlist = 0;
     __syncthreads();
+    /* a warp's 32 positions of round k are exactly the bits of head word (warp + 8k):
+     * position i is a run of its own when bits i and i+1 are both set, so the whole
+     * row is decided by two broadcast loads and a few word operations */
 #pragma unroll
     for (int k = 0; k < NLD; k++) {
-        const u32 i = tid + k * FIX_THREADS;
-        const bool single = (i >= cnt) ||
-            (((s_head[i >> 5] >> (i & 31)) & 1u) && ((s_head[(i + 1) >> 5] >> ((i + 1) & 31)) & 1u));
-        const u32 votes = __ballot_sync(FULL_MASK, !single);
+        const u32 w = (tid >> 5) + k * (FIX_THREADS / 32);
+        const u32 H = s_head[w], Hn = s_head[w + 1];
+        const u32 single = H & ((H >> 1) | (Hn << 31));
+        const u32 first = w * 32;
+        const u32 inside = first >= cnt ? 0u : (cnt - first >= 32 ? 0xffffffffu : ((1u << (cnt - first)) - 1u));
+        const u32 votes = ~single & inside;
         if (votes) {
             u32 base = 0;
             if ((tid & 31) == 0) base = atomicAdd(&s_nlist, (u32) __popc(votes));
             base = __shfl_sync(FULL_MASK, base, 0);
-            if (!single) s_list[base + __popc(votes & lanemask_lt())] = i;
+            if ((votes >> (tid & 31)) & 1u) s_list[base + __popc(votes & lanemask_lt())] = first + (tid & 31);
         }
     }
     __syncthreads();

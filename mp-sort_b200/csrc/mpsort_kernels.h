@@ -33,6 +33,16 @@ int mpsk_extract_keys(const void * base, size_t n, size_t elsize,
         size_t offset, uint32_t width, uint32_t nwords, int is_signed,
         uint32_t g, uint64_t sub, uint64_t * kout, uint32_t * hist, uint64_t * minmax, mpsk_stream_t stream);
 
+/* Record mode (elsize 8 or 16, key = one aligned u64 in the low or high half): counts of
+ * the nh (4 or 8) digits d0 .. d0+nh-1 of (key ^ flip) are ADDED to hist[d][256], and the
+ * OR of (key ^ key[0]) over all records is ORed into *diff (device u64, may be NULL):
+ * byte b of *diff is zero exactly when digit b is the same in every key.
+ * mpsk_rec_sample_diff does the OR over s evenly spaced records only (a preview). */
+int mpsk_rec_histograms(const void * recs, size_t n, size_t elsize, int key_in_high, uint64_t flip,
+        uint32_t d0, uint32_t nh, uint32_t * hist, uint64_t * diff, mpsk_stream_t stream);
+int mpsk_rec_sample_diff(const void * recs, size_t n, size_t elsize, int key_in_high, uint32_t s,
+        uint64_t * diff, mpsk_stream_t stream);
+
 /* Exclusive scan of each of `nhist` 256-bin histograms: hist[h][b] -> bins[h][b]. */
 int mpsk_scan_histograms(const uint32_t * hist, uint32_t * bins, int nhist, mpsk_stream_t stream);
 
