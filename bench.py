@@ -335,7 +335,9 @@ def main():
             "config": {"workload": "%s: 2^%d %d-byte records per GPU, %s key, device-resident in/out of place"
                                    % (args.workload, args.log2n, E, "i64" if signed else "u64"),
                        "records_per_gpu": n, "elsize": E, "l2": "inputs (%.1f GiB per GPU) larger than L2; no flush" % (n * E / 2.0**30),
-                       "transport": "none (1 GPU)" if comm.size == 1 else "NCCL grouped send/recv over NVLink",
+                       "transport": "none (1 GPU)" if comm.size == 1 else
+                                    (("peer copies over NVLink (CUDA IPC mapped receive buffers, DMA engines)" if stats.get("p2p_exchange")
+                                      else "NCCL grouped send/recv over NVLink") + ", %d part(s)" % max(1, stats.get("exchange_phases", 1))),
                        "baseline_config": "configs[1]" if comm.size == 1 else "configs[2] shape at %d GPUs" % comm.size},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu,

@@ -218,11 +218,18 @@ mpsort_comm_t mpsort_comm_init_rank(int rank, int size, const void * unique_id, 
     ncclUniqueId uid;
     memcpy(&uid, unique_id, sizeof(uid));
     NCCL_OK(c, ncclCommInitRank(&c->nccl, size, uid, rank));
-    /* peer stores beat NCCL send/recv at 2 GPUs (590 vs 543 GB/s) but not at 4 and 8
-     * (570 vs 619 GB/s at 8; profiles/r01_p2p_exchange.log): default on for pairs only,
-     * MPSORT_P2P=1 forces them for any size, MPSORT_NO_P2P=1 turns them off */
-    c->p2p.disabled = (getenv("MPSORT_NO_P2P") || (size > 2 && !getenv("MPSORT_P2P"))) ? 1 : 0;
+    /* Exchange transport inside one box (profiles/r01_p2p_exchange.log, GB/s per GPU and
+     * direction at 2 / 8 GPUs): peers' receive buffers are mapped with CUDA IPC and every
+     * slice moves by ONE cudaMemcpyAsync at a time in shifted order me+1, me+2, ... (at every
+     * step the pairs form a permutation): 768 / 749, and no SM is busy, so the merge of an
+     * earlier part can overlap. NCCL grouped send/recv: 543 / 649; peer stores from a copy
+     * kernel: 634 / 557; seven DMA copies at once: - / 442.
+     * MPSORT_NO_P2P=1: NCCL send/recv. MPSORT_P2P_CE=0: the copy kernel; =k: k DMA copies in flight. */
+    c->p2p.disabled = getenv("MPSORT_NO_P2P") ? 1 : 0;
     c->p2p.pull = getenv("MPSORT_P2P_PULL") ? 1 : 0;
+    c->p2p.copy_engine = getenv("MPSORT_P2P_CE") ? atoi(getenv("MPSORT_P2P_CE")) : 1;
+    if (c->p2p.copy_engine < 0) c->p2p.copy_engine = 0;
+    if (c->p2p.copy_engine > 7) c->p2p.copy_engine = 7;
     return c;
 }
 
@@ -275,6 +282,10 @@ void mpsort_comm_destroy(mpsort_comm_t c)
     for (s = 0; s < MPS_NSLOTS; s++) if (c->slot[s].ptr) cudaFree(c->slot[s].ptr);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->p2p.d_flag) cudaFree(c->p2p.d_flag);
+    if (c->p2p.ce_created) {
+        for (s = 0; s < 8; s++) cudaStreamDestroy(c->p2p.ce_stream[s]);
+        for (s = 0; s < 9; s++) cudaEventDestroy(c->p2p.ce_ev[s]);
+    }
     if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->phase_ev_created) { int i; for (i = 0; i <= MPS_MAX_RANKS; i++) cudaEventDestroy(c->phase_ev[i]); }
     if (c->kind == MPS_T_NCCL && c->nccl) ncclCommDestroy(c->nccl);
@@ -617,7 +628,29 @@ static void exchange_p2p(struct mpsort_comm * c, const void * sendbuf, const int
             const int q = (me + 1 + k) % p;
             rsrc[k] = src[q]; rdst[k] = dst[q]; rbytes[k] = bytes[q]; rrem[k] = isremote[q];
         }
-        KERN_OK(c, mpsk_p2p_alltoallv(rsrc, rdst, rbytes, rrem, p, c->stream));
+        if (c->p2p.copy_engine) {
+            /* the slices move by DMA: no SM is busy with the exchange, so a merge of an
+             * earlier part (MPSORT_EXCHANGE_PHASES) can have the whole GPU meanwhile */
+            if (!c->p2p.ce_created) {
+                for (k = 0; k < 8; k++) CUDA_OK(c, cudaStreamCreateWithFlags(&c->p2p.ce_stream[k], cudaStreamNonBlocking));
+                for (k = 0; k < 9; k++) CUDA_OK(c, cudaEventCreateWithFlags(&c->p2p.ce_ev[k], cudaEventDisableTiming));
+                c->p2p.ce_created = 1;
+            }
+            CUDA_OK(c, cudaEventRecord(c->p2p.ce_ev[8], c->stream));
+            for (k = 0; k < 8 && k < p; k++) CUDA_OK(c, cudaStreamWaitEvent(c->p2p.ce_stream[k], c->p2p.ce_ev[8], 0));
+            /* remote slices in shifted order (me+1, me+2, ...: at every step the pairs form a
+             * permutation) dealt round-robin to copy_engine streams; my own slice on stream 7 */
+            for (k = 0; k < p; k++)
+                if (rbytes[k])
+                    CUDA_OK(c, cudaMemcpyAsync(rdst[k], rsrc[k], (size_t) rbytes[k], cudaMemcpyDeviceToDevice,
+                                               c->p2p.ce_stream[rrem[k] ? k % c->p2p.copy_engine : 7]));
+            for (k = 0; k < 8 && k < p; k++) {
+                CUDA_OK(c, cudaEventRecord(c->p2p.ce_ev[k], c->p2p.ce_stream[k]));
+                CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->p2p.ce_ev[k], 0));
+            }
+        } else {
+            KERN_OK(c, mpsk_p2p_alltoallv(rsrc, rdst, rbytes, rrem, p, c->stream));
+        }
     }
     /* push: all stores into my buffer are complete when everyone's kernel is; pull: nobody
      * may reuse its send buffer before everyone has read it. A one-word all-reduce on the

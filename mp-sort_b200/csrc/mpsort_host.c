@@ -768,8 +768,11 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
      * rank takes the same branch. */
     int Q = 1;
     {
+        /* default: two parts when the slices move by DMA (the merge of part 0 then overlaps the
+         * transfer of part 1: 21.0 -> 19.2 ms per sort at 8 GPUs), one when SMs do the moving
+         * (transfer and merge then slow each other down, profiles/r01_pipelined_exchange.log) */
         const char * e = getenv("MPSORT_EXCHANGE_PHASES");
-        const int want = e ? atoi(e) : 1;
+        const int want = e ? atoi(e) : ((c->kind == MPS_T_NCCL && !c->p2p.disabled && c->p2p.copy_engine > 0 && !c->p2p.pull) ? 2 : 1);
         if (nw == 1 && p <= 32 && want > 1 && total / p >= ((int64_t) 1 << 22)) {
             Q = want;
             while (Q > 1 && p * Q > MPS_MAX_RANKS) Q--;

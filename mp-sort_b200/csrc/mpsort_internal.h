@@ -108,6 +108,10 @@ struct mpsort_comm {
         void * zombies[64];                    /* my old receive buffers peers may still have mapped */
         int nzombies;
         int * d_flag;                          /* device word for the completion all-reduce */
+        int copy_engine;                       /* 1: slices move by cudaMemcpyAsync (DMA engines, no SMs) */
+        cudaStream_t ce_stream[8];             /* copy-engine mode: peer copies fan out over these */
+        cudaEvent_t ce_ev[9];
+        int ce_created;
     } p2p;
 };
 
