@@ -10,11 +10,14 @@
  *     decoupled look-back status words.
  *
  * Kernel <-> reference map (paths relative to MP-sort v0.1.19):
- *   extract_kernel        radix() callbacks               binding.pyx:81-121, bench-mpi.c:13-15
- *   onesweep_kernel       mpsort_qsort_r / msort_with_tmp stdlib/msort.c:52-174,177-314
- *   gather_records_kernel record moves of the merge sort  stdlib/msort.c:153-173,270-294
- *   splitter_*_kernel     _histogram/_bsearch_last_lt/le  internal-parallel.h:8-126
- *   checksum_kernel       checksum()                      mpsort-mpi.c:148-159
+ *   extract_kernel, rec_hist_kernel   radix() callbacks               binding.pyx:81-121, bench-mpi.c:13-15
+ *   onesweep_kernel, onesweep_rec_kernel, fixup_rec_kernel
+ *                                     mpsort_qsort_r / msort_with_tmp stdlib/msort.c:52-174,177-314
+ *   gather_records_kernel             record moves of the merge sort  stdlib/msort.c:153-173,270-294
+ *   splitter_*_kernel                 _histogram/_bsearch_last_lt/le  internal-parallel.h:8-126
+ *   merge_*_kernel                    the second radix_sort           mpsort-mpi.c:597
+ *   p2p_copy_kernel                   MPIU_Alltoallv                  mp-mpiu.c:69-236
+ *   checksum_kernel                   checksum()                      mpsort-mpi.c:148-159
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -1028,7 +1031,7 @@ extern "C" int mpsk_onesweep_pass_rec(const void * in, void * out, size_t n, siz
  * are still in input order (the passes are stable), so ordering a run stably by the
  * low part gives exactly the order of the full eight-pass sort.
  *
- * fixup_rec16_kernel: one CTA per tile of FIX_T records (+ FIX_HALO look-ahead).
+ * fixup_rec_kernel: one CTA per tile of FIX_T records (+ FIX_HALO look-ahead).
  * A run belongs to the tile that holds its head. Runs of 2..FIX_HALO records are
  * ranked by counting (O(L^2), L is tiny) and rewritten in place; longer runs are
  * appended to a work list and sorted by the host with ordinary passes.

@@ -5,9 +5,11 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "mp-sort_b200"))
-import mpsort
-from mpsort import _capi as C
+import importlib.util
+import threading
+spec = importlib.util.spec_from_file_location("_capi", os.path.join(ROOT, "mp-sort_b200", "mpsort", "_capi.py"))
+C = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(C)
 
 lib = C.lib
 p = int(sys.argv[1]) if len(sys.argv) > 1 else 2
@@ -16,6 +18,11 @@ E = int(sys.argv[3]) if len(sys.argv) > 3 else 16
 kind = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 n = 1 << log2n
 desc = C.RadixDesc(0, 8, 1, 1 if kind == 2 else 0, 0)
+
+
+class _Comm(object):
+    def __init__(self, h):
+        self.handle = h
 
 
 def work(comm):
@@ -33,7 +40,15 @@ def work(comm):
     return kt, bad, C.last_run()
 
 
-res = mpsort.run_local(p, work, devices=[0] * p)
+devs = (ctypes.c_int * p)(*([0] * p))
+comms = (ctypes.c_void_p * p)()
+assert lib.mpsort_comm_init_local_group(p, devs, comms) == 0
+res = [None] * p
+def body(r):
+    res[r] = work(_Comm(ctypes.c_void_p(comms[r])))
+th = [threading.Thread(target=body, args=(r,)) for r in range(p)]
+[t.start() for t in th]
+[t.join() for t in th]
 kt, bad, phases = res[0]
 print("p=%d n=2^%d E=%d kind=%d bad=%s" % (p, log2n, E, kind, [r[1] for r in res]))
 print("  kernels(ms/sort):", "  ".join("%s %.3f/%d" % (k, v[0] / 2, v[1] // 2) for k, v in kt.items() if v[1]))
