@@ -109,6 +109,69 @@ def test_layout_solver_matches_reference_sendcounts(p, distinct):
         assert np.array_equal(sc, info["sendcounts"])
 
 
+@pytest.mark.parametrize("p,Q,distinct", [(2, 2, None), (4, 2, 3), (8, 2, None), (3, 4, 2), (8, 4, 1), (5, 3, None)])
+def test_layout_for_pipelined_exchange_refines_the_reference_layout(p, Q, distinct):
+    """The exchange runs in Q parts per rank (default 2): the layout is solved for p sources x
+    p*Q virtual destinations (mpsort_solve_layout2). Taking every Q-th cut must give exactly
+    the reference layout (mpsort-mpi.c:663-727), and the slices of one virtual destination,
+    concatenated in source order and stably merged, must be that part of the global stable sort."""
+    c_i64 = ctypes.c_int64
+    lib.mpsort_solve_layout2.restype = ctypes.c_int
+    lib.mpsort_solve_layout2.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.POINTER(c_i64)] * 5
+    rng = np.random.default_rng(77 * p + Q)
+    for trial in range(4):
+        sizes = [int(rng.integers(0, 300)) for _ in range(p)]
+        if trial == 1:
+            sizes[p - 1] = 0
+        total = sum(sizes)
+        cuts = sorted(int(c) for c in rng.integers(0, total + 1, size=p - 1))
+        outsizes = [b - a for a, b in zip([0] + cuts, cuts + [total])]
+        keys, tags = [], []
+        for r in range(p):
+            k = rng.integers(0, distinct, size=sizes[r]) if distinct else rng.integers(0, 1 << 62, size=sizes[r])
+            order = np.argsort(k, kind="stable")
+            keys.append(np.asarray(k, dtype="u8")[order])
+            tags.append(((r << 40) + np.arange(sizes[r]))[order])          # (source rank, source index)
+        allk = np.sort(np.concatenate(keys)) if total else np.zeros(0, dtype="u8")
+        pv = p * Q
+        Cv = [0]
+        for j in range(p):
+            for b in range(Q):
+                Cv.append(Cv[-1] + (outsizes[j] * (b + 1) // Q - outsizes[j] * b // Q))
+        assert Cv[-1] == total and [Cv[j * Q] for j in range(p + 1)] == [0] + list(np.cumsum(outsizes))
+
+        def solve(C, nd):
+            splitters = [allk[C[b] - 1] if C[b] > 0 else (allk[0] if total else 0) for b in range(1, nd)]
+            clt = (c_i64 * (p * (nd - 1)))()
+            cle = (c_i64 * (p * (nd - 1)))()
+            for j in range(p):
+                a, b = local_counts(keys[j], splitters)
+                for i in range(nd - 1):
+                    clt[j * (nd - 1) + i] = a[i]
+                    cle[j * (nd - 1) + i] = b[i]
+            cut = (c_i64 * (p * (nd + 1)))()
+            rc = lib.mpsort_solve_layout2(p, nd, (c_i64 * (nd + 1))(*C), clt, cle, (c_i64 * p)(*sizes), cut)
+            assert rc == 0
+            return [[cut[j * (nd + 1) + k] for k in range(nd + 1)] for j in range(p)]
+
+        fine = solve(Cv, pv)
+        coarse = solve([Cv[j * Q] for j in range(p + 1)], p)
+        for j in range(p):
+            assert fine[j][0] == 0 and fine[j][pv] == sizes[j]
+            assert all(fine[j][v] <= fine[j][v + 1] for v in range(pv))
+            assert [fine[j][k * Q] for k in range(p + 1)] == coarse[j]
+        # the global stable sort, ties by (source rank, source index)
+        gk = np.concatenate(keys) if total else np.zeros(0, dtype="u8")
+        gt = np.concatenate(tags) if total else np.zeros(0, dtype="i8")
+        order = np.lexsort((gt, gk))
+        for v in range(pv):
+            assert sum(fine[j][v + 1] - fine[j][v] for j in range(p)) == Cv[v + 1] - Cv[v]
+            part_k = np.concatenate([keys[j][fine[j][v]:fine[j][v + 1]] for j in range(p)])
+            part_t = np.concatenate([tags[j][fine[j][v]:fine[j][v + 1]] for j in range(p)])
+            merged = np.argsort(part_k, kind="stable")            # runs are in source order: stable merge
+            assert np.array_equal(part_t[merged], gt[order][Cv[v]:Cv[v + 1]])
+
+
 def test_layout_solver_reports_reference_bug_conditions():
     """the reference aborts with 'serious bug' (mpsort-mpi.c:707-716); we return codes"""
     p = 2
