@@ -1003,6 +1003,9 @@ onesweep_rec_kernel(const ITEM * __restrict__ in, ITEM * __restrict__ out,
 #ifndef MPSK_REC_PERSIST
 #define MPSK_REC_PERSIST 0
 #endif
+#ifndef MPSK_REC_PERSIST_PREFETCH
+#define MPSK_REC_PERSIST_PREFETCH 1
+#endif
 #if MPSK_REC_PERSIST
 template <int IPT, typename ITEM>
 __device__ __forceinline__ void rec_load_tile(ITEM (&it)[IPT], const ITEM * __restrict__ in, u32 n, u32 tile_base,
@@ -1137,9 +1140,12 @@ onesweep_rec_persist_kernel(const ITEM * __restrict__ in, ITEM * __restrict__ ou
         }
         if (BULK) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 
-        /* ---- the item registers are free: start loading the next tile */
+        /* ---- the item registers are free: start loading the next tile
+         * (MPSK_REC_PERSIST_PREFETCH=0 loads it after the stores instead: isolates the effect) */
         const u32 next = s_misc[12];
+#if MPSK_REC_PERSIST_PREFETCH
         if (next < ntiles) rec_load_tile<IPT, ITEM>(it, in, n, next * (u32) TILE, (u32) TILE, woff, flip);
+#endif
 
         /* ---- decoupled look-back */
         u32 excl = 0;
@@ -1177,6 +1183,9 @@ onesweep_rec_persist_kernel(const ITEM * __restrict__ in, ITEM * __restrict__ ou
         }
         if (next >= ntiles) break;
         tile = next;
+#if !MPSK_REC_PERSIST_PREFETCH
+        rec_load_tile<IPT, ITEM>(it, in, n, tile * (u32) TILE, (u32) TILE, woff, flip);
+#endif
         /* every warp resets its own histogram: past (D) nobody reads it any more, and the
          * other warps touch it again only after (A) of the next tile. (8-byte items: the store
          * loop above reads s_items and s_gofs; both are rewritten only after (B)/(C).) */
