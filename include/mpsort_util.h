@@ -20,6 +20,7 @@ extern "C" {
 int    mpsort_util_device_count(void);
 void * mpsort_util_dev_malloc(int device, size_t nbytes);
 void   mpsort_util_dev_free(int device, void * ptr);
+/* page-locked host memory; NULL if it cannot be pinned */
 void * mpsort_util_host_malloc_pinned(size_t nbytes);
 void   mpsort_util_host_free_pinned(void * ptr);
 /* blocking copy in any direction (cudaMemcpyDefault) */

@@ -30,14 +30,19 @@ void mpsort_util_dev_free(int device, void * ptr)
 
 void * mpsort_util_host_malloc_pinned(size_t nbytes)
 {
+    /* NULL (not fatal) when the box cannot pin that much: the caller may fall back to
+     * pageable memory */
     void * p = NULL;
-    CUDA_OK(NULL, cudaMallocHost(&p, nbytes ? nbytes : 256));
+    if (cudaMallocHost(&p, nbytes ? nbytes : 256) != cudaSuccess) {
+        cudaGetLastError();
+        return NULL;
+    }
     return p;
 }
 
 void mpsort_util_host_free_pinned(void * ptr)
 {
-    CUDA_OK(NULL, cudaFreeHost(ptr));
+    if (ptr) CUDA_OK(NULL, cudaFreeHost(ptr));
 }
 
 void mpsort_util_memcpy(int device, void * dst, const void * src, size_t nbytes)
