@@ -99,6 +99,13 @@ class Clocks(object):
         return out
 
 
+def workload_name(workload, log2n):
+    """the `config.workload` string both arms report"""
+    _, E, signed = KINDS[workload]
+    return ("%s: 2^%d %d-byte records per GPU, %s key, device-resident in/out of place"
+            % (workload, log2n, E, "i64" if signed else "u64"))
+
+
 def run_reference(args, workload, rank):
     """the reference arm: unmodified MP-sort (oracle/_ref/bench16 = bench-mpi's sibling
     for struct records) on the host cores, one MPI-shim rank per core, on a bounded
@@ -128,8 +135,11 @@ def run_reference(args, workload, rank):
         "ms_per_step": r["best_seconds"] * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "gb_per_s": value * elsize / 1e9,
-        "config": {"workload": workload, "records_per_step": per_rank * np_ranks, "elsize": elsize,
-                   "note": "bounded sample of the GPU arm's workload, CPU only"},
+        "config": {"workload": workload_name(workload, args.log2n), "records_per_gpu": 1 << args.log2n, "elsize": elsize,
+                   "baseline_config": "configs[1]" if args.gpus == 1 else "configs[2] shape at %d GPUs" % args.gpus,
+                   "records_per_step": per_rank * np_ranks,
+                   "note": "each step sorts a bounded sample of the GPU arm's workload (same generator, same record "
+                           "layout) with the reference's CPU implementation; no GPU"},
         "cpu_baseline": {"value": value, "unit": "records/s", "cores": np_ranks, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "phases_s": r["phases"], "wall_s": wall, "gpu_launches": 0,
@@ -347,8 +357,7 @@ def main():
             "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "gb_per_s": value * E / 1e9,
-            "config": {"workload": "%s: 2^%d %d-byte records per GPU, %s key, device-resident in/out of place"
-                                   % (args.workload, args.log2n, E, "i64" if signed else "u64"),
+            "config": {"workload": workload_name(args.workload, args.log2n),
                        "records_per_gpu": n, "elsize": E, "l2": "inputs (%.1f GiB per GPU) larger than L2; no flush" % (n * E / 2.0**30),
                        "transport": "none (1 GPU)" if comm.size == 1 else
                                     (("peer copies over NVLink (CUDA IPC mapped receive buffers, DMA engines)" if stats.get("p2p_exchange")
