@@ -159,6 +159,48 @@ void mpsort_mpi_newarray_desc_impl(void * base, size_t nmemb,
 void radix_sort_desc(void * base, size_t nmemb, size_t size,
         const struct mpsort_radix_desc * desc, int device);
 
+/* ------------------------------------------------------------------------- */
+/* The reference's OWN signatures (mpsort.h:1-4, :25-47), for callers that keep a host
+ * radix() callback: e.g. test-issue7.c:12-17 builds its key from two separate fields,
+ * which no single descriptor expresses. A host function pointer cannot run on the
+ * GPU, so the callback is evaluated once per record on the host into the front of an
+ * augmented record {radix | record}; the augmented records are sorted on the GPU by
+ * the descriptor mpsort_callback_desc(rsize) and the records copied back. Same
+ * ordering as the reference (radixsort.c:47-98,178-193: the radix compares as a
+ * little-endian integer of rsize bytes), same in-place / newarray semantics, same
+ * error convention. `base` / `out` must be HOST memory on this path (aborts on a
+ * device pointer: use the descriptor entry points for device-resident data);
+ * 1 <= rsize <= 128. Only the communicator type differs from the reference. */
+typedef void (*mpsort_radix_func)(const void * ptr, void * radix, void * arg);
+
+void mpsort_mpi_impl(void * base, size_t nmemb, size_t elsize,
+        mpsort_radix_func radix, size_t rsize, void * arg,
+        mpsort_comm_t comm, const int line, const char * file);
+#define mpsort_mpi(base, nmemb, elsize, radix, rsize, arg, comm) \
+    mpsort_mpi_impl(base, nmemb, elsize, radix, rsize, arg, comm, __LINE__, __FILE__)
+
+void mpsort_mpi_newarray_impl(void * base, size_t nmemb,
+        void * out, size_t outnmemb, size_t elsize,
+        mpsort_radix_func radix, size_t rsize, void * arg,
+        mpsort_comm_t comm, const int line, const char * file);
+#define mpsort_mpi_newarray(base, nmemb, out, outnmemb, elsize, radix, rsize, arg, comm) \
+    mpsort_mpi_newarray_impl(base, nmemb, out, outnmemb, elsize, radix, rsize, arg, comm, \
+    __LINE__, __FILE__)
+
+/* reference radix_sort (mpsort.h:1-4, radixsort.c:35-44): stable local sort of a host
+ * array on the calling thread's current CUDA device. */
+void radix_sort(void * base, size_t nmemb, size_t size,
+        mpsort_radix_func radix, size_t rsize, void * arg);
+
+/* The pieces of the callback path, exported so that they can be checked without a GPU:
+ * the descriptor + padded radix size an rsize-byte radix sorts under (0, or -1 if rsize is
+ * out of range); the host pass that writes {radix, zero padding to rpad, record} per
+ * record into `aug` (nmemb * (rpad + elsize) bytes); and its inverse. */
+int  mpsort_callback_desc(size_t rsize, struct mpsort_radix_desc * desc, size_t * rpad);
+void mpsort_callback_pack(const void * base, size_t nmemb, size_t elsize,
+        mpsort_radix_func radix, size_t rsize, void * arg, void * aug);
+void mpsort_callback_unpack(const void * aug, size_t nmemb, size_t elsize, size_t rsize, void * out);
+
 /* Replaces mpsort_mpi_report_last_run (mpsort.h:49, mpsort-mpi.c:110-119): prints
  * "<phase>: <seconds>" for FirstSort, PmaxPmin, bisectNNNN, findP, LayDistr,
  * LaySolve, Exchange, SecondSort, measured with CUDA events on the comm's stream. */

@@ -1032,3 +1032,116 @@ void radix_sort_desc(void * base, size_t nmemb, size_t size,
     if (!self[device]) self[device] = mpsort_comm_self(device);
     mpsort_mpi_newarray_desc_impl(base, nmemb, base, nmemb, size, desc, self[device], __LINE__, __FILE__);
 }
+
+/* ------------------------------------------------------------------------- */
+/* the reference's own signatures: host radix() callback + rsize + arg        */
+/*
+ * mpsort_mpi_impl / mpsort_mpi_newarray_impl / radix_sort exactly as declared in the
+ * reference's mpsort.h:1-4,25-47, for callers whose key is not one contiguous field
+ * (test-issue7.c:12-17 builds it from two) and that cannot switch to a descriptor.
+ * A host function pointer cannot run on the GPU, so the callback is evaluated once per
+ * record ON THE HOST (the reference evaluates it twice per comparison,
+ * radixsort.c:19-26) into the front of an augmented record {radix | record}; the
+ * augmented records are sorted on the GPU by the descriptor of that radix and the
+ * records are copied back out. The radix orders as a little-endian integer of rsize
+ * bytes (radixsort.c:47-98,178-193 on a little-endian host): rsize 2/4/8 are native
+ * words, a multiple of 8 is u64 words with the last one most significant, anything
+ * else compares byte-wise from the last byte down.
+ * Buffers must be host memory here; device-resident data needs the descriptor API.
+ * The reference's warnings about element / radix sizes that are large and not a
+ * multiple of 8 (mpsort-mpi.c:200-215) concern MPI datatypes and are not repeated.
+ */
+int mpsort_callback_desc(size_t rsize, struct mpsort_radix_desc * d, size_t * rpad)
+{
+    if (rsize == 0 || rsize > (size_t) MPS_MAX_KEY_WORDS * 8) return -1;
+    memset(d, 0, sizeof(*d));
+    d->offset = 0;
+    if (rsize % 8 == 0) { d->width = 8; d->nwords = (uint32_t) (rsize / 8); }
+    else if (rsize == 4 || rsize == 2) { d->width = (uint32_t) rsize; d->nwords = 1; }
+    else { d->width = 1; d->nwords = (uint32_t) rsize; }
+    *rpad = (rsize + 7) & ~(size_t) 7;       /* keeps the record part 8-byte aligned */
+    return 0;
+}
+
+void mpsort_callback_pack(const void * base, size_t nmemb, size_t elsize,
+        mpsort_radix_func radix, size_t rsize, void * arg, void * aug)
+{
+    const size_t rpad = (rsize + 7) & ~(size_t) 7, E2 = rpad + elsize;
+    const char * src = (const char *) base;
+    char * dst = (char *) aug;
+    size_t i;
+    for (i = 0; i < nmemb; i++) {
+        if (rpad != rsize) memset(dst + rsize, 0, rpad - rsize);
+        radix(src, dst, arg);
+        memcpy(dst + rpad, src, elsize);
+        src += elsize;
+        dst += E2;
+    }
+}
+
+void mpsort_callback_unpack(const void * aug, size_t nmemb, size_t elsize, size_t rsize, void * out)
+{
+    const size_t rpad = (rsize + 7) & ~(size_t) 7, E2 = rpad + elsize;
+    const char * src = (const char *) aug + rpad;
+    char * dst = (char *) out;
+    size_t i;
+    for (i = 0; i < nmemb; i++) {
+        memcpy(dst, src, elsize);
+        src += E2;
+        dst += elsize;
+    }
+}
+
+void mpsort_mpi_newarray_impl(void * base, size_t nmemb,
+        void * out, size_t outnmemb, size_t elsize,
+        mpsort_radix_func radix, size_t rsize, void * arg,
+        mpsort_comm_t c, const int line, const char * file)
+{
+    struct mpsort_radix_desc d;
+    size_t rpad = 0;
+    mps_caller_file = file ? file : "?";
+    mps_caller_line = line;
+    if (!c) { fprintf(stderr, "MPSort: NULL communicator. Caller site: %s:%d\n", mps_caller_file, mps_caller_line); abort(); }
+    if (!radix) mps_fatal(c, __FILE__, __LINE__, "NULL radix callback");
+    if (elsize == 0) mps_fatal(c, __FILE__, __LINE__, "element size is zero");
+    if (mpsort_callback_desc(rsize, &d, &rpad) != 0)
+        mps_fatal(c, __FILE__, __LINE__, "radix size %zu bytes is not in 1 .. %d", rsize, MPS_MAX_KEY_WORDS * 8);
+    CUDA_OK(c, cudaSetDevice(c->device));
+    if ((nmemb && is_device_pointer(c, base)) || (outnmemb && is_device_pointer(c, out)))
+        mps_fatal(c, __FILE__, __LINE__, "a radix() callback runs on the host and cannot read device memory: "
+                                          "pass host buffers, or describe the key with mpsort_mpi_newarray_desc");
+
+    const size_t E2 = rpad + elsize;
+    const int inplace = (out == base);
+    /* in place (out == base) both views share one buffer: size it for the larger count */
+    const size_t nin = (inplace && outnmemb > nmemb) ? outnmemb : nmemb;
+    char * aug_in = (char *) mps_host_malloc("mpsort radix+record (in)", (nin ? nin : 1) * E2, __FILE__, __LINE__);
+    char * aug_out = inplace ? aug_in
+        : (char *) mps_host_malloc("mpsort radix+record (out)", (outnmemb ? outnmemb : 1) * E2, __FILE__, __LINE__);
+    if (!aug_in || !aug_out) mps_fatal(c, __FILE__, __LINE__, "out of host memory for %zu + %zu augmented records of %zu bytes", nmemb, outnmemb, E2);
+    mpsort_callback_pack(base, nmemb, elsize, radix, rsize, arg, aug_in);
+    mpsort_mpi_newarray_desc_impl(aug_in, nmemb, aug_out, outnmemb, E2, &d, c, line, file);
+    mpsort_callback_unpack(aug_out, outnmemb, elsize, rsize, out);
+    if (!inplace) mps_host_free(aug_out, __FILE__, __LINE__);
+    mps_host_free(aug_in, __FILE__, __LINE__);
+}
+
+void mpsort_mpi_impl(void * base, size_t nmemb, size_t elsize,
+        mpsort_radix_func radix, size_t rsize, void * arg,
+        mpsort_comm_t comm, const int line, const char * file)
+{
+    mpsort_mpi_newarray_impl(base, nmemb, base, nmemb, elsize, radix, rsize, arg, comm, line, file);
+}
+
+void radix_sort(void * base, size_t nmemb, size_t size,
+        mpsort_radix_func radix, size_t rsize, void * arg)
+{
+    /* the reference's radix_sort has no communicator: one cached size-1 communicator on
+     * the calling thread's current CUDA device */
+    static __thread mpsort_comm_t self[64];
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess) { cudaGetLastError(); device = 0; }
+    if (device < 0 || device >= 64) device = 0;
+    if (!self[device]) self[device] = mpsort_comm_self(device);
+    mpsort_mpi_newarray_impl(base, nmemb, base, nmemb, size, radix, rsize, arg, self[device], __LINE__, __FILE__);
+}

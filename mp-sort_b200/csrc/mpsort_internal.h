@@ -141,6 +141,10 @@ extern __thread int mps_caller_line;
 #define NCCL_OK(c, call) do { ncclResult_t e__ = (call); if (e__ != ncclSuccess) \
     mps_fatal((c), __FILE__, __LINE__, "NCCL error %d (%s) in %s", (int) e__, ncclGetErrorString(e__), #call); } while (0)
 
+/* ---- host allocations of significance go through the mpiu_set_malloc hook ---- */
+void * mps_host_malloc(const char * name, size_t size, const char * file, int line);
+void mps_host_free(void * ptr, const char * file, int line);
+
 /* ---- arena ---- */
 void * mps_arena_get(struct mpsort_comm * c, int slot, size_t bytes);
 void * mps_host_stage(struct mpsort_comm * c, size_t bytes);
