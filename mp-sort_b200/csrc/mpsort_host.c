@@ -527,7 +527,7 @@ static int merge_received_runs(struct mpsort_comm * c, const void * recvbuf, con
     uint64_t * skeys = (uint64_t *) mps_arena_get(c, MPS_S_MERGE_SAMP, (size_t) (ns ? ns : 1) * sizeof(uint64_t));
     uint32_t * cut = (uint32_t *) mps_arena_get(c, MPS_S_MERGE_CUT, ((size_t) ntiles + 1) * p * sizeof(uint32_t) + 256);
     uint32_t * overflow = cut + ((size_t) ntiles + 1) * p;
-    CUDA_OK(c, cudaMemsetAsync(overflow, 0, sizeof(uint32_t), c->stream));
+    CUDA_OK(c, cudaMemsetAsync(overflow, 0, 2 * sizeof(uint32_t), c->stream));   /* [1]: tiles the bucket candidate handed to the rounds */
     KERN_T(c, MPS_K_MERGE, mpsk_merge_samples(recvbuf, elsize, desc->offset, desc->width, desc->nwords, desc->is_signed,
                                               (uint32_t) p, S, k, rd, ss, skeys, c->stream));
     /* sample keys are already packed (sign-flipped): sort them as bare unsigned u64 records */
@@ -539,10 +539,11 @@ static int merge_received_runs(struct mpsort_comm * c, const void * recvbuf, con
     KERN_T(c, MPS_K_MERGE, mpsk_merge_runs(recvbuf, dout, elsize, desc->offset, desc->width, desc->nwords, desc->is_signed,
                                            (uint32_t) p, S, k, rd, ss, sv.skeys, sv.idx, ntiles, cut, overflow, c->stream));
     {
-        uint32_t * h = (uint32_t *) mps_host_stage(c, sizeof(uint32_t));
-        CUDA_OK(c, cudaMemcpyAsync(h, overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        uint32_t * h = (uint32_t *) mps_host_stage(c, 2 * sizeof(uint32_t));
+        CUDA_OK(c, cudaMemcpyAsync(h, overflow, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         CUDA_OK(c, cudaStreamSynchronize(c->stream));
-        if (*h != 0) mps_fatal(c, __FILE__, __LINE__, "serious bug: %u merge tiles exceeded their bound", *h);
+        if (h[0] != 0) mps_fatal(c, __FILE__, __LINE__, "serious bug: %u merge tiles exceeded their bound", h[0]);
+        c->stats.merge_bucket_fallback_tiles += h[1];
     }
     c->stats.second_sort_merge_tiles += ntiles;
     return 0;

@@ -55,7 +55,7 @@ class LastStats(ctypes.Structure):
                 ("record_mode", ctypes.c_uint32), ("hybrid", ctypes.c_uint32),
                 ("hybrid_long_runs", ctypes.c_uint32), ("rebased", ctypes.c_uint32),
                 ("p2p_exchange", ctypes.c_uint32), ("exchange_phases", ctypes.c_uint32),
-                ("reserved", ctypes.c_uint32)]
+                ("merge_bucket_fallback_tiles", ctypes.c_uint32)]
 
 
 def _proto(name, restype, *argtypes):
