@@ -55,3 +55,50 @@ def test_bucket_merge_matches_oracle():
     rc = subprocess.run([sys.executable, "-c", WORKER % {"root": ROOT}], env=env, timeout=900,
                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     assert rc.returncode == 0 and b"CANDIDATE OK" in rc.stdout, rc.stdout.decode()[-4000:]
+
+
+WORKER_PROPS = r"""
+import sys, os
+sys.path.insert(0, os.path.join(%(root)r, "mp-sort_b200"))
+import ctypes
+import mpsort
+from mpsort import _capi as C
+lib = C.lib
+p, n, E, kind = 4, 1 << 22, %(E)d, %(kind)d
+desc = C.RadixDesc(0, 8, 1, 1 if kind == 2 else 0, 0)
+res = [None] * p
+def work(comm):
+    r = comm.rank
+    buf = lib.mpsort_util_dev_malloc(0, n * E)
+    out = lib.mpsort_util_dev_malloc(0, n * E)
+    lib.mpsort_util_generate(comm.handle, buf, n, E, kind, 0x5EED0001)
+    s1 = lib.mpsort_util_checksum(comm.handle, buf, n * E)
+    lib.mpsort_mpi_newarray_desc_impl(buf, n, out, n, E, ctypes.byref(desc), comm.handle, 0, b"cand")
+    st = C.last_stats(comm.handle, p)
+    s2 = lib.mpsort_util_checksum(comm.handle, out, n * E)
+    fl = (ctypes.c_uint64 * 2)()
+    bad = lib.mpsort_util_check_sorted(comm.handle, out, n, E, ctypes.byref(desc), 1, 8, fl)
+    res[r] = (s1, s2, bad, fl[0], fl[1], st)
+mpsort.run_local(p, work)
+mask = (1 << 64) - 1
+ok = (sum(x[0] for x in res) & mask) == (sum(x[1] for x in res) & mask) and all(x[2] == 0 for x in res)
+ok = ok and all(res[r - 1][4] <= res[r][3] for r in range(1, p))
+print("phases", [x[5]["exchange_phases"] for x in res], "merge tiles", [x[5]["second_sort_merge_tiles"] for x in res],
+      "to the rounds", [x[5]["merge_bucket_fallback_tiles"] for x in res], "record mode", [x[5]["record_mode"] for x in res])
+ok = ok and all(x[5]["exchange_phases"] == 2 for x in res)
+print("CANDIDATE OK" if ok else "CANDIDATE FAILED")
+sys.exit(0 if ok else 1)
+"""
+
+
+@pytest.mark.parametrize("E,kind,extra", [(48, 2, {"MPSORT_PACK_PIPELINE": "1"}),
+                                          (24, 3, {"MPSORT_PACK_PIPELINE": "1"}),
+                                          (16, 0, {"MPSORT_MERGE_BUCKET": "1"}),
+                                          (48, 2, {"MPSORT_MERGE_BUCKET": "1", "MPSORT_PACK_PIPELINE": "1"})])
+def test_candidates_at_2_22_records_per_rank_by_properties(E, kind, extra):
+    """4 rank threads x 2^22 records, exchange in two parts: global order, tie order (tags), checksum
+    of checksums -- with the pipelined pack (index mode) and / or the bucket merge switched on"""
+    env = dict(os.environ, MPSORT_EXCHANGE_PHASES="2", **extra)
+    rc = subprocess.run([sys.executable, "-c", WORKER_PROPS % {"root": ROOT, "E": E, "kind": kind}], env=env, timeout=900,
+                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert rc.returncode == 0 and b"CANDIDATE OK" in rc.stdout, rc.stdout.decode()[-4000:]
