@@ -341,7 +341,7 @@ static void local_sort(struct mpsort_comm * c, const void * dbase, size_t n, siz
  * random record sits in). The run fix-up costs that many comparisons per record, so
  * the hybrid is taken while the estimate stays below 16. */
 static int hybrid_predictor(struct mpsort_comm * c, const void * dbase, size_t n, size_t E,
-        const struct mpsort_radix_desc * desc, uint32_t lobits)
+        const struct mpsort_radix_desc * desc, uint32_t lobits, double * mean_run)
 {
     const uint64_t flip = desc->is_signed ? (1ULL << 63) : 0ULL;
     const uint32_t s = MPS_HYBRID_SAMPLES;
@@ -360,6 +360,8 @@ static int hybrid_predictor(struct mpsort_comm * c, const void * dbase, size_t n
     CUDA_OK(c, cudaMemcpyAsync(h, dcount, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
     const double limit = 8.0 * (double) s * (double) s / (double) n;
+    /* pairs = s^2/(2n) * mean run length */
+    if (mean_run) *mean_run = (double) *h * 2.0 * (double) n / ((double) s * (double) s);
     return (double) *h <= (limit < 8.0 ? 8.0 : limit);
 }
 
@@ -431,12 +433,23 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
 
     /* ---- hybrid: four passes over the most significant digits + run fix-up */
     if (P >= 6 && hybrid_ok) {
-        const int H = 4;
-        const uint32_t lobits = 8u * (uint32_t) digits[P - H];
+        int H = 4;
+        uint32_t lobits = 8u * (uint32_t) digits[P - H];
         if (digits[P - H] < 4) ENSURE_LOW_HISTOGRAMS();
         uint32_t hsave[8 * 256];
         memcpy(hsave, hhist, sizeof(hsave));
-        const int yes = hybrid_predictor(c, dbase, n, E, desc, lobits);
+        double mean_run = 0.0;
+        int yes = hybrid_predictor(c, dbase, n, E, desc, lobits, &mean_run);
+        /* CANDIDATE, off by default (MPSORT_HYBRID_DEPTH5=1; not yet run on a GPU): keys whose four
+         * top digits leave runs of ~16 (mostly sorted ids: fix-up 4.3 ms) are nearly distinct in five;
+         * a fifth pass (1.9 ms) then leaves the fix-up its 1.2 ms. Any depth gives the same bytes. */
+        if (P >= 7 && mean_run > 8.0 && getenv("MPSORT_HYBRID_DEPTH5")) {
+            const uint32_t lobits5 = 8u * (uint32_t) digits[P - 5];
+            double mean_run5 = 0.0;
+            if (hybrid_predictor(c, dbase, n, E, desc, lobits5, &mean_run5) && mean_run5 <= 4.0) {
+                H = 5; lobits = lobits5; yes = 1;
+            }
+        }
         {
             /* the predictor's sample sort reused the histogram slot and the host stage:
              * put the big array's histograms and scanned bins back */
@@ -446,6 +459,7 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
             KERN_T(c, MPS_K_EXTRACT, mpsk_scan_histograms(hist, bins, 8, c->stream));
             CUDA_OK(c, cudaStreamSynchronize(c->stream));   /* the stage is reused below */
         }
+        if (yes && digits[P - H] < 4) ENSURE_LOW_HISTOGRAMS();   /* only ever true for the five-pass depth */
         if (yes) {
             rec16_passes(c, dbase, n, E, desc, dest, digits + (P - H), H, bins, scratch);
             uint32_t * wl = (uint32_t *) mps_arena_get(c, MPS_S_MERGE_CUT, (2 * MPS_HYBRID_MAX_LONG_RUNS + 64) * sizeof(uint32_t));

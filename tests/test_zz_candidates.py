@@ -3,6 +3,8 @@ at hand (end of round 1). They run only with MPSORT_TEST_CANDIDATES=1, so that t
 states what the shipped paths do; tools/candidates_ab.sh runs them and times each candidate.
 
   MPSORT_MERGE_BUCKET=1   one-round bucket merge of the received runs (merge_tile_bucket_kernel)
+  MPSORT_PACK_PIPELINE=1  index mode: pack of exchange part q+1 beside the transfer of part q
+  MPSORT_HYBRID_DEPTH5=1  five high-digit passes when four leave long runs of equal high parts
 """
 import os
 import subprocess
@@ -64,7 +66,7 @@ import ctypes
 import mpsort
 from mpsort import _capi as C
 lib = C.lib
-p, n, E, kind = 4, 1 << 22, %(E)d, %(kind)d
+p, n, E, kind = 4, 1 << %(log2n)d, %(E)d, %(kind)d
 desc = C.RadixDesc(0, 8, 1, 1 if kind == 2 else 0, 0)
 res = [None] * p
 def work(comm):
@@ -84,8 +86,11 @@ mask = (1 << 64) - 1
 ok = (sum(x[0] for x in res) & mask) == (sum(x[1] for x in res) & mask) and all(x[2] == 0 for x in res)
 ok = ok and all(res[r - 1][4] <= res[r][3] for r in range(1, p))
 print("phases", [x[5]["exchange_phases"] for x in res], "merge tiles", [x[5]["second_sort_merge_tiles"] for x in res],
-      "to the rounds", [x[5]["merge_bucket_fallback_tiles"] for x in res], "record mode", [x[5]["record_mode"] for x in res])
+      "to the rounds", [x[5]["merge_bucket_fallback_tiles"] for x in res], "record mode", [x[5]["record_mode"] for x in res],
+      "passes", [x[5]["first_sort_passes"] for x in res])
 ok = ok and all(x[5]["exchange_phases"] == 2 for x in res)
+if %(passes)d:
+    ok = ok and all(x[5]["first_sort_passes"] == %(passes)d for x in res)
 print("CANDIDATE OK" if ok else "CANDIDATE FAILED")
 sys.exit(0 if ok else 1)
 """
@@ -99,6 +104,15 @@ def test_candidates_at_2_22_records_per_rank_by_properties(E, kind, extra):
     """4 rank threads x 2^22 records, exchange in two parts: global order, tie order (tags), checksum
     of checksums -- with the pipelined pack (index mode) and / or the bucket merge switched on"""
     env = dict(os.environ, MPSORT_EXCHANGE_PHASES="2", **extra)
-    rc = subprocess.run([sys.executable, "-c", WORKER_PROPS % {"root": ROOT, "E": E, "kind": kind}], env=env, timeout=900,
-                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    rc = subprocess.run([sys.executable, "-c", WORKER_PROPS % {"root": ROOT, "E": E, "kind": kind, "log2n": 22, "passes": 0}],
+                        env=env, timeout=900, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert rc.returncode == 0 and b"CANDIDATE OK" in rc.stdout, rc.stdout.decode()[-4000:]
+
+
+def test_hybrid_five_passes_on_mostly_sorted_keys():
+    """MPSORT_HYBRID_DEPTH5=1: 4 rank threads x 2^27 mostly sorted 16-byte records (2^29 in total, so that
+    seven key bytes vary and four top digits leave runs of 16): five passes + fix-up, same properties"""
+    env = dict(os.environ, MPSORT_EXCHANGE_PHASES="2", MPSORT_HYBRID_DEPTH5="1")
+    rc = subprocess.run([sys.executable, "-c", WORKER_PROPS % {"root": ROOT, "E": 16, "kind": 1, "log2n": 27, "passes": 5}],
+                        env=env, timeout=900, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     assert rc.returncode == 0 and b"CANDIDATE OK" in rc.stdout, rc.stdout.decode()[-4000:]

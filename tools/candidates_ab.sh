@@ -26,6 +26,16 @@ done
 if [ "$N" -gt 1 ]; then
   echo "== bench.py --gpus $N: default | MPSORT_MERGE_BUCKET=1"
   bash tools/exchange_modes.sh $N "MPSORT_MERGE_BUCKET=0" "MPSORT_MERGE_BUCKET=1"
+  echo "== bench.py --gpus $N --workload mostly_sorted16: default | MPSORT_HYBRID_DEPTH5=1"
+  for cfg in "MPSORT_X=0" "MPSORT_HYBRID_DEPTH5=1"; do
+    echo "-- $cfg"
+    env $cfg python bench.py --gpus $N --steps 3 --warmup 2 --no-e2e --no-cpu-baseline --workload mostly_sorted16 2>/dev/null | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('ms/step %.2f  value %.2f Grec/s'%(d['ms_per_step'], d['value']/1e9)); print('  phases', [(k,round(v,2)) for k,v in d['phases_ms'] if v>0.2]); print('  kern', {k:round(v['ms_per_step'],2) for k,v in d['kernels'].items()}, d['local_sort'])
+"
+  done
   echo "== bench.py --gpus $N --workload particles48: default | MPSORT_PACK_PIPELINE=1 | + MPSORT_EXCHANGE_PHASES=4"
   for cfg in "MPSORT_X=0" "MPSORT_PACK_PIPELINE=1" "MPSORT_PACK_PIPELINE=1 MPSORT_EXCHANGE_PHASES=4" "MPSORT_PACK_PIPELINE=1 MPSORT_MERGE_BUCKET=1"; do
     echo "-- $cfg"
