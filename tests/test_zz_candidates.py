@@ -90,7 +90,8 @@ print("phases", [x[5]["exchange_phases"] for x in res], "merge tiles", [x[5]["se
       "passes", [x[5]["first_sort_passes"] for x in res])
 ok = ok and all(x[5]["exchange_phases"] == 2 for x in res)
 if %(passes)d:
-    ok = ok and all(x[5]["first_sort_passes"] == %(passes)d for x in res)
+    # which key bytes vary is a per-rank fact (the swapped keys of a neighbour decide): at least one rank
+    ok = ok and any(x[5]["first_sort_passes"] == %(passes)d for x in res)
 print("CANDIDATE OK" if ok else "CANDIDATE FAILED")
 sys.exit(0 if ok else 1)
 """
