@@ -1059,14 +1059,20 @@ void mpsort_mpi_desc_impl(void * base, size_t nmemb, size_t elsize,
     mpsort_mpi_newarray_desc_impl(base, nmemb, base, nmemb, elsize, desc, comm, line, file);
 }
 
-void radix_sort_desc(void * base, size_t nmemb, size_t size,
-        const struct mpsort_radix_desc * desc, int device)
+/* one cached size-1 communicator (stream + arena) per device and thread, shared by
+ * radix_sort_desc and radix_sort */
+static mpsort_comm_t cached_self_comm(int device)
 {
-    /* one cached size-1 communicator per device and thread */
     static __thread mpsort_comm_t self[64];
     if (device < 0 || device >= 64) { fprintf(stderr, "MPSort: bad device %d\n", device); abort(); }
     if (!self[device]) self[device] = mpsort_comm_self(device);
-    mpsort_mpi_newarray_desc_impl(base, nmemb, base, nmemb, size, desc, self[device], __LINE__, __FILE__);
+    return self[device];
+}
+
+void radix_sort_desc(void * base, size_t nmemb, size_t size,
+        const struct mpsort_radix_desc * desc, int device)
+{
+    mpsort_mpi_newarray_desc_impl(base, nmemb, base, nmemb, size, desc, cached_self_comm(device), __LINE__, __FILE__);
 }
 
 /* ------------------------------------------------------------------------- */
@@ -1172,12 +1178,10 @@ void mpsort_mpi_impl(void * base, size_t nmemb, size_t elsize,
 void radix_sort(void * base, size_t nmemb, size_t size,
         mpsort_radix_func radix, size_t rsize, void * arg)
 {
-    /* the reference's radix_sort has no communicator: one cached size-1 communicator on
-     * the calling thread's current CUDA device */
-    static __thread mpsort_comm_t self[64];
+    /* the reference's radix_sort has no communicator: the cached size-1 communicator of the
+     * calling thread's current CUDA device */
     int device = 0;
     if (cudaGetDevice(&device) != cudaSuccess) { cudaGetLastError(); device = 0; }
     if (device < 0 || device >= 64) device = 0;
-    if (!self[device]) self[device] = mpsort_comm_self(device);
-    mpsort_mpi_newarray_impl(base, nmemb, base, nmemb, size, radix, rsize, arg, self[device], __LINE__, __FILE__);
+    mpsort_mpi_newarray_impl(base, nmemb, base, nmemb, size, radix, rsize, arg, cached_self_comm(device), __LINE__, __FILE__);
 }
