@@ -658,3 +658,33 @@ static void exchange_p2p(struct mpsort_comm * c, const void * sendbuf, const int
     NCCL_OK(c, ncclAllReduce(c->p2p.d_flag, c->p2p.d_flag, 1, ncclInt32, ncclSum, c->nccl, c->stream));
     if (bytes_remote) *bytes_remote += remote;
 }
+
+/* CANDIDATE (MPSORT_FUSED_PACK=1, push transport only): one phase of the exchange straight from the
+ * unsorted records `base` and the sorted permutation `idx`: my records at sorted positions
+ * [sendoff[k], sendoff[k] + sendcnt[k]) go to item peer_recvoff[k] of rank k's receive buffer.
+ * Same completion barrier as exchange_p2p. Needs a successful mps_comm_p2p_prepare. */
+void mps_comm_exchange_gather(struct mpsort_comm * c, const void * base, const uint32_t * idx,
+        const int64_t * sendoff, const int64_t * sendcnt, void * recvbuf, const int64_t * peer_recvoff,
+        size_t elsize, uint64_t * bytes_remote)
+{
+    const int p = c->size, me = c->rank;
+    int k;
+    const uint32_t * sidx[MPS_MAX_RANKS];
+    void * dst[MPS_MAX_RANKS];
+    uint64_t nrec[MPS_MAX_RANKS], remote = 0;
+    if (!c->p2p.d_flag) {
+        CUDA_OK(c, cudaMalloc((void **) &c->p2p.d_flag, 256));
+        CUDA_OK(c, cudaMemsetAsync(c->p2p.d_flag, 0, 256, c->stream));
+    }
+    /* segments in shifted order: me+1, me+2, ..., me (self last) */
+    for (k = 0; k < p; k++) {
+        const int q = (me + 1 + k) % p;
+        sidx[k] = idx + sendoff[q];
+        dst[k] = (char *) (q == me ? recvbuf : c->p2p.peer_base[q]) + (size_t) peer_recvoff[q] * elsize;
+        nrec[k] = (uint64_t) sendcnt[q];
+        if (q != me) remote += (uint64_t) sendcnt[q] * elsize;
+    }
+    KERN_OK(c, mpsk_p2p_gather_alltoallv(base, sidx, dst, nrec, elsize, p, c->stream));
+    NCCL_OK(c, ncclAllReduce(c->p2p.d_flag, c->p2p.d_flag, 1, ncclInt32, ncclSum, c->nccl, c->stream));
+    if (bytes_remote) *bytes_remote += remote;
+}

@@ -892,8 +892,13 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
     /* CANDIDATE, off by default (MPSORT_PACK_PIPELINE=1; not yet run on a GPU): with Q > 1 parts the
      * slices of part q+1 are packed on the second stream while part q is in flight, instead of packing
      * everything first (48-byte particles at 8 GPUs: pack 8.7 ms, then 21.5 ms of exchange). */
-    const int pack_pipe = Q > 1 && v1.sorted_recs != sendbuf && getenv("MPSORT_PACK_PIPELINE") != NULL;
-    if (v1.sorted_recs != sendbuf && !pack_pipe)
+    /* CANDIDATE, off by default (MPSORT_FUSED_PACK=1; not yet run on a GPU): index mode over mapped
+     * peer buffers skips the pack: one kernel gathers by sorted index and stores into the peers'
+     * receive buffers (mps_comm_exchange_gather). use_p2p is a collective verdict, so is this. */
+    const int fused_pack = use_p2p && !c->p2p.pull && v1.sorted_recs != sendbuf && n <= 0xffffffffu
+                           && getenv("MPSORT_FUSED_PACK") != NULL;
+    const int pack_pipe = !fused_pack && Q > 1 && v1.sorted_recs != sendbuf && getenv("MPSORT_PACK_PIPELINE") != NULL;
+    if (v1.sorted_recs != sendbuf && !pack_pipe && !fused_pack)
         KERN_T(c, MPS_K_GATHER_RECORDS, mpsk_gather_records(dbase, v1.idx, sendbuf, n, elsize, c->stream));
     timer_mark(c, "Pack");
     const int dense = mpsort_mpi_has_options(MPSORT_DISABLE_SPARSE_ALLTOALLV)
@@ -939,8 +944,11 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
             if (q > 0) CUDA_OK(c, cudaStreamWaitEvent(c->stream, pev[q], 0));
         }
         mps_kt_begin(c, MPS_K_EXCHANGE);
-        mps_comm_exchange(c, sendbuf, sendoff, sendcnt, recvbuf, PARTBASE(me, q), recvcnt_q[q], peer_recvoff, peer_sendoff,
-                          elsize, dense, use_p2p, &c->stats.bytes_sent_remote);
+        if (fused_pack)
+            mps_comm_exchange_gather(c, dbase, v1.idx, sendoff, sendcnt, recvbuf, peer_recvoff, elsize, &c->stats.bytes_sent_remote);
+        else
+            mps_comm_exchange(c, sendbuf, sendoff, sendcnt, recvbuf, PARTBASE(me, q), recvcnt_q[q], peer_recvoff, peer_sendoff,
+                              elsize, dense, use_p2p, &c->stats.bytes_sent_remote);
         mps_kt_end(c);
         CUDA_OK(c, cudaEventRecord(c->phase_ev[q], c->stream));
     }
@@ -957,7 +965,9 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
             int64_t rdispl[MPS_MAX_RANKS + 1];
             rdispl[0] = 0;
             for (j = 0; j < p; j++) rdispl[j + 1] = rdispl[j] + recvcnt_q[q][j];
-            if (Q > 1) CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->phase_ev[q], 0));
+            /* (the fused pack candidate reads the input and the sorted permutation until its last
+             * part is out, and the merge's sample sort reuses those arena slots: no merge before that) */
+            if (Q > 1) CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->phase_ev[fused_pack ? Q - 1 : q], 0));
             char * part_in = (char *) recvbuf + (size_t) base * elsize;
             char * part_out = (char *) dout + (size_t) base * elsize;
             if (merge_received_runs(c, part_in, rdispl, part_out, (size_t) cnt, elsize, desc) != 0) {

@@ -166,6 +166,12 @@ void mps_comm_exchange(struct mpsort_comm * c, const void * sendbuf, const int64
         const int64_t * peer_recvoff, const int64_t * peer_sendoff,
         size_t elsize, int dense, int use_p2p, uint64_t * bytes_remote);
 
+/* CANDIDATE (MPSORT_FUSED_PACK=1): the same phase from the unsorted records and the sorted
+ * permutation, gather and peer stores in one kernel (push transport, after mps_comm_p2p_prepare) */
+void mps_comm_exchange_gather(struct mpsort_comm * c, const void * base, const uint32_t * idx,
+        const int64_t * sendoff, const int64_t * sendcnt, void * recvbuf, const int64_t * peer_recvoff,
+        size_t elsize, uint64_t * bytes_remote);
+
 /* ---- layout solver (mpsort_layout.c; pure host arithmetic, unit-testable) ---- */
 /* C[p+1] desired cumulative output counts; clt/cle[j*(p-1) + b] local counts of rank j
  * for splitter b; nmemb[j]; writes cut[j*(p+1) + k]. Returns 0, or a negative code on

@@ -158,6 +158,12 @@ int mpsk_merge_runs(const void * recv, void * out, size_t elsize, size_t offset,
 int mpsk_p2p_alltoallv(const void * const * src, void * const * dst, const uint64_t * bytes,
         const unsigned char * remote, int nseg, mpsk_stream_t stream);
 
+/* CANDIDATE (MPSORT_FUSED_PACK=1): pack + exchange of index mode in one kernel. Segment k stores
+ * the nrec[k] records base[idx[k][0 .. nrec[k])] (elsize bytes each) consecutively at dst[k] (a
+ * peer's mapped receive buffer or local memory). */
+int mpsk_p2p_gather_alltoallv(const void * base, const uint32_t * const * idx, void * const * dst,
+        const uint64_t * nrec, size_t elsize, int nseg, mpsk_stream_t stream);
+
 /* K8: reference checksum (mpsort-mpi.c:148-159): sum of all bytes as SIGNED chars,
  * wrapping in 64 bits; accumulated (atomicAdd) into *sum which the caller zeroes. */
 int mpsk_checksum(const void * base, size_t nbytes, uint64_t * sum, mpsk_stream_t stream);

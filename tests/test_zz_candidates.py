@@ -5,6 +5,7 @@ states what the shipped paths do; tools/candidates_ab.sh runs them and times eac
   MPSORT_MERGE_BUCKET=1   one-round bucket merge of the received runs (merge_tile_bucket_kernel)
   MPSORT_PACK_PIPELINE=1  index mode: pack of exchange part q+1 beside the transfer of part q
   MPSORT_HYBRID_DEPTH5=1  five high-digit passes when four leave long runs of equal high parts
+  MPSORT_FUSED_PACK=1     index mode: gather by sorted index + peer stores in one kernel (needs >= 2 GPUs)
 """
 import os
 import subprocess
@@ -117,3 +118,19 @@ def test_hybrid_five_passes_on_mostly_sorted_keys():
     rc = subprocess.run([sys.executable, "-c", WORKER_PROPS % {"root": ROOT, "E": 16, "kind": 1, "log2n": 27, "passes": 5}],
                         env=env, timeout=900, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     assert rc.returncode == 0 and b"CANDIDATE OK" in rc.stdout, rc.stdout.decode()[-4000:]
+
+
+def test_fused_pack_exchange_over_nccl_processes():
+    """MPSORT_FUSED_PACK=1 needs mapped peer buffers, i.e. one process per GPU: the NCCL worker of the
+    default suite (48-byte and 16-byte records, uneven sizes, all tunings) with the candidate on"""
+    sys.path.insert(0, os.path.join(ROOT, "mp-sort_b200"))
+    from mpsort import _capi as C
+    ngpu = min(C.lib.mpsort_util_device_count(), 8)
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29519", MPSORT_FUSED_PACK="1")
+    rc = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(ngpu),
+                         "--master-addr", "127.0.0.1", "--master-port", "29519",
+                         os.path.join(ROOT, "tests", "nccl_worker.py")], env=env, timeout=600,
+                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert rc.returncode == 0 and b"NCCL PARITY OK" in rc.stdout, rc.stdout.decode()[-4000:]

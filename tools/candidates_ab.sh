@@ -36,8 +36,9 @@ for l in sys.stdin:
         d=json.loads(l); print('ms/step %.2f  value %.2f Grec/s'%(d['ms_per_step'], d['value']/1e9)); print('  phases', [(k,round(v,2)) for k,v in d['phases_ms'] if v>0.2]); print('  kern', {k:round(v['ms_per_step'],2) for k,v in d['kernels'].items()}, d['local_sort'])
 "
   done
-  echo "== bench.py --gpus $N --workload particles48: default | MPSORT_PACK_PIPELINE=1 | + MPSORT_EXCHANGE_PHASES=4"
-  for cfg in "MPSORT_X=0" "MPSORT_PACK_PIPELINE=1" "MPSORT_PACK_PIPELINE=1 MPSORT_EXCHANGE_PHASES=4" "MPSORT_PACK_PIPELINE=1 MPSORT_MERGE_BUCKET=1"; do
+  echo "== bench.py --gpus $N --workload particles48: default | pipelined pack (2, 4 parts, + bucket merge) | fused pack + peer stores"
+  for cfg in "MPSORT_X=0" "MPSORT_PACK_PIPELINE=1" "MPSORT_PACK_PIPELINE=1 MPSORT_EXCHANGE_PHASES=4" "MPSORT_PACK_PIPELINE=1 MPSORT_MERGE_BUCKET=1" \
+             "MPSORT_FUSED_PACK=1 MPSORT_P2P_CE=0 MPSORT_EXCHANGE_PHASES=1" "MPSORT_FUSED_PACK=1 MPSORT_P2P_CE=0 MPSORT_EXCHANGE_PHASES=1 MPSORT_P2P_CTAS_PER_SM=1"; do
     echo "-- $cfg"
     env $cfg python bench.py --gpus $N --steps 3 --warmup 2 --no-e2e --no-cpu-baseline --workload particles48 2>/dev/null | python -c "
 import sys,json
