@@ -277,7 +277,10 @@ void mpsort_comm_destroy(mpsort_comm_t c)
     cudaStreamSynchronize(c->stream);
     for (s = 0; s < c->size && c->kind == MPS_T_NCCL; s++)
         if (c->p2p.peer_base[s]) cudaIpcCloseMemHandle(c->p2p.peer_base[s]);
+    if (c->kind == MPS_T_NCCL && c->peer.state > 0)
+        for (s = 0; s < c->size; s++) if (s != c->rank && c->peer.box[s]) cudaIpcCloseMemHandle(c->peer.box[s]);
     if (c->kind == MPS_T_NCCL && c->size > 1) mpsort_comm_barrier(c);   /* everyone unmapped before anyone frees */
+    if (c->peer.mine) cudaFree(c->peer.mine);
     for (s = 0; s < c->p2p.nzombies; s++) cudaFree(c->p2p.zombies[s]);
     for (s = 0; s < MPS_NSLOTS; s++) if (c->slot[s].ptr) cudaFree(c->slot[s].ptr);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -687,4 +690,79 @@ void mps_comm_exchange_gather(struct mpsort_comm * c, const void * base, const u
     KERN_OK(c, mpsk_p2p_gather_alltoallv(base, sidx, dst, nrec, elsize, p, c->stream));
     NCCL_OK(c, ncclAllReduce(c->p2p.d_flag, c->p2p.d_flag, 1, ncclInt32, ncclSum, c->nccl, c->stream));
     if (bytes_remote) *bytes_remote += remote;
+}
+
+/* ------------------------------------------------------------------------- */
+/* CANDIDATE (MPSORT_PEER_SPLITTER=1): mailboxes of the one-kernel splitter descent */
+
+int mps_comm_peer_boxes_prepare(struct mpsort_comm * c)
+{
+    int j, ok = 1;
+    if (c->peer.state) return c->peer.state > 0;
+    if (c->kind == MPS_T_SELF || c->size > MPS_MAX_RANKS) { c->peer.state = -1; return 0; }
+    const size_t bytes = mpsk_peer_box_bytes();
+    CUDA_OK(c, cudaSetDevice(c->device));
+    CUDA_OK(c, cudaMalloc(&c->peer.mine, bytes + 256));
+    CUDA_OK(c, cudaMemsetAsync(c->peer.mine, 0, bytes + 256, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    c->peer.box[c->rank] = c->peer.mine;
+    if (c->kind == MPS_T_LOCAL) {
+        c->grp->slot[c->rank] = c->peer.mine;
+        local_barrier(c);
+        for (j = 0; j < c->size; j++) c->peer.box[j] = (void *) c->grp->slot[j];
+        local_barrier(c);
+        c->peer.state = 1;
+        return 1;
+    }
+    struct { int ok; unsigned char handle[64]; } mine, all[MPS_MAX_RANKS];
+    memset(&mine, 0, sizeof(mine));
+    cudaIpcMemHandle_t hdl;
+    if (cudaIpcGetMemHandle(&hdl, c->peer.mine) == cudaSuccess) {
+        mine.ok = 1;
+        memcpy(mine.handle, &hdl, sizeof(hdl) <= sizeof(mine.handle) ? sizeof(hdl) : sizeof(mine.handle));
+    } else cudaGetLastError();
+    mpsort_comm_allgather_host(c, &mine, all, sizeof(mine));
+    for (j = 0; j < c->size; j++) if (!all[j].ok) ok = 0;
+    int mine_ok = ok;
+    for (j = 0; j < c->size && mine_ok; j++) {
+        if (j == c->rank) continue;
+        void * p = NULL;
+        memcpy(&hdl, all[j].handle, sizeof(hdl));
+        if (cudaIpcOpenMemHandle(&p, hdl, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); mine_ok = 0; break; }
+        c->peer.box[j] = p;
+    }
+    char flag = (char) mine_ok, flags[MPS_MAX_RANKS];
+    mpsort_comm_allgather_host(c, &flag, flags, 1);
+    for (j = 0; j < c->size; j++) if (!flags[j]) ok = 0;
+    if (!ok) {
+        for (j = 0; j < c->size; j++)
+            if (j != c->rank && c->peer.box[j]) { cudaIpcCloseMemHandle(c->peer.box[j]); c->peer.box[j] = NULL; }
+        c->peer.state = -1;
+        if (c->rank == 0) fprintf(stderr, "MPSort: mailboxes of the peer splitter kernel cannot be mapped; using ncclAllReduce per level\n");
+        return 0;
+    }
+    c->peer.state = 1;
+    return 1;
+}
+
+int mps_comm_peer_descent(struct mpsort_comm * c, struct mpsk_keyview kv, size_t n, uint32_t nw,
+        uint64_t * d_prefix, const uint64_t * d_target, int ns, int level0, int nlevels)
+{
+    uint32_t * d_err = (uint32_t *) ((char *) c->peer.mine + mpsk_peer_box_bytes());
+    /* rank threads that share a GPU: a cudaMalloc / cudaFree of a slower rank (arena growth before
+     * its own launch) would wait for the device, i.e. for my spinning kernel, which waits for that
+     * rank's kernel. Launch together: nothing allocates between here and the check. */
+    if (c->kind == MPS_T_LOCAL) local_barrier(c);
+    const int rc = mpsk_splitter_descent_peer(kv, n, nw, d_prefix, d_target, ns, level0, nlevels,
+                                              (uint32_t) c->rank, (uint32_t) c->size, c->peer.box, c->peer.seq, d_err, c->stream);
+    c->peer.seq += 256;
+    return rc;
+}
+
+void mps_comm_peer_descent_check(struct mpsort_comm * c)
+{
+    uint32_t * h = (uint32_t *) mps_host_stage(c, sizeof(uint32_t));
+    CUDA_OK(c, cudaMemcpyAsync(h, (char *) c->peer.mine + mpsk_peer_box_bytes(), sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    if (*h) mps_fatal(c, __FILE__, __LINE__, "the peer splitter kernel waited too long for another rank");
 }

@@ -822,7 +822,18 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
         CUDA_OK(c, cudaMemcpyAsync(d_prefix, h, ((size_t) ns * nw + ns) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
     }
     int level, round = 0;
-    for (level = level0; level < nlevels; level++) {
+    /* CANDIDATE, off by default (MPSORT_PEER_SPLITTER=1; not yet run on a GPU): every level in one
+     * kernel per GPU, the sums taken over mapped peer memory (mpsk_splitter_descent_peer). The
+     * switch must be set on all ranks or on none; mapping failures fall back together. */
+    const int peer_desc = ns > 0 && ns <= 63 && level0 < nlevels && getenv("MPSORT_PEER_SPLITTER") != NULL
+                          && mps_comm_peer_boxes_prepare(c);
+    if (peer_desc) {
+        KERN_T(c, MPS_K_SPLITTER, mps_comm_peer_descent(c, v1.kv, n, nw, d_prefix, d_target, ns, level0, nlevels));
+        mps_comm_peer_descent_check(c);
+        round = nlevels - level0;
+        timer_mark(c, "bisect0001");
+    }
+    for (level = level0; level < nlevels && !peer_desc; level++) {
         KERN_T(c, MPS_K_SPLITTER, mpsk_splitter_count(v1.kv, n, nw, d_prefix, ns, level, d_counts, c->stream));
         mps_comm_allreduce_u64_dev(c, d_counts, (size_t) ns * 256);
         KERN_T(c, MPS_K_SPLITTER, mpsk_splitter_select(d_counts, d_target, d_prefix, nw, ns, level, c->stream));

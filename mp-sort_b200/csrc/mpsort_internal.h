@@ -99,6 +99,14 @@ struct mpsort_comm {
     cudaEvent_t phase_ev[MPS_MAX_RANKS + 1];
     int phase_ev_created;
 
+    /* CANDIDATE (MPSORT_PEER_SPLITTER=1): mailboxes of the one-kernel splitter descent */
+    struct {
+        int state;                             /* 0 not tried yet, 1 ready, -1 unavailable */
+        void * mine;                           /* my mailbox + error word (cudaMalloc) */
+        void * box[MPS_MAX_RANKS];             /* rank j's mailbox as mapped here */
+        uint32_t seq;                          /* 256 * sorts that used the kernel so far */
+    } peer;
+
     /* peer-store exchange (NCCL transport only): every rank's receive buffer mapped here */
     struct {
         int disabled;                          /* env MPSORT_NO_P2P, or a mapping failed somewhere */
@@ -171,6 +179,14 @@ void mps_comm_exchange(struct mpsort_comm * c, const void * sendbuf, const int64
 void mps_comm_exchange_gather(struct mpsort_comm * c, const void * base, const uint32_t * idx,
         const int64_t * sendoff, const int64_t * sendcnt, void * recvbuf, const int64_t * peer_recvoff,
         size_t elsize, uint64_t * bytes_remote);
+
+/* CANDIDATE (MPSORT_PEER_SPLITTER=1): collective; 1 when every rank has every mailbox mapped */
+int mps_comm_peer_boxes_prepare(struct mpsort_comm * c);
+/* all descent levels in one kernel (mpsk_splitter_descent_peer); returns a CUDA error code */
+int mps_comm_peer_descent(struct mpsort_comm * c, struct mpsk_keyview kv, size_t n, uint32_t nw,
+        uint64_t * d_prefix, const uint64_t * d_target, int ns, int level0, int nlevels);
+/* after the stream was synchronised: aborts the job if a peer never answered */
+void mps_comm_peer_descent_check(struct mpsort_comm * c);
 
 /* ---- layout solver (mpsort_layout.c; pure host arithmetic, unit-testable) ---- */
 /* C[p+1] desired cumulative output counts; clt/cle[j*(p-1) + b] local counts of rank j

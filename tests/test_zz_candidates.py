@@ -6,6 +6,7 @@ states what the shipped paths do; tools/candidates_ab.sh runs them and times eac
   MPSORT_PACK_PIPELINE=1  index mode: pack of exchange part q+1 beside the transfer of part q
   MPSORT_HYBRID_DEPTH5=1  five high-digit passes when four leave long runs of equal high parts
   MPSORT_FUSED_PACK=1     index mode: gather by sorted index + peer stores in one kernel (needs >= 2 GPUs)
+  MPSORT_PEER_SPLITTER=1  all levels of the splitter descent in one kernel, sums over mapped peer memory
 """
 import os
 import subprocess
@@ -53,8 +54,10 @@ sys.exit(0 if ok else 1)
 """
 
 
-def test_bucket_merge_matches_oracle():
-    env = dict(os.environ, MPSORT_MERGE_BUCKET="1")
+@pytest.mark.parametrize("switch", ["MPSORT_MERGE_BUCKET", "MPSORT_PEER_SPLITTER"])
+def test_candidate_matches_oracle(switch):
+    """bit-exact against the oracle on 2-8 rank threads, 16/24/48-byte records, all three key kinds"""
+    env = dict(os.environ, **{switch: "1"})
     rc = subprocess.run([sys.executable, "-c", WORKER % {"root": ROOT}], env=env, timeout=900,
                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     assert rc.returncode == 0 and b"CANDIDATE OK" in rc.stdout, rc.stdout.decode()[-4000:]
@@ -101,7 +104,8 @@ sys.exit(0 if ok else 1)
 @pytest.mark.parametrize("E,kind,extra", [(48, 2, {"MPSORT_PACK_PIPELINE": "1"}),
                                           (24, 3, {"MPSORT_PACK_PIPELINE": "1"}),
                                           (16, 0, {"MPSORT_MERGE_BUCKET": "1"}),
-                                          (48, 2, {"MPSORT_MERGE_BUCKET": "1", "MPSORT_PACK_PIPELINE": "1"})])
+                                          (48, 2, {"MPSORT_MERGE_BUCKET": "1", "MPSORT_PACK_PIPELINE": "1"}),
+                                          (16, 0, {"MPSORT_PEER_SPLITTER": "1"})])
 def test_candidates_at_2_22_records_per_rank_by_properties(E, kind, extra):
     """4 rank threads x 2^22 records, exchange in two parts: global order, tie order (tags), checksum
     of checksums -- with the pipelined pack (index mode) and / or the bucket merge switched on"""
@@ -120,15 +124,16 @@ def test_hybrid_five_passes_on_mostly_sorted_keys():
     assert rc.returncode == 0 and b"CANDIDATE OK" in rc.stdout, rc.stdout.decode()[-4000:]
 
 
-def test_fused_pack_exchange_over_nccl_processes():
-    """MPSORT_FUSED_PACK=1 needs mapped peer buffers, i.e. one process per GPU: the NCCL worker of the
-    default suite (48-byte and 16-byte records, uneven sizes, all tunings) with the candidate on"""
+@pytest.mark.parametrize("switch", ["MPSORT_FUSED_PACK", "MPSORT_PEER_SPLITTER"])
+def test_candidates_over_nccl_processes(switch):
+    """one process per GPU (mapped peer memory): the NCCL worker of the default suite (48-byte and
+    16-byte records, uneven sizes, all tunings) with the candidate on"""
     sys.path.insert(0, os.path.join(ROOT, "mp-sort_b200"))
     from mpsort import _capi as C
     ngpu = min(C.lib.mpsort_util_device_count(), 8)
     if ngpu < 2:
         pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29519", MPSORT_FUSED_PACK="1")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29519", **{switch: "1"})
     rc = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(ngpu),
                          "--master-addr", "127.0.0.1", "--master-port", "29519",
                          os.path.join(ROOT, "tests", "nccl_worker.py")], env=env, timeout=600,

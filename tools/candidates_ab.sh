@@ -24,8 +24,8 @@ for K in "16 1" "48 2"; do
   MPSORT_MERGE_BUCKET=1 timeout 600 python tools/group_probe.py 8 25 $K 2>&1 | tail -3
 done
 if [ "$N" -gt 1 ]; then
-  echo "== bench.py --gpus $N: default | MPSORT_MERGE_BUCKET=1"
-  bash tools/exchange_modes.sh $N "MPSORT_MERGE_BUCKET=0" "MPSORT_MERGE_BUCKET=1"
+  echo "== bench.py --gpus $N: default | bucket merge | peer splitter kernel | both"
+  bash tools/exchange_modes.sh $N "MPSORT_MERGE_BUCKET=0" "MPSORT_MERGE_BUCKET=1" "MPSORT_PEER_SPLITTER=1" "MPSORT_PEER_SPLITTER=1 MPSORT_MERGE_BUCKET=1"
   echo "== bench.py --gpus $N --workload mostly_sorted16: default | MPSORT_HYBRID_DEPTH5=1"
   for cfg in "MPSORT_X=0" "MPSORT_HYBRID_DEPTH5=1"; do
     echo "-- $cfg"
