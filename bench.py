@@ -301,10 +301,17 @@ def main():
         else:
             # the box refused to pin 2 x n*E bytes: pageable numpy arrays (slower copies, same call)
             lib.mpsort_util_host_free_pinned(hin_p)
-            hin = np.empty(n, dtype=dt)
-            hout = np.empty(n, dtype=dt)
-            hin_p, hout_p = hin.ctypes.data, hout.ctypes.data
+            try:
+                hin = np.empty(n, dtype=dt)
+                hout = np.empty(n, dtype=dt)
+                hin_p, hout_p = hin.ctypes.data, hout.ctypes.data
+            except MemoryError:
+                hin = hout = None
         pinned = min(comm.allgather(pinned_here))
+        have_host = min(comm.allgather(hin is not None))
+    if not args.no_e2e and not have_host:
+        e2e = {"value": None, "unit": "records/s", "error": "no host memory for 2 x %d bytes per rank" % (n * E)}
+    elif not args.no_e2e:
         lib.mpsort_util_memcpy(dev, hin_p, din, n * E)
         mpsort.sort(hin, "key", out=hout, comm=comm)                    # warm-up
         comm.barrier()
