@@ -1,0 +1,63 @@
+"""bench.py's output contract, checked without a GPU: the GPU arm runs against a stand-in library
+(tests/support/fake_bench.py) so that every key the driver reads is present and well-formed; the
+reference arm runs for real on a tiny sample."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+import mpsort_oracle as O
+from conftest import ROOT
+
+BASE_KEYS = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "cpu_baseline"]
+
+
+def run(args):
+    rc = subprocess.run([sys.executable] + args, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert rc.returncode == 0, rc.stderr.decode()[-2000:]
+    lines = [l for l in rc.stdout.decode().splitlines() if l.startswith("{")]
+    assert len(lines) == 1, "exactly one JSON line"
+    return json.loads(lines[0])
+
+
+@pytest.mark.parametrize("extra", [[], ["--pinfail"]])
+def test_gpu_arm_line_has_every_contract_key(extra):
+    d = run([os.path.join(ROOT, "tests", "support", "fake_bench.py")] + extra)
+    for k in BASE_KEYS + ["clocks", "roofline"]:
+        assert k in d, k
+    assert d["metric"] == "sorted records/s" and d["unit"] == "records/s" and d["higher_is_better"] is True
+    assert d["scaling"] == "weak" and d["vs_baseline"] is None and d["dtype"] == "u64" and d["data"] == "synthetic"
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["gpu_launches"] > 0
+    assert "workload" in d["config"] and "model" not in d["config"]
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in d["e2e"], k
+    assert d["e2e"]["h2d_bytes_per_step"] == d["config"]["records_per_gpu"] * d["config"]["elsize"]
+    assert ("pageable" if extra else "pinned") in d["e2e"]["api"]
+    r = d["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in r, k
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    for k in ("sm_mhz", "sm_max_mhz", "reasons"):
+        assert k in d["clocks"], k
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
+def test_reference_arm_line():
+    d = run([os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-records", "32768"])
+    for k in BASE_KEYS:
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "sorted records/s" and d["unit"] == "records/s"
+    assert d["e2e"] == {"value": d["value"], "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    c = d["cpu_baseline"]
+    assert c["kind"] == "reference" and c["cores"] >= 1 and c["value"] == d["value"] and "sample" in c
+    assert d["config"]["workload"].startswith("uniform16: 2^28")
+
+
+def test_reference_arm_on_other_ranks_is_silent():
+    env = dict(os.environ, RANK="3", WORLD_SIZE="8")
+    rc = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "8"], env=env,
+                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+    assert rc.returncode == 0 and rc.stdout.strip() == b""
