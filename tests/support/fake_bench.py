@@ -6,6 +6,12 @@ import sys, types, ctypes, json, io, contextlib
 sys.argv = ["bench.py", "--log2n", "10", "--steps", "2", "--warmup", "1", "--no-cpu-baseline"] + sys.argv[1:]
 PIN_FAIL = "--pinfail" in sys.argv
 if PIN_FAIL: sys.argv.remove("--pinfail")
+SIZE = 1
+if "--size" in sys.argv:
+    i = sys.argv.index("--size"); SIZE = int(sys.argv[i + 1]); del sys.argv[i:i + 2]
+    sys.argv += ["--gpus", str(SIZE)]
+    import os as _os
+    _os.environ["WORLD_SIZE"] = str(SIZE); _os.environ["RANK"] = "0"
 keep = []
 class Lib:
     def __getattr__(self, name):
@@ -33,10 +39,10 @@ capi.last_run = lambda: [("FirstSort", 0.010), ("Exchange", 0.005)]
 capi.last_stats = lambda h, s: {"first_sort_passes": 4, "second_sort_passes": 0, "record_mode": 1, "second_sort_merge_tiles": 10, "bytes_sent_remote": 1000, "p2p_exchange": 1, "exchange_phases": 2}
 mp = types.ModuleType("mpsort")
 class Comm:
-    rank, size, device, handle = 0, 1, 0, 1
+    rank, size, device, handle = 0, SIZE, 0, 1
     @classmethod
     def from_env(cls): return cls()
-    def allgather(self, x): return [x]
+    def allgather(self, x): return [x] * SIZE
     def barrier(self): pass
     def destroy(self): pass
 mp.Comm = Comm

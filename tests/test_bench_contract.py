@@ -61,3 +61,14 @@ def test_reference_arm_on_other_ranks_is_silent():
     rc = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "8"], env=env,
                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
     assert rc.returncode == 0 and rc.stdout.strip() == b""
+
+
+def test_gpu_arm_line_at_eight_ranks():
+    """rank 0 of 8 (the other ranks' answers are copies of its own): whole-job value and e2e byte counts"""
+    d = run([os.path.join(ROOT, "tests", "support", "fake_bench.py"), "--size", "8"])
+    assert d["n_gpus"] == 8 and d["cpu_baseline"] is None
+    per_gpu = d["config"]["records_per_gpu"]
+    assert abs(d["value"] - 8 * per_gpu / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 8 * per_gpu * d["config"]["elsize"]
+    assert "NVLink" in d["config"]["transport"] and d["config"]["baseline_config"].startswith("configs[2]")
+    assert d["exchange"]["gb_per_s_per_gpu"] > 0
