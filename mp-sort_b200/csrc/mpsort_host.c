@@ -14,8 +14,9 @@
  *                                     + select kernel per level, no host round trip
  *   LayDistr    :450-456              one host allgather of local CLT/CLE rows
  *   LaySolve    :460-464, :663-727    mpsort_solve_layout() on every rank
- *   Exchange    :571-592              payload gather (pack) + grouped send/recv
- *   SecondSort  radix_sort :597       local_sort() of the received runs + gather
+ *   Exchange    :571-592              payload gather (pack, index mode) + DMA peer copies
+ *                                     in two parts (or grouped send/recv)
+ *   SecondSort  radix_sort :597       stable p-way merge of the received runs (or re-sort)
  */
 #include <stdarg.h>
 #include <string.h>
@@ -773,14 +774,11 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
     const int level0 = mpsort_key_range(p, nw, nmemb, kmin, kmax, Pmin, Pmax, prefix0);
     timer_mark(c, "PmaxPmin");
 
-    /* ---- optional pipelining (MPSORT_EXCHANGE_PHASES=Q): every rank's output is cut into
-     * Q consecutive parts ("virtual ranks", pv = p*Q destinations). The exchange then runs
+    /* ---- pipelining (MPSORT_EXCHANGE_PHASES=Q): every rank's output is cut into Q
+     * consecutive parts ("virtual ranks", pv = p*Q destinations). The exchange then runs
      * part by part and the merge of part q overlaps the transfer of part q+1 on a second
-     * stream. The result is the same global stable sort: only more cut points. Off by
-     * default: on B200 the merge kernels starve the concurrent NCCL/peer-store kernels of
-     * SMs and HBM bandwidth, so the overlapped total is no shorter than the sum
-     * (profiles/r01_pipelined_exchange.log). Q is decided from global facts so that every
-     * rank takes the same branch. */
+     * stream. The result is the same global stable sort: only more cut points. Q is
+     * decided from global facts so that every rank takes the same branch. */
     int Q = 1;
     {
         /* default: two parts when the slices move by DMA (the merge of part 0 then overlaps the
