@@ -1,0 +1,106 @@
+"""Host orchestration of libmpsort-b200.so WITHOUT a GPU: mpsort_host.c / mpsort_comm.c /
+mpsort_layout.c / mpsort_util.c, compiled unchanged, run against tests/native/mock_device.c
+(kernel ABI, CUDA runtime and NCCL restated as plain loops / no-ops). What passes here is the
+C host logic -- phases, splitter targets, layout over virtual ranks, exchange parts, gather
+path, callback entry points, arena bookkeeping, the Cython binding -- NOT the kernels: those
+are checked by the same test files on the B200 (`-m gpu`) through the real library.
+
+The GPU test files are re-run in a subprocess with MPSORT_LIB pointing at the mock build, so
+every host-side path the GPU suite drives is driven here too, and a host bug shows up on the
+CPU box instead of at the end of a round."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "tests", "support"))
+import hostmock  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def mock_env():
+    so = hostmock.build()
+    env = dict(os.environ, MPSORT_LIB=so)
+    for k in list(env):
+        if k.startswith("MPSORT_") and k != "MPSORT_LIB":
+            del env[k]
+    return env
+
+
+def run_py(env, code_or_args, timeout=900, **extra):
+    args = [sys.executable] + (code_or_args if isinstance(code_or_args, list) else ["-c", code_or_args])
+    return subprocess.run(args, cwd=ROOT, env=dict(env, **extra), timeout=timeout, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+
+
+def test_mock_provides_every_symbol_the_host_code_uses(mock_env):
+    """linked with -z defs: a new CUDA / NCCL / kernel-ABI call in the host files fails the build here"""
+    assert os.path.exists(mock_env["MPSORT_LIB"])
+
+
+# the two full-size property tests take minutes as CPU loops; their host flow is the same as the 2^22 cases below
+BIG = ["tests/test_gpu_parity.py::test_full_size_config_b_by_properties",
+       "tests/test_gpu_parity.py::test_large_particles48_and_mostly_sorted_by_properties"]
+
+
+def test_gpu_suite_host_flow_on_the_mock(mock_env):
+    """tests/test_python_api.py (the reference's own test file re-hosted), test_gpu_parity.py and
+    test_zz_callback_api.py, `-m gpu`, against the mock build"""
+    args = ["-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "tests/test_python_api.py",
+            "tests/test_gpu_parity.py", "tests/test_zz_callback_api.py"]
+    for b in BIG:
+        args += ["--deselect", b]
+    rc = run_py(mock_env, args, timeout=1500)
+    out = rc.stdout.decode()
+    assert rc.returncode == 0, out[-4000:]
+    m = re.search(r"(\d+) passed", out)
+    assert m and int(m.group(1)) >= 150 and "failed" not in out, out[-2000:]
+
+
+def _candidates():
+    import test_zz_candidates as T
+    return T
+
+
+@pytest.mark.parametrize("extra", [{}, {"MPSORT_EXCHANGE_PHASES": "2"}, {"MPSORT_EXCHANGE_PHASES": "3", "MPSORT_PACK_PIPELINE": "1"},
+                                   {"MPSORT_NO_MERGE": "1"}, {"MPSORT_NO_REC16": "1", "MPSORT_NO_REBASE": "1"},
+                                   {"MPSORT_NO_HYBRID": "1", "MPSORT_NO_HIST4": "1"}],
+                         ids=lambda e: "+".join(sorted(e)) or "default")
+def test_switches_leave_the_result_bit_exact(mock_env, extra):
+    """2-8 rank threads, 16/24/48-byte records, the three key kinds, uneven sizes: the oracle's bytes
+    whatever host-side switch is set"""
+    code = _candidates().WORKER % {"root": ROOT}
+    if "MPSORT_NO_MERGE" in extra:      # the second sort is then a radix re-sort: no merge tiles to count
+        code = code.replace('all(s["second_sort_merge_tiles"] > 0 for s in stats)', 'all(s["second_sort_passes"] > 0 for s in stats)')
+        assert "second_sort_passes" in code
+    rc = run_py(mock_env, code, **extra)
+    assert rc.returncode == 0 and b"CANDIDATE OK" in rc.stdout, rc.stdout.decode()[-4000:]
+
+
+@pytest.mark.parametrize("E,kind,extra", [(16, 0, {}), (48, 2, {}), (48, 2, {"MPSORT_PACK_PIPELINE": "1"}),
+                                          (24, 3, {"MPSORT_PACK_PIPELINE": "1", "MPSORT_EXCHANGE_PHASES": "4"})])
+def test_exchange_in_parts_at_2_22_records_per_rank(mock_env, E, kind, extra):
+    """4 rank threads x 2^22 records (the smallest size at which the exchange is cut into parts): order, tie order,
+    checksum of checksums, and that the parts were really taken; with and without the pipelined pack"""
+    code = _candidates().WORKER_PROPS % {"root": ROOT, "E": E, "kind": kind, "log2n": 22, "passes": 0}
+    if extra.get("MPSORT_EXCHANGE_PHASES", "2") != "2":
+        code = code.replace('x[5]["exchange_phases"] == 2', 'x[5]["exchange_phases"] == %s' % extra["MPSORT_EXCHANGE_PHASES"])
+    rc = run_py(mock_env, code, **dict({"MPSORT_EXCHANGE_PHASES": "2"}, **extra))
+    assert rc.returncode == 0 and b"CANDIDATE OK" in rc.stdout, rc.stdout.decode()[-4000:]
+
+
+def test_bench_gpu_arm_runs_end_to_end_on_the_mock(mock_env):
+    """bench.py itself (not a stand-in for it): device-resident leg, e2e leg through mpsort.sort, verification,
+    roofline bookkeeping, one JSON line. Numbers are meaningless here; the control flow is what is checked."""
+    rc = subprocess.run([sys.executable, "bench.py", "--log2n", "16", "--steps", "2", "--warmup", "1", "--no-cpu-baseline"],
+                        cwd=ROOT, env=mock_env, timeout=600, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert rc.returncode == 0, rc.stderr.decode()[-3000:]
+    lines = [l for l in rc.stdout.decode().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["value"] > 0 and d["e2e"]["value"] > 0 and d["gpu_launches"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == (1 << 16) * 16 and d["roofline"]["bound"] == "hbm"
