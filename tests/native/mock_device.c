@@ -9,8 +9,9 @@
  * What is mocked: (1) the CUDA runtime calls the host code makes -- "device memory" is malloc,
  * every stream operation runs synchronously, events carry host wall time; (2) the kernel ABI of
  * mpsort_kernels.h -- each entry point is restated as a plain loop with the SAME contract
- * (what it reads, what it writes, stability), not the same algorithm; (3) NCCL -- absent: only
- * the in-process transport (rank threads) works here.
+ * (what it reads, what it writes, stability), not the same algorithm; (3) NCCL and CUDA IPC --
+ * between the rank THREADS of one process, every collective blocking (so both the in-process
+ * transport and the NCCL transport with its mapped peer buffers run here).
  *
  * What this can NOT show: anything about the real kernels, stream ordering, races, peer memory,
  * NCCL. It is never built by the product Makefile, never shipped, and the product library has no
@@ -22,6 +23,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 
 #include <cuda_runtime_api.h>
 #include <nccl.h>
@@ -101,31 +103,254 @@ const char * cudaGetErrorString(cudaError_t e) { (void) e; return "mock device e
 cudaError_t cudaDeviceSetLimit(enum cudaLimit l, size_t v) { (void) l; (void) v; return cudaSuccess; }
 cudaError_t cudaDeviceCanAccessPeer(int * can, int a, int b) { (void) a; (void) b; *can = 1; return cudaSuccess; }
 cudaError_t cudaDeviceEnablePeerAccess(int d, unsigned f) { (void) d; (void) f; return cudaSuccess; }
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t * h, void * p) { (void) h; (void) p; return cudaErrorNotSupported; }
-cudaError_t cudaIpcOpenMemHandle(void ** p, cudaIpcMemHandle_t h, unsigned f) { (void) p; (void) h; (void) f; return cudaErrorNotSupported; }
+/* CUDA IPC between the rank THREADS of this process (the real runtime refuses to open a handle in the
+ * process that made it; here a handle is the base address of the allocation, as the real one stands for
+ * the whole allocation). MOCK_NO_IPC=1: not supported, which sends the host code to its NCCL fallback. */
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t * h, void * p)
+{
+    int i;
+    char * base = NULL;
+    if (getenv("MOCK_NO_IPC")) return cudaErrorNotSupported;
+    pthread_mutex_lock(&g_lock);
+    for (i = 0; i < MAXALLOC; i++)
+        if (g_alloc[i].p && (char *) p >= g_alloc[i].p && (char *) p < g_alloc[i].p + g_alloc[i].n) { base = g_alloc[i].p; break; }
+    pthread_mutex_unlock(&g_lock);
+    if (!base) return cudaErrorInvalidValue;
+    memset(h, 0, sizeof(*h));
+    memcpy(h, &base, sizeof(base));
+    return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void ** p, cudaIpcMemHandle_t h, unsigned f)
+{
+    (void) f;
+    if (getenv("MOCK_NO_IPC")) return cudaErrorNotSupported;
+    memcpy(p, &h, sizeof(*p));
+    return *p ? cudaSuccess : cudaErrorInvalidValue;
+}
 cudaError_t cudaIpcCloseMemHandle(void * p) { (void) p; return cudaSuccess; }
 cudaError_t cudaMemGetInfo(size_t * fr, size_t * tot) { *fr = (size_t) 1 << 34; *tot = (size_t) 1 << 35; return cudaSuccess; }
 
 /* ------------------------------------------------------------------------- */
-/* NCCL: absent                                                               */
+/* NCCL among the THREADS of this process (real NCCL allows several ranks per process too):
+ * every call blocks until all ranks of the communicator have made it -- collectives in a
+ * different order on different ranks, which would corrupt or hang a real run, hang here and
+ * the test's timeout reports it. Grouped calls (broadcast, send, recv) are collected per
+ * thread and run at ncclGroupEnd pair by pair (a rank with nothing to post is not waited for):
+ * all sends are published, then the receives copy, then the sender waits until its buffers
+ * have been read.                                                                          */
 
-ncclResult_t ncclGetUniqueId(ncclUniqueId * id) { (void) id; return ncclInternalError; }
-ncclResult_t ncclCommInitRank(ncclComm_t * c, int n, ncclUniqueId id, int r) { (void) c; (void) n; (void) id; (void) r; return ncclInternalError; }
-ncclResult_t ncclCommDestroy(ncclComm_t c) { (void) c; return ncclSuccess; }
+#define MOCK_MAXRANKS 64
+#define MOCK_MAXOPS   256
+struct mock_op { int kind; const void * send; void * recv; size_t bytes; int peer; };   /* kind: 0 send, 1 recv, 2 bcast (peer = root) */
+#define MOCK_FIFO 8
+struct mock_fifo { unsigned long head, tail; struct { const void * ptr; size_t bytes; } msg[MOCK_FIFO]; };
+struct mock_group {
+    int used, size, joined, refs;
+    char id[32];
+    pthread_barrier_t bar;
+    const void * slot[MOCK_MAXRANKS];
+    void * rslot[MOCK_MAXRANKS];
+    struct mock_fifo * fifo;            /* [from][to][channel]: 0 send/recv, 1 broadcast */
+    pthread_mutex_t mlock;
+    pthread_cond_t mcond;
+};
+struct ncclComm { struct mock_group * g; int rank; };
+static struct mock_group g_groups[32];
+static int g_uid_seq;
+static __thread int t_group_depth;
+static __thread int t_nops;
+static __thread struct mock_op t_ops[MOCK_MAXOPS];
+static __thread struct ncclComm * t_group_comm;
+
+static size_t nccl_size(ncclDataType_t t)
+{
+    switch (t) {
+    case ncclInt8: case ncclUint8: return 1;
+    case ncclInt32: case ncclUint32: case ncclFloat32: return 4;
+    case ncclInt64: case ncclUint64: case ncclFloat64: return 8;
+    default: return 0;
+    }
+}
+
+ncclResult_t ncclGetUniqueId(ncclUniqueId * id)
+{
+    memset(id, 0, sizeof(*id));
+    pthread_mutex_lock(&g_lock);
+    snprintf(id->internal, 32, "mock-nccl-%d-%d", (int) getpid(), ++g_uid_seq);
+    pthread_mutex_unlock(&g_lock);
+    return ncclSuccess;
+}
+
+ncclResult_t ncclCommInitRank(ncclComm_t * c, int n, ncclUniqueId id, int r)
+{
+    int i;
+    struct mock_group * g = NULL;
+    if (n < 1 || n > MOCK_MAXRANKS || r < 0 || r >= n || id.internal[0] == 0) return ncclInvalidArgument;
+    pthread_mutex_lock(&g_lock);
+    for (i = 0; i < 32; i++) if (g_groups[i].used && memcmp(g_groups[i].id, id.internal, 32) == 0) { g = &g_groups[i]; break; }
+    if (!g) {
+        for (i = 0; i < 32; i++) if (!g_groups[i].used) { g = &g_groups[i]; break; }
+        if (!g) { pthread_mutex_unlock(&g_lock); return ncclInternalError; }
+        memset(g, 0, sizeof(*g));
+        g->used = 1; g->size = n;
+        memcpy(g->id, id.internal, 32);
+        pthread_barrier_init(&g->bar, NULL, (unsigned) n);
+        pthread_mutex_init(&g->mlock, NULL);
+        pthread_cond_init(&g->mcond, NULL);
+        g->fifo = (struct mock_fifo *) calloc((size_t) n * n * 2, sizeof(struct mock_fifo));
+    }
+    if (g->size != n) { pthread_mutex_unlock(&g_lock); return ncclInvalidArgument; }
+    g->joined++; g->refs++;
+    pthread_mutex_unlock(&g_lock);
+    *c = (struct ncclComm *) malloc(sizeof(struct ncclComm));
+    (*c)->g = g; (*c)->rank = r;
+    pthread_barrier_wait(&g->bar);      /* like the real call: returns when every rank has joined */
+    return ncclSuccess;
+}
+
+ncclResult_t ncclCommDestroy(ncclComm_t c)
+{
+    int last;
+    if (!c) return ncclSuccess;
+    pthread_mutex_lock(&g_lock);
+    last = (--c->g->refs == 0);
+    if (last) { pthread_barrier_destroy(&c->g->bar); free(c->g->fifo); c->g->used = 0; }
+    pthread_mutex_unlock(&g_lock);
+    free(c);
+    return ncclSuccess;
+}
 ncclResult_t ncclCommAbort(ncclComm_t c) { (void) c; return ncclSuccess; }
-const char * ncclGetErrorString(ncclResult_t r) { (void) r; return "no NCCL in the mock"; }
-ncclResult_t ncclGroupStart(void) { return ncclInternalError; }
-ncclResult_t ncclGroupEnd(void) { return ncclInternalError; }
+const char * ncclGetErrorString(ncclResult_t r) { (void) r; return "mock NCCL error"; }
+
 ncclResult_t ncclAllReduce(const void * s, void * r, size_t n, ncclDataType_t t, ncclRedOp_t o, ncclComm_t c, cudaStream_t st)
-{ (void) s; (void) r; (void) n; (void) t; (void) o; (void) c; (void) st; return ncclInternalError; }
+{
+    struct mock_group * g = c->g;
+    const size_t w = nccl_size(t);
+    size_t i;
+    int k;
+    (void) st;
+    if (o != ncclSum || (w != 4 && w != 8) || t_group_depth) return ncclInvalidUsage;
+    g->slot[c->rank] = s;
+    pthread_barrier_wait(&g->bar);
+    void * tmp = malloc(n * w + 1);
+    for (i = 0; i < n; i++) {
+        uint64_t acc = 0;
+        for (k = 0; k < g->size; k++)
+            acc += (w == 8) ? ((const uint64_t *) g->slot[k])[i] : (uint64_t) ((const uint32_t *) g->slot[k])[i];
+        if (w == 8) ((uint64_t *) tmp)[i] = acc; else ((uint32_t *) tmp)[i] = (uint32_t) acc;
+    }
+    pthread_barrier_wait(&g->bar);      /* everyone has read every input: in-place results may land */
+    memcpy(r, tmp, n * w);
+    free(tmp);
+    return ncclSuccess;
+}
+
 ncclResult_t ncclAllGather(const void * s, void * r, size_t n, ncclDataType_t t, ncclComm_t c, cudaStream_t st)
-{ (void) s; (void) r; (void) n; (void) t; (void) c; (void) st; return ncclInternalError; }
+{
+    struct mock_group * g = c->g;
+    const size_t bytes = n * nccl_size(t);
+    int k;
+    (void) st;
+    if (t_group_depth) return ncclInvalidUsage;
+    g->slot[c->rank] = s;
+    pthread_barrier_wait(&g->bar);
+    /* in place (s == r + rank * bytes) is allowed: a peer's piece lives where I never write */
+    for (k = 0; k < g->size; k++)
+        if ((const char *) g->slot[k] != (char *) r + (size_t) k * bytes) memmove((char *) r + (size_t) k * bytes, g->slot[k], bytes);
+    pthread_barrier_wait(&g->bar);
+    return ncclSuccess;
+}
+
+ncclResult_t ncclGroupStart(void) { if (t_group_depth++ == 0) { t_nops = 0; t_group_comm = NULL; } return ncclSuccess; }
+
+static ncclResult_t group_add(int kind, const void * s, void * r, size_t bytes, int peer, ncclComm_t c)
+{
+    if (!t_group_depth) return ncclInvalidUsage;        /* the host code only uses these inside a group */
+    if (t_group_comm && t_group_comm != c) return ncclInvalidUsage;
+    if (t_nops == MOCK_MAXOPS || peer < 0 || peer >= c->g->size) return ncclInvalidArgument;
+    t_group_comm = c;
+    t_ops[t_nops].kind = kind; t_ops[t_nops].send = s; t_ops[t_nops].recv = r; t_ops[t_nops].bytes = bytes; t_ops[t_nops].peer = peer;
+    t_nops++;
+    return ncclSuccess;
+}
+
 ncclResult_t ncclBroadcast(const void * s, void * r, size_t n, ncclDataType_t t, int root, ncclComm_t c, cudaStream_t st)
-{ (void) s; (void) r; (void) n; (void) t; (void) root; (void) c; (void) st; return ncclInternalError; }
+{ (void) st; return group_add(2, s, r, n * nccl_size(t), root, c); }
 ncclResult_t ncclSend(const void * s, size_t n, ncclDataType_t t, int peer, ncclComm_t c, cudaStream_t st)
-{ (void) s; (void) n; (void) t; (void) peer; (void) c; (void) st; return ncclInternalError; }
+{ (void) st; if (peer == c->rank) return ncclInvalidArgument; return group_add(0, s, NULL, n * nccl_size(t), peer, c); }
 ncclResult_t ncclRecv(void * r, size_t n, ncclDataType_t t, int peer, ncclComm_t c, cudaStream_t st)
-{ (void) r; (void) n; (void) t; (void) peer; (void) c; (void) st; return ncclInternalError; }
+{ (void) st; if (peer == c->rank) return ncclInvalidArgument; return group_add(1, NULL, r, n * nccl_size(t), peer, c); }
+
+#define FIFO(g, from, to, ch) (&(g)->fifo[(((size_t) (from) * (g)->size + (to)) * 2) + (ch)])
+
+static void fifo_post(struct mock_group * g, int from, int to, int ch, const void * ptr, size_t bytes)
+{
+    struct mock_fifo * f = FIFO(g, from, to, ch);
+    pthread_mutex_lock(&g->mlock);
+    while (f->tail - f->head == MOCK_FIFO) pthread_cond_wait(&g->mcond, &g->mlock);
+    const unsigned long seq = f->tail++;
+    f->msg[seq % MOCK_FIFO].ptr = ptr;
+    f->msg[seq % MOCK_FIFO].bytes = bytes;
+    pthread_cond_broadcast(&g->mcond);
+    pthread_mutex_unlock(&g->mlock);
+}
+
+static int fifo_take(struct mock_group * g, int from, int to, int ch, void * dst, size_t bytes)
+{
+    struct mock_fifo * f = FIFO(g, from, to, ch);
+    pthread_mutex_lock(&g->mlock);
+    while (f->tail == f->head) pthread_cond_wait(&g->mcond, &g->mlock);
+    const void * src = f->msg[f->head % MOCK_FIFO].ptr;
+    const size_t have = f->msg[f->head % MOCK_FIFO].bytes;
+    pthread_mutex_unlock(&g->mlock);
+    const int ok = (have == bytes);
+    if (ok && bytes) memcpy(dst, src, bytes);           /* the sender keeps its buffer until head moves */
+    else if (!ok) fprintf(stderr, "mock NCCL: rank %d expects %zu bytes from rank %d, which sends %zu\n", to, bytes, from, have);
+    pthread_mutex_lock(&g->mlock);
+    f->head++;
+    pthread_cond_broadcast(&g->mcond);
+    pthread_mutex_unlock(&g->mlock);
+    return ok;
+}
+
+/* only `from` posts to this queue: once it has stopped posting, head == tail means all was read */
+static void fifo_wait_drained(struct mock_group * g, int from, int to, int ch)
+{
+    struct mock_fifo * f = FIFO(g, from, to, ch);
+    pthread_mutex_lock(&g->mlock);
+    while (f->head != f->tail) pthread_cond_wait(&g->mcond, &g->mlock);
+    pthread_mutex_unlock(&g->mlock);
+}
+
+ncclResult_t ncclGroupEnd(void)
+{
+    int i, k, bad = 0;
+    if (t_group_depth <= 0) return ncclInvalidUsage;
+    if (--t_group_depth > 0) return ncclSuccess;
+    struct ncclComm * c = t_group_comm;
+    if (!c) return ncclSuccess;                          /* nothing posted */
+    struct mock_group * g = c->g;
+    const int me = c->rank;
+    for (i = 0; i < t_nops; i++) {
+        const struct mock_op * o = &t_ops[i];
+        if (o->kind == 0) fifo_post(g, me, o->peer, 0, o->send, o->bytes);
+        else if (o->kind == 2 && o->peer == me)
+            for (k = 0; k < g->size; k++) if (k != me) fifo_post(g, me, k, 1, o->send, o->bytes);
+    }
+    for (i = 0; i < t_nops; i++) {
+        const struct mock_op * o = &t_ops[i];
+        if (o->kind == 1) bad |= !fifo_take(g, o->peer, me, 0, o->recv, o->bytes);
+        else if (o->kind == 2 && o->peer != me) bad |= !fifo_take(g, o->peer, me, 1, o->recv, o->bytes);
+        else if (o->kind == 2 && o->recv != o->send && o->bytes) memmove(o->recv, o->send, o->bytes);
+    }
+    for (i = 0; i < t_nops; i++) {
+        const struct mock_op * o = &t_ops[i];
+        if (o->kind == 0) fifo_wait_drained(g, me, o->peer, 0);
+        else if (o->kind == 2 && o->peer == me)
+            for (k = 0; k < g->size; k++) if (k != me) fifo_wait_drained(g, me, k, 1);
+    }
+    return bad ? ncclInvalidUsage : ncclSuccess;
+}
 
 /* ------------------------------------------------------------------------- */
 /* kernel ABI (mpsort_kernels.h), restated as loops                           */
@@ -540,15 +765,24 @@ int mpsk_merge_runs(const void * recv, void * out, size_t elsize, size_t offset,
 int mpsk_p2p_alltoallv(const void * const * src, void * const * dst, const uint64_t * bytes, const unsigned char * remote,
         int nseg, mpsk_stream_t stream)
 {
-    (void) src; (void) dst; (void) bytes; (void) remote; (void) nseg; (void) stream;
-    return NOT_MOCKED;      /* peer memory: NCCL transport only */
+    int k;
+    (void) remote; (void) stream;
+    LAUNCHED();
+    for (k = 0; k < nseg; k++) if (bytes[k]) memcpy(dst[k], src[k], (size_t) bytes[k]);
+    return 0;
 }
 
 int mpsk_p2p_gather_alltoallv(const void * base, const uint32_t * const * idx, void * const * dst, const uint64_t * nrec,
         size_t elsize, int nseg, mpsk_stream_t stream)
 {
-    (void) base; (void) idx; (void) dst; (void) nrec; (void) elsize; (void) nseg; (void) stream;
-    return NOT_MOCKED;
+    int k;
+    uint64_t i;
+    (void) stream;
+    LAUNCHED();
+    for (k = 0; k < nseg; k++)
+        for (i = 0; i < nrec[k]; i++)
+            memcpy((char *) dst[k] + (size_t) i * elsize, (const char *) base + (size_t) idx[k][i] * elsize, elsize);
+    return 0;
 }
 
 int mpsk_checksum(const void * base, size_t nbytes, uint64_t * sum, mpsk_stream_t stream)

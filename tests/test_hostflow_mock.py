@@ -104,3 +104,33 @@ def test_bench_gpu_arm_runs_end_to_end_on_the_mock(mock_env):
     d = json.loads(lines[0])
     assert d["n_gpus"] == 1 and d["steps"] == 2 and d["value"] > 0 and d["e2e"]["value"] > 0 and d["gpu_launches"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == (1 << 16) * 16 and d["roofline"]["bound"] == "hbm"
+
+
+# ---- the NCCL transport (mpsort_comm_init_rank), one rank per thread of the worker ------------------
+NCCL_WORKER = os.path.join(ROOT, "tests", "support", "nccl_threads_worker.py")
+
+
+@pytest.mark.parametrize("p,extra,p2p", [(4, {}, 1), (2, {}, 1), (7, {"MOCK_NO_IPC": "1"}, 0), (4, {"MPSORT_NO_P2P": "1"}, 0),
+                                         (3, {"MPSORT_P2P_PULL": "1"}, 1), (4, {"MPSORT_P2P_CE": "0"}, 1), (5, {"MPSORT_P2P_CE": "7"}, 1)],
+                         ids=lambda v: "+".join("%s=%s" % kv for kv in sorted(v.items())) or "default" if isinstance(v, dict) else str(v))
+def test_nccl_transport_small_cases(mock_env, p, extra, p2p):
+    """the cases of tests/nccl_worker.py (which needs >= 2 GPUs) over every exchange transport of mpsort_comm.c:
+    DMA copies into mapped peer buffers (default), peer stores from the copy kernel, pull, grouped ncclSend/ncclRecv
+    by choice and as the fallback when the buffers cannot be mapped; sparse and dense; the gather path; empty input"""
+    rc = run_py(mock_env, [NCCL_WORKER, str(p)], EXPECT_P2P=str(p2p), **extra)
+    assert rc.returncode == 0 and b"NCCL THREADS OK" in rc.stdout, rc.stdout.decode()[-4000:]
+
+
+@pytest.mark.parametrize("extra,phases", [({}, 2), ({"MPSORT_PACK_PIPELINE": "1", "MPSORT_EXCHANGE_PHASES": "3"}, 3),
+                                          ({"MPSORT_FUSED_PACK": "1"}, 2), ({"MOCK_NO_IPC": "1"}, None)],
+                         ids=lambda v: "+".join("%s=%s" % kv for kv in sorted(v.items())) or "default" if isinstance(v, dict) else str(v))
+def test_nccl_transport_exchange_in_parts(mock_env, extra, phases):
+    """3 ranks x 2^22 records (16-byte uniform keys, 48-byte records with duplicates): the default of one process per
+    GPU -- two exchange parts over mapped peer buffers with the merge of part 0 beside the transfer of part 1 --
+    and the candidates that change the host flow of that path"""
+    # (buffers that cannot be mapped are only found out during the first sort of a communicator, after the number of
+    # parts has been chosen: that one sort moves its two parts with ncclSend/ncclRecv, later ones take one part)
+    if phases is not None:
+        extra = dict(extra, EXPECT_PHASES=str(phases))
+    rc = run_py(mock_env, [NCCL_WORKER, "3", "big"], **extra)
+    assert rc.returncode == 0 and b"NCCL THREADS OK" in rc.stdout, rc.stdout.decode()[-4000:]
