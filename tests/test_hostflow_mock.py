@@ -134,3 +134,23 @@ def test_nccl_transport_exchange_in_parts(mock_env, extra, phases):
         extra = dict(extra, EXPECT_PHASES=str(phases))
     rc = run_py(mock_env, [NCCL_WORKER, "3", "big"], **extra)
     assert rc.returncode == 0 and b"NCCL THREADS OK" in rc.stdout, rc.stdout.decode()[-4000:]
+
+
+# ---- rank threads under ThreadSanitizer ------------------------------------------------------------
+def test_rank_threads_have_no_data_races(tmp_path):
+    """tests/native/hostflow_threads.c + the host files + the mock, all built with -fsanitize=thread: rank threads
+    of an in-process group and NCCL ranks as threads, two sorts each, 16- and 48-byte records with cross-rank ties"""
+    exe = str(tmp_path / "hostflow_tsan")
+    srcs = [os.path.join(ROOT, "tests", "native", "hostflow_threads.c"), os.path.join(ROOT, "tests", "native", "mock_device.c")] \
+        + [os.path.join(hostmock.CSRC, f) for f in hostmock.HOST_FILES]
+    cc = subprocess.run(["gcc", "-O1", "-g", "-fsanitize=thread", "-std=gnu11", "-I" + os.path.join(ROOT, "include"), "-I" + hostmock.CSRC,
+                         "-I" + os.path.join(ROOT, "oracle"), "-I" + hostmock.CUDA_INC, "-o", exe] + srcs + ["-lpthread", "-lm"],
+                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    if cc.returncode != 0 and b"tsan" in cc.stdout.lower():
+        pytest.skip("no ThreadSanitizer runtime on this box")
+    assert cc.returncode == 0, cc.stdout.decode()[-3000:]
+    env = {k: v for k, v in os.environ.items() if not k.startswith("MPSORT_")}
+    for args in (["4", "30000", "16"], ["3", "20000", "48"], ["7", "5000", "24"]):
+        rc = subprocess.run([exe] + args, env=env, timeout=600, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+        out = rc.stdout.decode()
+        assert rc.returncode == 0 and "THREADS OK" in out and "ThreadSanitizer" not in out, out[-4000:]
