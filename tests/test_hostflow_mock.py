@@ -154,3 +154,27 @@ def test_rank_threads_have_no_data_races(tmp_path):
         rc = subprocess.run([exe] + args, env=env, timeout=600, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
         out = rc.stdout.decode()
         assert rc.returncode == 0 and "THREADS OK" in out and "ThreadSanitizer" not in out, out[-4000:]
+
+
+# ---- the host files under AddressSanitizer + UBSan ---------------------------------------------------
+def test_host_code_under_address_and_ub_sanitizers(tmp_path, mock_env):
+    """the mock build again with -fsanitize=address,undefined ("device memory" is malloc here, so an arena slot that is
+    too small for what a kernel's contract writes is a heap overflow): NCCL-transport cases and the callback entry
+    points, sanitizer runtimes preloaded into the python worker"""
+    so = str(tmp_path / "libmpsort-hostmock-asan.so")
+    srcs = [os.path.join(ROOT, "tests", "native", "mock_device.c")] + [os.path.join(hostmock.CSRC, f) for f in hostmock.HOST_FILES]
+    cc = subprocess.run(["gcc", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-fPIC", "-shared", "-std=gnu11",
+                         "-I" + os.path.join(ROOT, "include"), "-I" + hostmock.CSRC, "-I" + os.path.join(ROOT, "oracle"),
+                         "-I" + hostmock.CUDA_INC, "-o", so] + srcs + ["-lpthread"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert cc.returncode == 0, cc.stdout.decode()[-3000:]
+    pre = [subprocess.run(["gcc", "-print-file-name=" + n], stdout=subprocess.PIPE).stdout.decode().strip() for n in ("libasan.so", "libubsan.so")]
+    if not all(os.path.isabs(x) and os.path.exists(x) for x in pre):
+        pytest.skip("sanitizer runtimes not found")
+    env = dict(mock_env, MPSORT_LIB=so, LD_PRELOAD=" ".join(pre), ASAN_OPTIONS="detect_leaks=0", UBSAN_OPTIONS="print_stacktrace=1")
+    rc = run_py(env, [NCCL_WORKER, "5"])
+    out = rc.stdout.decode()
+    assert rc.returncode == 0 and "NCCL THREADS OK" in out and "AddressSanitizer" not in out and "runtime error" not in out, out[-4000:]
+    rc = run_py(env, ["-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "-s", "tests/test_zz_callback_api.py",
+                      "tests/test_gpu_parity.py", "-k", "callback or golden or other_key_shapes or radix_sort_desc"])
+    out = rc.stdout.decode()
+    assert rc.returncode == 0 and "AddressSanitizer" not in out and "runtime error" not in out, out[-4000:]
