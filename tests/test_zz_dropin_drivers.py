@@ -7,7 +7,9 @@ Each driver checks itself (checksum, local order, neighbour order) and exits non
 
 CPU part: linked against the mock device build (host flow only, rank threads). GPU part: the binaries that
 build() made from /root/reference while it was there (tests/dropin/_build/, shipped with the snapshot),
-against libmpsort-b200.so: one rank, rank threads on one GPU, and one process per GPU when there are several."""
+against libmpsort-b200.so: one rank, rank threads on one GPU, and one process per GPU when there are several.
+
+Collected last on purpose (file name): written in a GPU-less session, first GPU run is the round-end suite."""
 import os
 import subprocess
 import sys
