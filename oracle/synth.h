@@ -1,6 +1,6 @@
 /*
  * synth.h -- CPU restatement of the synthetic record generator of the device
- * library (mp-sort_b200/csrc/mpsort_kernels.cu: synth_record), so that the
+ * library (mp-sort_b200/csrc/kernels/support.cuh: synth_record), so that the
  * reference and the oracle can be fed byte-identical inputs (TEST INFRASTRUCTURE).
  * Record kinds follow SURVEY.md 8(d):
  *   0 uniform u64 key | 1 mostly sorted (1% perturbed) | 2 skewed signed ids with a
