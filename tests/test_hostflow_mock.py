@@ -122,17 +122,13 @@ def test_nccl_transport_small_cases(mock_env, p, extra, p2p):
 
 
 @pytest.mark.parametrize("extra,phases", [({}, 2), ({"MPSORT_PACK_PIPELINE": "1", "MPSORT_EXCHANGE_PHASES": "3"}, 3),
-                                          ({"MPSORT_FUSED_PACK": "1"}, 2), ({"MOCK_NO_IPC": "1"}, None)],
+                                          ({"MPSORT_FUSED_PACK": "1"}, 2)],
                          ids=lambda v: "+".join("%s=%s" % kv for kv in sorted(v.items())) or "default" if isinstance(v, dict) else str(v))
 def test_nccl_transport_exchange_in_parts(mock_env, extra, phases):
     """3 ranks x 2^22 records (16-byte uniform keys, 48-byte records with duplicates): the default of one process per
     GPU -- two exchange parts over mapped peer buffers with the merge of part 0 beside the transfer of part 1 --
     and the candidates that change the host flow of that path"""
-    # (buffers that cannot be mapped are only found out during the first sort of a communicator, after the number of
-    # parts has been chosen: that one sort moves its two parts with ncclSend/ncclRecv, later ones take one part)
-    if phases is not None:
-        extra = dict(extra, EXPECT_PHASES=str(phases))
-    rc = run_py(mock_env, [NCCL_WORKER, "3", "big"], **extra)
+    rc = run_py(mock_env, [NCCL_WORKER, "3", "big"], EXPECT_PHASES=str(phases), **extra)
     assert rc.returncode == 0 and b"NCCL THREADS OK" in rc.stdout, rc.stdout.decode()[-4000:]
 
 
