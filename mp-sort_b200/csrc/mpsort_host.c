@@ -786,7 +786,11 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
          * (transfer and merge then slow each other down, profiles/r01_pipelined_exchange.log) */
         const char * e = getenv("MPSORT_EXCHANGE_PHASES");
         const int want = e ? atoi(e) : ((c->kind == MPS_T_NCCL && !c->p2p.disabled && c->p2p.copy_engine > 0 && !c->p2p.pull) ? 2 : 1);
-        if (nw == 1 && p <= 32 && want > 1 && total / p >= ((int64_t) 1 << 22)) {
+        /* parts only pay for themselves on large inputs; MPSORT_PHASES_MIN_RECORDS (records per rank,
+         * default 2^22) moves the threshold -- the CPU host-flow tests use it to cut tiny inputs */
+        const char * m = getenv("MPSORT_PHASES_MIN_RECORDS");
+        const int64_t min_per_rank = m ? (int64_t) atoll(m) : ((int64_t) 1 << 22);
+        if (nw == 1 && p <= 32 && want > 1 && total / p >= min_per_rank) {
             Q = want;
             while (Q > 1 && p * Q > MPS_MAX_RANKS) Q--;
         }

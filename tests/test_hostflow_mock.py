@@ -185,3 +185,14 @@ def test_hybrid_depth_decisions(mock_env, extra, passes):
     assert rc.returncode == 0 and ("passes=%d " % passes) in out and "equal=True" in out, out[-2000:]
     if passes != 7:
         assert "hybrid=1 long_runs=1" in out
+
+
+# ---- randomised cases ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed,transport", [(20261017, []), (20261018, ["nccl"])], ids=["in-process", "nccl-threads"])
+def test_randomised_host_flow_cases(mock_env, seed, transport):
+    """tests/support/hostflow_fuzz.py: 250 random cases per transport -- ranks, sizes with zeros, output layouts, record and
+    key shapes, key distributions (duplicates, all equal, sorted, narrow signed range), options, 1-4 exchange parts on tiny
+    inputs (MPSORT_PHASES_MIN_RECORDS=1), host-side switches -- each compared byte for byte with the oracle's contract"""
+    rc = run_py(mock_env, [os.path.join(ROOT, "tests", "support", "hostflow_fuzz.py"), str(seed), "250"] + transport)
+    out = rc.stdout.decode()
+    assert rc.returncode == 0 and "FUZZ OK" in out, out[-3000:]
