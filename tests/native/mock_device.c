@@ -686,14 +686,59 @@ int mpsk_splitter_final(struct mpsk_keyview view, size_t n, uint32_t nw, const u
     return 0;
 }
 
-size_t mpsk_peer_box_bytes(void) { return 4096; }
+/* the one-kernel descent over peer mailboxes (candidate): the PROTOCOL of splitter_descent_peer_kernel restated with
+ * rank threads -- per level, counts into the own mailbox (parity = level & 1), release-store of the per-splitter flag,
+ * acquire-poll of the peers' flags, sum of the peers' counts, digit choice. Layout as in kernels/splitter.cuh:
+ * counts[2][63][256] u64, then 256 flag words. What it cannot show: the GPU memory model, co-residency. */
+#define MOCK_PEER_MAXS 63
+size_t mpsk_peer_box_bytes(void) { return (size_t) 2 * MOCK_PEER_MAXS * 256 * sizeof(uint64_t) + 256 * sizeof(uint32_t); }
 int mpsk_splitter_descent_peer(struct mpsk_keyview view, size_t n, uint32_t nw, uint64_t * prefix, const uint64_t * target,
         int nsplit, int level0, int nlevels, uint32_t me, uint32_t p, void * const * boxes, uint32_t seq, uint32_t * err,
         mpsk_stream_t stream)
 {
-    (void) view; (void) n; (void) nw; (void) prefix; (void) target; (void) nsplit; (void) level0; (void) nlevels;
-    (void) me; (void) p; (void) boxes; (void) seq; (void) err; (void) stream;
-    return NOT_MOCKED;      /* needs concurrently running kernels */
+    int level, b;
+    uint32_t d, w, r;
+    (void) stream;
+    if (nsplit <= 0 || level0 >= nlevels) return 0;
+    if (nw > 16 || nsplit > MOCK_PEER_MAXS || p > 64 || me >= p) return (int) cudaErrorInvalidValue;
+    LAUNCHED();
+    if (getenv("MOCK_TRACE")) fprintf(stderr, "mock: peer descent, rank %u of %u, %d splitters, levels %d..%d, seq %u\n", me, p, nsplit, level0, nlevels - 1, seq);
+    uint64_t * mycounts = (uint64_t *) boxes[me];
+    uint32_t * myflags = (uint32_t *) (mycounts + (size_t) 2 * MOCK_PEER_MAXS * 256);
+    for (level = level0; level < nlevels; level++) {
+        const uint32_t par = (uint32_t) level & 1u, want = seq + (uint32_t) level + 1u;
+        const uint32_t byteidx = 8 * nw - 1 - (uint32_t) level, wi = byteidx >> 3, sh = (byteidx & 7) * 8;
+        for (b = 0; b < nsplit; b++) {
+            for (d = 0; d < 256; d++) {
+                uint64_t cand[16];
+                for (w = 0; w < nw; w++) {
+                    uint64_t x = prefix[(size_t) b * nw + w];
+                    if (w < wi) x = ~0ULL;
+                    else if (w == wi) x |= ((uint64_t) d << sh) | ((sh == 0) ? 0ULL : ((1ULL << sh) - 1ULL));
+                    cand[w] = x;
+                }
+                mycounts[((size_t) par * MOCK_PEER_MAXS + b) * 256 + d] = bound_view(view, n, cand, nw, 1);
+            }
+            __atomic_store_n(&myflags[b], want, __ATOMIC_RELEASE);
+        }
+        for (b = 0; b < nsplit; b++) {
+            uint32_t pick = 255;
+            for (r = 0; r < p; r++) {
+                if (r == me) continue;
+                const uint32_t * pf = (const uint32_t *) ((const uint64_t *) boxes[r] + (size_t) 2 * MOCK_PEER_MAXS * 256) + b;
+                const double t0 = now_ms();
+                while ((int32_t) (__atomic_load_n(pf, __ATOMIC_ACQUIRE) - want) < 0)
+                    if (now_ms() - t0 > 20000.0) { *err = 1; return 0; }
+            }
+            for (d = 0; d < 256; d++) {
+                uint64_t sum = 0;
+                for (r = 0; r < p; r++) sum += ((const uint64_t *) boxes[r])[((size_t) par * MOCK_PEER_MAXS + b) * 256 + d];
+                if (sum >= target[b]) { pick = d; break; }
+            }
+            prefix[(size_t) b * nw + wi] |= ((uint64_t) pick) << sh;
+        }
+    }
+    return 0;
 }
 
 int mpsk_sum_u64(uint64_t * dst, const uint64_t * const * srcs, int nsrc, size_t count, mpsk_stream_t stream)

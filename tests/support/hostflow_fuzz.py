@@ -21,7 +21,7 @@ import mpsort_oracle as O  # noqa: E402
 lib = C.lib
 SEEN = {}
 SWITCHES = ["MPSORT_PACK_PIPELINE", "MPSORT_FUSED_PACK", "MPSORT_NO_MERGE", "MPSORT_NO_REC16", "MPSORT_NO_REBASE", "MPSORT_NO_P2P",
-            "MPSORT_P2P_PULL", "MOCK_NO_IPC", "MPSORT_MERGE_BUCKET"]
+            "MPSORT_P2P_PULL", "MOCK_NO_IPC", "MPSORT_MERGE_BUCKET", "MPSORT_PEER_SPLITTER"]
 
 
 def make_case(rng):

@@ -67,7 +67,7 @@ def _candidates():
 
 
 @pytest.mark.parametrize("extra", [{}, {"MPSORT_EXCHANGE_PHASES": "2"}, {"MPSORT_EXCHANGE_PHASES": "3", "MPSORT_PACK_PIPELINE": "1"},
-                                   {"MPSORT_NO_MERGE": "1"}, {"MPSORT_NO_REC16": "1", "MPSORT_NO_REBASE": "1"},
+                                   {"MPSORT_NO_MERGE": "1"}, {"MPSORT_NO_REC16": "1", "MPSORT_NO_REBASE": "1"}, {"MPSORT_PEER_SPLITTER": "1"},
                                    {"MPSORT_NO_HYBRID": "1", "MPSORT_NO_HIST4": "1"}],
                          ids=lambda e: "+".join(sorted(e)) or "default")
 def test_switches_leave_the_result_bit_exact(mock_env, extra):
@@ -111,7 +111,8 @@ NCCL_WORKER = os.path.join(ROOT, "tests", "support", "nccl_threads_worker.py")
 
 
 @pytest.mark.parametrize("p,extra,p2p", [(4, {}, 1), (2, {}, 1), (7, {"MOCK_NO_IPC": "1"}, 0), (4, {"MPSORT_NO_P2P": "1"}, 0),
-                                         (3, {"MPSORT_P2P_PULL": "1"}, 1), (4, {"MPSORT_P2P_CE": "0"}, 1), (5, {"MPSORT_P2P_CE": "7"}, 1)],
+                                         (3, {"MPSORT_P2P_PULL": "1"}, 1), (4, {"MPSORT_P2P_CE": "0"}, 1), (5, {"MPSORT_P2P_CE": "7"}, 1),
+                                         (6, {"MPSORT_PEER_SPLITTER": "1"}, 1), (3, {"MPSORT_PEER_SPLITTER": "1", "MOCK_NO_IPC": "1"}, 0)],
                          ids=lambda v: "+".join("%s=%s" % kv for kv in sorted(v.items())) or "default" if isinstance(v, dict) else str(v))
 def test_nccl_transport_small_cases(mock_env, p, extra, p2p):
     """the cases of tests/nccl_worker.py (which needs >= 2 GPUs) over every exchange transport of mpsort_comm.c:
