@@ -77,19 +77,24 @@ def make_case(rng):
                 dist=dist, opts=opts, inplace=inplace), recs
 
 
-def run_case(par, recs, nccl):
+def run_case(par, recs, nccl, more=()):
+    """`more`: further (recs, outsizes) rounds sorted on the SAME communicator after the first (buffers grow, peers'
+    mappings change, sequence numbers advance)"""
     p, E = par["p"], par["E"]
     desc = O.Desc(par["offset"], par["width"], par["nwords"], par["signed"], 0)
-    exp = O.numpy_sort(recs, desc, par["outsizes"])
-    ins = [r.copy() for r in recs]
-    outs = ins if par["inplace"] else [np.zeros((par["outsizes"][k], E), np.uint8) for k in range(p)]
+    rounds = [(recs, par["outsizes"])] + list(more)
+    exps = [O.numpy_sort(rc, desc, osz) for rc, osz in rounds]
+    inss = [[r.copy() for r in rc] for rc, _ in rounds]
+    outss = [ins if (par["inplace"] and [len(x) for x in ins] == list(osz)) else [np.zeros((osz[k], E), np.uint8) for k in range(p)]
+             for ins, (_, osz) in zip(inss, rounds)]
     d = C.RadixDesc(par["offset"], par["width"], par["nwords"], par["signed"], 0)
     lib.mpsort_mpi_unset_options(-1)
     lib.mpsort_mpi_set_options(par["opts"])
 
     def sort(h, r):
-        lib.mpsort_mpi_newarray_desc_impl(ins[r].ctypes.data, len(ins[r]), outs[r].ctypes.data, len(outs[r]), E,
-                                          ctypes.byref(d), h, 0, b"fuzz")
+        for ins, outs in zip(inss, outss):
+            lib.mpsort_mpi_newarray_desc_impl(ins[r].ctypes.data, len(ins[r]), outs[r].ctypes.data, len(outs[r]), E,
+                                              ctypes.byref(d), h, 0, b"fuzz")
         if r == 0:
             st = C.last_stats(h, p)
             for k in ("used_gather", "record_mode", "rebased", "p2p_exchange", "dense_exchange"):
@@ -119,7 +124,7 @@ def run_case(par, recs, nccl):
             return False
     else:
         mpsort.run_local(p, lambda comm: sort(comm.handle, comm.rank), timeout=120)
-    return all(np.array_equal(outs[k], exp[k]) for k in range(p))
+    return all(np.array_equal(outs[k], exp[k]) for outs, exp in zip(outss, exps) for k in range(p))
 
 
 def main():
@@ -138,7 +143,18 @@ def main():
         for k in par["switches"]:
             os.environ[k] = "1"
         os.environ["MPSORT_P2P_CE"] = str(int(rng.choice([1, 1, 0, 3])))
-        if not run_case(par, recs, nccl):
+        more = []
+        if rng.integers(0, 3) == 0:
+            # the same communicator sorts two more inputs of other sizes (same record and key shape)
+            for _ in range(2):
+                sizes = [int(rng.integers(0, 3 * max(par["sizes"]) + 2)) for _ in range(par["p"])]
+                tot = sum(sizes)
+                cuts = np.sort(rng.integers(0, tot + 1, par["p"] - 1)) if par["p"] > 1 else np.array([], dtype=np.int64)
+                osz = [int(x) for x in np.diff(np.concatenate([[0], cuts, [tot]]))]
+                rc = [rng.integers(0, 4, size=(n, par["E"]), dtype=np.uint8) * rng.integers(0, 256, size=(1, par["E"]), dtype=np.uint8) for n in sizes]
+                more.append((rc, osz))
+            par["more_sizes"] = [[len(x) for x in rc] for rc, _ in more]
+        if not run_case(par, recs, nccl, more):
             print("FUZZ FAILED at case %d of seed %d:" % (i, seed), par)
             return 1
     print("FUZZ OK: %d cases, seed %d, %s ranks; paths taken:" % (ncases, seed, "NCCL-thread" if nccl else "in-process"), SEEN)

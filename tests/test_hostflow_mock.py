@@ -171,6 +171,10 @@ def test_host_code_under_address_and_ub_sanitizers(tmp_path, mock_env):
     rc = run_py(env, [NCCL_WORKER, "5"])
     out = rc.stdout.decode()
     assert rc.returncode == 0 and "NCCL THREADS OK" in out and "AddressSanitizer" not in out and "runtime error" not in out, out[-4000:]
+    # randomised cases incl. several sorts per communicator: receive buffers grow, peers' mappings of the old ones go stale
+    rc = run_py(env, [os.path.join(ROOT, "tests", "support", "hostflow_fuzz.py"), "77", "120", "nccl"])
+    out = rc.stdout.decode()
+    assert rc.returncode == 0 and "FUZZ OK" in out and "AddressSanitizer" not in out and "runtime error" not in out, out[-4000:]
     rc = run_py(env, ["-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "-s", "tests/test_zz_callback_api.py",
                       "tests/test_gpu_parity.py", "-k", "callback or golden or other_key_shapes or radix_sort_desc"])
     out = rc.stdout.decode()
