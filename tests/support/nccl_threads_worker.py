@@ -2,7 +2,8 @@
 one rank per THREAD of this process, which real NCCL allows too) against the mock device, whose NCCL and
 CUDA IPC work between threads. Runs the cases of tests/nccl_worker.py plus 2^22 records per rank (the
 size at which the exchange is cut into parts) and compares every rank's bytes with the oracle.
-usage: nccl_threads_worker.py P [big]      (env: MPSORT_LIB = the mock build; MOCK_NO_IPC, MPSORT_* switches)"""
+usage: nccl_threads_worker.py P [big]      (env: MPSORT_LIB = the mock build; MOCK_NO_IPC, MPSORT_* switches;
+BIG_LOG2N: records per rank of the big cases, default 22 = the default threshold for cutting the exchange into parts)"""
 import ctypes
 import os
 import sys
@@ -51,7 +52,8 @@ def main():
              (2, 48, 1, 30000, C.MPSORT_DISABLE_SPARSE_ALLTOALLV), (3, 24, 0, 9000, 0),
              (0, 16, 0, 50, C.MPSORT_REQUIRE_GATHER_SORT), (0, 16, 0, 50, 0), (0, 16, 0, 0, 0)]
     if big:
-        cases = [(0, 16, 0, 1 << 22, 0), (2, 48, 1, 1 << 22, 0)]
+        nbig = 1 << int(os.environ.get("BIG_LOG2N", "22"))
+        cases = [(0, 16, 0, nbig, 0), (2, 48, 1, nbig, 0)]
     ok = True
     for kind, E, signed, n, opts in cases:
         sizes = [n + 13 * k if n else 0 for k in range(p)]

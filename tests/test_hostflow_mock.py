@@ -122,13 +122,16 @@ def test_nccl_transport_small_cases(mock_env, p, extra, p2p):
     assert rc.returncode == 0 and b"NCCL THREADS OK" in rc.stdout, rc.stdout.decode()[-4000:]
 
 
-@pytest.mark.parametrize("extra,phases", [({}, 2), ({"MPSORT_PACK_PIPELINE": "1", "MPSORT_EXCHANGE_PHASES": "3"}, 3),
-                                          ({"MPSORT_FUSED_PACK": "1"}, 2)],
+SMALLER = {"BIG_LOG2N": "18", "MPSORT_PHASES_MIN_RECORDS": "1000"}      # the candidates: same flow at 2^18 records per rank
+
+
+@pytest.mark.parametrize("extra,phases", [({}, 2), (dict(SMALLER, MPSORT_PACK_PIPELINE="1", MPSORT_EXCHANGE_PHASES="3"), 3),
+                                          (dict(SMALLER, MPSORT_FUSED_PACK="1", MPSORT_EXCHANGE_PHASES="2"), 2)],
                          ids=lambda v: "+".join("%s=%s" % kv for kv in sorted(v.items())) or "default" if isinstance(v, dict) else str(v))
 def test_nccl_transport_exchange_in_parts(mock_env, extra, phases):
     """3 ranks x 2^22 records (16-byte uniform keys, 48-byte records with duplicates): the default of one process per
-    GPU -- two exchange parts over mapped peer buffers with the merge of part 0 beside the transfer of part 1 --
-    and the candidates that change the host flow of that path"""
+    GPU -- two exchange parts over mapped peer buffers with the merge of part 0 beside the transfer of part 1, taken
+    from 2^22 records per rank on -- and the candidates that change the host flow of that path"""
     rc = run_py(mock_env, [NCCL_WORKER, "3", "big"], EXPECT_PHASES=str(phases), **extra)
     assert rc.returncode == 0 and b"NCCL THREADS OK" in rc.stdout, rc.stdout.decode()[-4000:]
 
