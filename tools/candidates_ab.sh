@@ -10,7 +10,7 @@ mkdir -p gpurun_out
 {
 echo "# candidates A/B, $(nvidia-smi --query-gpu=name --format=csv,noheader | head -1), N=$N"
 echo "== parity of the candidates (tests/test_zz_candidates.py)"
-MPSORT_TEST_CANDIDATES=1 timeout 900 python -m pytest tests/test_zz_candidates.py -q -m gpu 2>&1 | tail -5
+MPSORT_TEST_CANDIDATES=1 timeout 1800 python -m pytest tests/test_zz_candidates.py -q -m gpu 2>&1 | tail -8
 echo "== parity of the callback entry points (tests/test_zz_callback_api.py)"
 timeout 900 python -m pytest tests/test_zz_callback_api.py -q -m gpu 2>&1 | tail -3
 for P in 2 4 8; do
