@@ -19,6 +19,8 @@ from mpsort import _capi as C  # noqa: E402
 import mpsort_oracle as O  # noqa: E402
 
 lib = C.lib
+NDEV = max(1, lib.mpsort_util_device_count())
+REAL_GPU = "hostmock" not in C.LIB_PATH        # real NCCL wants one device per rank
 SEEN = {}
 SWITCHES = ["MPSORT_PACK_PIPELINE", "MPSORT_FUSED_PACK", "MPSORT_NO_MERGE", "MPSORT_NO_REC16", "MPSORT_NO_REBASE", "MPSORT_NO_P2P",
             "MPSORT_P2P_PULL", "MOCK_NO_IPC", "MPSORT_MERGE_BUCKET", "MPSORT_PEER_SPLITTER"]
@@ -112,7 +114,7 @@ def run_case(par, recs, nccl, more=()):
 
         def body(r):
             try:
-                h = ctypes.c_void_p(lib.mpsort_comm_init_rank(r, p, uid, 0))
+                h = ctypes.c_void_p(lib.mpsort_comm_init_rank(r, p, uid, r % NDEV))
                 sort(h, r)
                 lib.mpsort_comm_destroy(h)
             except BaseException as e:  # noqa: B902
@@ -135,6 +137,8 @@ def main():
     rng = np.random.default_rng(seed)
     for i in range(ncases):
         par, recs = make_case(rng)
+        if nccl and REAL_GPU and par["p"] > NDEV:
+            continue
         q = int(rng.choice([1, 1, 2, 3, 4]))
         os.environ["MPSORT_EXCHANGE_PHASES"] = str(q)
         os.environ["MPSORT_PHASES_MIN_RECORDS"] = "1"

@@ -141,12 +141,19 @@ def test_candidates_over_nccl_processes(switch):
     assert rc.returncode == 0 and b"NCCL PARITY OK" in rc.stdout, rc.stdout.decode()[-4000:]
 
 
-def test_randomised_cases_on_the_gpu():
+@pytest.mark.parametrize("transport", [[], ["nccl"]], ids=["rank-threads", "nccl"])
+def test_randomised_cases_on_the_gpu(transport):
     """tests/support/hostflow_fuzz.py (the generator of the CPU host-flow tests) against the REAL library: 300 random
-    cases on rank threads of one GPU -- shipped switches only, 1-4 exchange parts on tiny inputs -- byte for byte
-    against the oracle's contract. Opt-in like the rest of this file: written without a GPU at hand."""
+    cases on rank threads of one GPU, and as NCCL ranks (threads of one process, one GPU each; cases with more ranks than
+    GPUs are left out) -- shipped switches only, 1-4 exchange parts on tiny inputs -- byte for byte against the oracle's
+    contract. Opt-in like the rest of this file: written without a GPU at hand."""
+    if transport:
+        sys.path.insert(0, os.path.join(ROOT, "mp-sort_b200"))
+        from mpsort import _capi as C
+        if C.lib.mpsort_util_device_count() < 2:
+            pytest.skip("needs >= 2 GPUs")
     env = dict(os.environ, FUZZ_SWITCHES="shipped")
     env.pop("MPSORT_LIB", None)
-    rc = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "support", "hostflow_fuzz.py"), "20261019", "300"], env=env,
-                        timeout=1200, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    rc = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "support", "hostflow_fuzz.py"), "20261019", "300"] + transport,
+                        env=env, timeout=1200, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     assert rc.returncode == 0 and b"FUZZ OK" in rc.stdout, rc.stdout.decode()[-4000:]
