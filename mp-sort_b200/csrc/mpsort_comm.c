@@ -639,15 +639,22 @@ static void exchange_p2p(struct mpsort_comm * c, const void * sendbuf, const int
                 for (k = 0; k < 9; k++) CUDA_OK(c, cudaEventCreateWithFlags(&c->p2p.ce_ev[k], cudaEventDisableTiming));
                 c->p2p.ce_created = 1;
             }
-            CUDA_OK(c, cudaEventRecord(c->p2p.ce_ev[8], c->stream));
-            for (k = 0; k < 8 && k < p; k++) CUDA_OK(c, cudaStreamWaitEvent(c->p2p.ce_stream[k], c->p2p.ce_ev[8], 0));
             /* remote slices in shifted order (me+1, me+2, ...: at every step the pairs form a
-             * permutation) dealt round-robin to copy_engine streams; my own slice on stream 7 */
+             * permutation) dealt round-robin to copy_engine streams; my own slice on stream 7.
+             * Every copy stream that gets a copy first waits for the send buffer (the main stream
+             * up to here) and the main stream then waits for every one of them -- stream 7 included,
+             * whatever p is (it used to be left out for p < 8: found by the CPU stream model,
+             * tests/native/mock_async.cpp). */
+            unsigned used = 0;
+            for (k = 0; k < p; k++) if (rbytes[k]) used |= 1u << (rrem[k] ? k % c->p2p.copy_engine : 7);
+            CUDA_OK(c, cudaEventRecord(c->p2p.ce_ev[8], c->stream));
+            for (k = 0; k < 8; k++) if ((used >> k) & 1u) CUDA_OK(c, cudaStreamWaitEvent(c->p2p.ce_stream[k], c->p2p.ce_ev[8], 0));
             for (k = 0; k < p; k++)
                 if (rbytes[k])
                     CUDA_OK(c, cudaMemcpyAsync(rdst[k], rsrc[k], (size_t) rbytes[k], cudaMemcpyDeviceToDevice,
                                                c->p2p.ce_stream[rrem[k] ? k % c->p2p.copy_engine : 7]));
-            for (k = 0; k < 8 && k < p; k++) {
+            for (k = 0; k < 8; k++) {
+                if (!((used >> k) & 1u)) continue;
                 CUDA_OK(c, cudaEventRecord(c->p2p.ce_ev[k], c->p2p.ce_stream[k]));
                 CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->p2p.ce_ev[k], 0));
             }

@@ -17,6 +17,9 @@
  * NCCL. It is never built by the product Makefile, never shipped, and the product library has no
  * CPU path: it aborts without a CUDA device.
  */
+#ifdef MOCK_WITH_ASYNC_LAYER
+#include "mock_rename.h"    /* the stream-ordered entry points become mocksync_*: mock_async.cpp decides when they run */
+#endif
 #include <pthread.h>
 #include <stdint.h>
 #include <stdio.h>

@@ -20,7 +20,7 @@ import mpsort_oracle as O  # noqa: E402
 
 lib = C.lib
 NDEV = max(1, lib.mpsort_util_device_count())
-REAL_GPU = "hostmock" not in C.LIB_PATH        # real NCCL wants one device per rank
+REAL_GPU = not hasattr(lib, "mpsk_launch_count") or not hasattr(lib, "mocksync_cudaFree")    # real NCCL wants one device per rank
 SEEN = {}
 SWITCHES = ["MPSORT_PACK_PIPELINE", "MPSORT_FUSED_PACK", "MPSORT_NO_MERGE", "MPSORT_NO_REC16", "MPSORT_NO_REBASE", "MPSORT_NO_P2P",
             "MPSORT_P2P_PULL", "MOCK_NO_IPC", "MPSORT_MERGE_BUCKET", "MPSORT_PEER_SPLITTER"]
@@ -160,6 +160,8 @@ def main():
                 rc = [rng.integers(0, 4, size=(n, par["E"]), dtype=np.uint8) * rng.integers(0, 256, size=(1, par["E"]), dtype=np.uint8) for n in sizes]
                 more.append((rc, osz))
             par["more_sizes"] = [[len(x) for x in rc] for rc, _ in more]
+        if os.environ.get("FUZZ_VERBOSE"):
+            print("case %d:" % i, par, flush=True)
         if not run_case(par, recs, nccl, more):
             print("FUZZ FAILED at case %d of seed %d:" % (i, seed), par)
             return 1
