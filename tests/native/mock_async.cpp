@@ -99,7 +99,6 @@ struct MockEvent {
     double t_ms = 0.0;
 };
 
-static int g_async = -1;                /* -1 not read yet, 0 off, 1 on */
 static unsigned long g_seed = 0;
 static pthread_mutex_t g_reg_lock = PTHREAD_MUTEX_INITIALIZER;
 static std::map<const void *, size_t> g_pinned;     /* cudaMallocHost allocations: base -> bytes */
@@ -109,15 +108,14 @@ static thread_local std::vector<MockStream *> t_streams;
 static thread_local uint64_t t_rng = 0;
 static thread_local int t_depth = 0;
 
-static bool async_on()
+static bool read_switch()
 {
-    if (g_async < 0) {
-        const char * e = getenv("MOCK_ASYNC");
-        g_seed = e ? strtoul(e, NULL, 10) : 0;
-        g_async = (e && *e) ? 1 : 0;
-    }
-    return g_async == 1;
+    const char * e = getenv("MOCK_ASYNC");
+    g_seed = e ? strtoul(e, NULL, 10) : 0;
+    return e && *e;
 }
+static const bool g_async = read_switch();      /* read once, when the library is loaded */
+static bool async_on() { return g_async; }
 
 static uint64_t rnd()
 {

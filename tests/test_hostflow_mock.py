@@ -48,17 +48,15 @@ BIG = ["tests/test_gpu_parity.py::test_full_size_config_b_by_properties",
 
 
 def test_gpu_suite_host_flow_on_the_mock(mock_env):
-    """tests/test_python_api.py (the reference's own test file re-hosted), test_gpu_parity.py and
-    test_zz_callback_api.py, `-m gpu`, against the mock build"""
-    args = ["-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "tests/test_python_api.py",
-            "tests/test_gpu_parity.py", "tests/test_zz_callback_api.py"]
-    for b in BIG:
-        args += ["--deselect", b]
+    """tests/test_python_api.py (the reference's own test file re-hosted) and test_zz_callback_api.py, `-m gpu`, against
+    the mock build, every stream operation run at once (test_gpu_parity.py joins them in
+    test_gpu_suite_host_flow_with_deferred_stream_operations below)"""
+    args = ["-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "tests/test_python_api.py", "tests/test_zz_callback_api.py"]
     rc = run_py(mock_env, args, timeout=1500)
     out = rc.stdout.decode()
     assert rc.returncode == 0, out[-4000:]
     m = re.search(r"(\d+) passed", out)
-    assert m and int(m.group(1)) >= 150 and "failed" not in out, out[-2000:]
+    assert m and int(m.group(1)) >= 60 and "failed" not in out, out[-2000:]
 
 
 def _candidates():
@@ -141,14 +139,11 @@ def test_rank_threads_have_no_data_races(tmp_path):
     """tests/native/hostflow_threads.c + the host files + the mock, all built with -fsanitize=thread: rank threads
     of an in-process group and NCCL ranks as threads, two sorts each, 16- and 48-byte records with cross-rank ties"""
     exe = str(tmp_path / "hostflow_tsan")
-    srcs = [os.path.join(ROOT, "tests", "native", "hostflow_threads.c"), os.path.join(ROOT, "tests", "native", "mock_device.c")] \
-        + [os.path.join(hostmock.CSRC, f) for f in hostmock.HOST_FILES]
-    cc = subprocess.run(["gcc", "-O1", "-g", "-fsanitize=thread", "-std=gnu11", "-I" + os.path.join(ROOT, "include"), "-I" + hostmock.CSRC,
-                         "-I" + os.path.join(ROOT, "oracle"), "-I" + hostmock.CUDA_INC, "-o", exe] + srcs + ["-lpthread", "-lm"],
-                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
-    if cc.returncode != 0 and b"tsan" in cc.stdout.lower():
+    try:
+        hostmock.compile_and_link(exe, flags=("-fsanitize=thread",), shared=False,
+                                  extra_sources=[os.path.join(ROOT, "tests", "native", "hostflow_threads.c")])
+    except subprocess.CalledProcessError:
         pytest.skip("no ThreadSanitizer runtime on this box")
-    assert cc.returncode == 0, cc.stdout.decode()[-3000:]
     env = {k: v for k, v in os.environ.items() if not k.startswith("MPSORT_")}
     for args in (["4", "30000", "16"], ["3", "20000", "48"], ["7", "5000", "24"]):
         rc = subprocess.run([exe] + args, env=env, timeout=600, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
@@ -161,12 +156,7 @@ def test_host_code_under_address_and_ub_sanitizers(tmp_path, mock_env):
     """the mock build again with -fsanitize=address,undefined ("device memory" is malloc here, so an arena slot that is
     too small for what a kernel's contract writes is a heap overflow): NCCL-transport cases and the callback entry
     points, sanitizer runtimes preloaded into the python worker"""
-    so = str(tmp_path / "libmpsort-hostmock-asan.so")
-    srcs = [os.path.join(ROOT, "tests", "native", "mock_device.c")] + [os.path.join(hostmock.CSRC, f) for f in hostmock.HOST_FILES]
-    cc = subprocess.run(["gcc", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-fPIC", "-shared", "-std=gnu11",
-                         "-I" + os.path.join(ROOT, "include"), "-I" + hostmock.CSRC, "-I" + os.path.join(ROOT, "oracle"),
-                         "-I" + hostmock.CUDA_INC, "-o", so] + srcs + ["-lpthread"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
-    assert cc.returncode == 0, cc.stdout.decode()[-3000:]
+    so = hostmock.compile_and_link(str(tmp_path / "libmpsort-hostmock-asan.so"), flags=("-fsanitize=address,undefined", "-fno-omit-frame-pointer"))
     pre = [subprocess.run(["gcc", "-print-file-name=" + n], stdout=subprocess.PIPE).stdout.decode().strip() for n in ("libasan.so", "libubsan.so")]
     if not all(os.path.isabs(x) and os.path.exists(x) for x in pre):
         pytest.skip("sanitizer runtimes not found")
@@ -175,9 +165,11 @@ def test_host_code_under_address_and_ub_sanitizers(tmp_path, mock_env):
     out = rc.stdout.decode()
     assert rc.returncode == 0 and "NCCL THREADS OK" in out and "AddressSanitizer" not in out and "runtime error" not in out, out[-4000:]
     # randomised cases incl. several sorts per communicator: receive buffers grow, peers' mappings of the old ones go stale
-    rc = run_py(env, [os.path.join(ROOT, "tests", "support", "hostflow_fuzz.py"), "77", "120", "nccl"])
-    out = rc.stdout.decode()
-    assert rc.returncode == 0 and "FUZZ OK" in out and "AddressSanitizer" not in out and "runtime error" not in out, out[-4000:]
+    # ... and with the stream operations deferred (a deferred copy into a buffer that was freed meanwhile would show here)
+    for extra in ({}, {"MOCK_ASYNC": "5"}):
+        rc = run_py(env, [os.path.join(ROOT, "tests", "support", "hostflow_fuzz.py"), "77", "60", "nccl"], **extra)
+        out = rc.stdout.decode()
+        assert rc.returncode == 0 and "FUZZ OK" in out and "AddressSanitizer" not in out and "runtime error" not in out, out[-4000:]
     rc = run_py(env, ["-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "-s", "tests/test_zz_callback_api.py",
                       "tests/test_gpu_parity.py", "-k", "callback or golden or other_key_shapes or radix_sort_desc"])
     out = rc.stdout.decode()
@@ -204,3 +196,61 @@ def test_randomised_host_flow_cases(mock_env, seed, transport):
     rc = run_py(mock_env, [os.path.join(ROOT, "tests", "support", "hostflow_fuzz.py"), str(seed), "250"] + transport)
     out = rc.stdout.decode()
     assert rc.returncode == 0 and "FUZZ OK" in out, out[-3000:]
+
+
+# ---- stream semantics: deferred, randomly interleaved execution of the stream operations -----------------
+@pytest.mark.parametrize("transport", [[], ["nccl"]], ids=["in-process", "nccl-threads"])
+@pytest.mark.parametrize("async_seed", ["1", "2"])
+def test_randomised_cases_with_deferred_stream_operations(mock_env, transport, async_seed):
+    """tests/native/mock_async.cpp (MOCK_ASYNC=<seed>): copies, memsets, events, NCCL calls and kernel launches only run
+    when a synchronisation, an event wait or the seeded scheduler makes them, so a consumer that does not wait for its
+    producer gets stale bytes. 150 random cases per transport and seed, every switch incl. the candidates' stream juggling."""
+    rc = run_py(mock_env, [os.path.join(ROOT, "tests", "support", "hostflow_fuzz.py"), "4242", "150"] + transport, MOCK_ASYNC=async_seed)
+    out = rc.stdout.decode()
+    assert rc.returncode == 0 and "FUZZ OK" in out, out[-3000:]
+
+
+def test_gpu_suite_host_flow_with_deferred_stream_operations(mock_env):
+    """the GPU test files again (see test_gpu_suite_host_flow_on_the_mock), stream operations deferred"""
+    args = ["-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "tests/test_python_api.py",
+            "tests/test_gpu_parity.py", "tests/test_zz_callback_api.py"]
+    for b in BIG:
+        args += ["--deselect", b]
+    rc = run_py(mock_env, args, timeout=1500, MOCK_ASYNC="3")
+    out = rc.stdout.decode()
+    m = re.search(r"(\d+) passed", out)
+    assert rc.returncode == 0 and m and int(m.group(1)) >= 150 and "failed" not in out, out[-4000:]
+
+
+MUTANTS = [
+    # the bug this model found in round 1: the copy stream of the own slice was only synchronised when p == 8
+    ("mpsort_comm.c", "for (k = 0; k < 8; k++) if ((used >> k) & 1u) CUDA_OK(c, cudaStreamWaitEvent(c->p2p.ce_stream[k], c->p2p.ce_ev[8], 0));",
+     "for (k = 0; k < 8 && k < p; k++) if ((used >> k) & 1u) CUDA_OK(c, cudaStreamWaitEvent(c->p2p.ce_stream[k], c->p2p.ce_ev[8], 0));"),
+    # the merge of a part does not wait for its transfer
+    ("mpsort_host.c", "if (Q > 1) CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->phase_ev[fused_pack ? Q - 1 : q], 0));", "/* mutant */"),
+    # the caller's stream does not wait for the merges on the second stream
+    ("mpsort_host.c", "CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->phase_ev[MPS_MAX_RANKS], 0));", "/* mutant */"),
+]
+
+
+@pytest.mark.parametrize("fname,old,new", MUTANTS, ids=["own-slice-stream", "merge-before-transfer", "return-before-merge"])
+def test_stream_model_catches_seeded_synchronisation_bugs(tmp_path, mock_env, fname, old, new):
+    """mutation check of the checker: a copy of the host sources with ONE synchronisation removed must fail the
+    randomised cases under MOCK_ASYNC (and these three do, with every seed tried)"""
+    import shutil
+    csrc = str(tmp_path / "csrc")
+    shutil.copytree(hostmock.CSRC, csrc, ignore=shutil.ignore_patterns("kernels"))
+    path = os.path.join(csrc, fname)
+    src = open(path).read()
+    assert src.count(old) == 1, "the mutated line moved: update MUTANTS"
+    open(path, "w").write(src.replace(old, new))
+    saved = hostmock.CSRC, list(hostmock.INCLUDES)
+    try:
+        hostmock.CSRC = csrc
+        hostmock.INCLUDES[1] = "-I" + csrc
+        so = hostmock.compile_and_link(str(tmp_path / "libmutant.so"))
+    finally:
+        hostmock.CSRC = saved[0]
+        hostmock.INCLUDES[:] = saved[1]
+    rc = run_py(dict(mock_env, MPSORT_LIB=so), [os.path.join(ROOT, "tests", "support", "hostflow_fuzz.py"), "3", "200", "nccl"], MOCK_ASYNC="1")
+    assert rc.returncode != 0 and b"FUZZ OK" not in rc.stdout, "the mutant went unnoticed"
