@@ -145,8 +145,12 @@ def test_rank_threads_have_no_data_races(tmp_path):
     except subprocess.CalledProcessError:
         pytest.skip("no ThreadSanitizer runtime on this box")
     env = {k: v for k, v in os.environ.items() if not k.startswith("MPSORT_")}
-    for args in (["4", "30000", "16"], ["3", "20000", "48"], ["7", "5000", "24"]):
-        rc = subprocess.run([exe] + args, env=env, timeout=600, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    # plain, and with deferred stream operations + the exchange in two parts: a peer's deferred copy into my receive buffer
+    # and my merge of it are then ordered by nothing but the host code's own synchronisation
+    deferred = dict(env, MOCK_ASYNC="1", MPSORT_EXCHANGE_PHASES="2", MPSORT_PHASES_MIN_RECORDS="1")
+    for e, args in ((env, ["4", "30000", "16"]), (env, ["3", "20000", "48"]), (env, ["7", "5000", "24"]),
+                    (deferred, ["4", "30000", "16"]), (deferred, ["3", "20000", "48"])):
+        rc = subprocess.run([exe] + args, env=e, timeout=600, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
         out = rc.stdout.decode()
         assert rc.returncode == 0 and "THREADS OK" in out and "ThreadSanitizer" not in out, out[-4000:]
 
