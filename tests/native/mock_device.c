@@ -7,14 +7,18 @@
  * against the oracle with rank threads.
  *
  * What is mocked: (1) the CUDA runtime calls the host code makes -- "device memory" is malloc,
- * every stream operation runs synchronously, events carry host wall time; (2) the kernel ABI of
+ * every stream operation runs at once, events carry host wall time; (2) the kernel ABI of
  * mpsort_kernels.h -- each entry point is restated as a plain loop with the SAME contract
  * (what it reads, what it writes, stability), not the same algorithm; (3) NCCL and CUDA IPC --
  * between the rank THREADS of one process, every collective blocking (so both the in-process
  * transport and the NCCL transport with its mapped peer buffers run here).
+ * Built on its own this file is the complete, synchronous mock. tests/support/hostmock.py builds
+ * it with -DMOCK_WITH_ASYNC_LAYER: the stream-ordered entry points are then renamed
+ * (mock_rename.h) and exported by mock_async.cpp instead, which can defer and interleave them
+ * (MOCK_ASYNC=<seed>) so that missing synchronisation between streams shows up as wrong bytes.
  *
- * What this can NOT show: anything about the real kernels, stream ordering, races, peer memory,
- * NCCL. It is never built by the product Makefile, never shipped, and the product library has no
+ * What this can NOT show: anything about the real kernels, peer-memory visibility on hardware,
+ * real NCCL. It is never built by the product Makefile, never shipped, and the product library has no
  * CPU path: it aborts without a CUDA device.
  */
 #ifdef MOCK_WITH_ASYNC_LAYER
