@@ -27,9 +27,9 @@ CASES = [("main-mpi", ["100000"]), ("main-mpi", ["7"]), ("main-mpi", ["0"]),
          ("bench-mpi", ["-g", "-s", "-b", "4", "30000"]), ("bench-mpi", ["-b", "10", "-g", "100000"]), ("bench-mpi", ["1"])]
 
 
-def run_driver(exe, args, threads=None, launcher=None, env=None):
+def run_driver(exe, args, threads=None, launcher=None, env=None, keep=()):
     env = dict(env or os.environ)
-    env = {k: v for k, v in env.items() if not k.startswith("MPSORT_")}
+    env = {k: v for k, v in env.items() if not k.startswith("MPSORT_") and (not k.startswith("MOCK_") or k in keep)}
     if threads:
         env["MPSORT_DROPIN_THREADS"] = str(threads)
     cmd = [exe] + args
@@ -57,6 +57,7 @@ def test_reference_drivers_host_flow_on_the_mock(mock_drivers, driver, args):
     exe = os.path.join(mock_drivers, driver + ".mock")
     run_driver(exe, args)                      # one rank
     out = run_driver(exe, args, threads=5)     # five rank threads
+    run_driver(exe, args, threads=3, env=dict(os.environ, MOCK_ASYNC="1"), keep=("MOCK_ASYNC",))    # stream operations deferred
     if driver == "bench-mpi":
         assert "NTask = 5" in out and "MPSort total time" in out
     if args[-1] not in ("0", "1", "7", "3000"):
