@@ -25,6 +25,12 @@ if _nccl:
 
 lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
 
+# tests/native/ builds a stand-in for the GPU side (the C host code against a mock device) for CPU-only host-flow
+# tests. It is not a CPU path of the product: loading it takes MPSORT_LIB pointing at it AND this second switch.
+if hasattr(lib, "mocksync_cudaFree") and os.environ.get("MPSORT_ALLOW_MOCK_DEVICE") != "1":
+    raise ImportError("mpsort-b200: %s is the mock-device build of the test suite, not the product library; "
+                      "there is no CPU fallback (tests set MPSORT_ALLOW_MOCK_DEVICE=1)" % LIB_PATH)
+
 c_void_p = ctypes.c_void_p
 c_size_t = ctypes.c_size_t
 c_int = ctypes.c_int

@@ -1,5 +1,5 @@
 """Randomised cases for the C host code on the mock device (worker of tests/test_hostflow_mock.py; also a tool:
-`MPSORT_LIB=tests/native/_build/libmpsort-hostmock.so python tests/support/hostflow_fuzz.py SEED NCASES [nccl]`).
+`MPSORT_ALLOW_MOCK_DEVICE=1 MPSORT_LIB=tests/native/_build/libmpsort-hostmock.so python tests/support/hostflow_fuzz.py SEED NCASES [nccl]`).
 Each case: random number of ranks, input and output sizes (zeros included), record size, key shape (width, words,
 signedness, offset), key distribution (uniform, few distinct values, all equal, sorted, reverse, narrow signed range),
 options and exchange parts; every rank's bytes are compared with the oracle's statement of the contract

@@ -1,7 +1,7 @@
 """Builds tests/native/_build/libmpsort-hostmock.so: the product's C host files, compiled
 unchanged, linked against tests/native/mock_device.c + mock_async.cpp instead of the CUDA kernels,
 the CUDA runtime and NCCL (TEST INFRASTRUCTURE; see the headers of those files for what they can and
-cannot show). Processes that should use it set MPSORT_LIB to the returned path BEFORE importing
+cannot show). Processes that should use it set MPSORT_LIB to the returned path and MPSORT_ALLOW_MOCK_DEVICE=1 BEFORE importing
 mpsort; the product itself never looks for it. MOCK_ASYNC=<seed> in the environment of such a
 process turns on the deferred, randomly interleaved execution of stream operations."""
 import os

@@ -2,7 +2,7 @@
 one rank per THREAD of this process, which real NCCL allows too) against the mock device, whose NCCL and
 CUDA IPC work between threads. Runs the cases of tests/nccl_worker.py plus 2^22 records per rank (the
 size at which the exchange is cut into parts) and compares every rank's bytes with the oracle.
-usage: nccl_threads_worker.py P [big]      (env: MPSORT_LIB = the mock build; MOCK_NO_IPC, MPSORT_* switches;
+usage: nccl_threads_worker.py P [big]      (env: MPSORT_LIB = the mock build + MPSORT_ALLOW_MOCK_DEVICE=1; MOCK_NO_IPC, MPSORT_* switches;
 BIG_LOG2N: records per rank of the big cases, default 22 = the default threshold for cutting the exchange into parts)"""
 import ctypes
 import os

@@ -25,9 +25,9 @@ import hostmock  # noqa: E402
 @pytest.fixture(scope="module")
 def mock_env():
     so = hostmock.build()
-    env = dict(os.environ, MPSORT_LIB=so)
+    env = dict(os.environ, MPSORT_LIB=so, MPSORT_ALLOW_MOCK_DEVICE="1")
     for k in list(env):
-        if k.startswith("MPSORT_") and k != "MPSORT_LIB":
+        if k.startswith("MPSORT_") and k not in ("MPSORT_LIB", "MPSORT_ALLOW_MOCK_DEVICE"):
             del env[k]
     return env
 
@@ -258,3 +258,10 @@ def test_stream_model_catches_seeded_synchronisation_bugs(tmp_path, mock_env, fn
         hostmock.INCLUDES[:] = saved[1]
     rc = run_py(dict(mock_env, MPSORT_LIB=so), [os.path.join(ROOT, "tests", "support", "hostflow_fuzz.py"), "3", "200", "nccl"], MOCK_ASYNC="1")
     assert rc.returncode != 0 and b"FUZZ OK" not in rc.stdout, "the mutant went unnoticed"
+
+
+def test_mock_build_is_not_a_cpu_path_of_the_product(mock_env):
+    """pointing MPSORT_LIB at the mock build is not enough: the Python package refuses it without the tests' second switch"""
+    env = {k: v for k, v in mock_env.items() if k != "MPSORT_ALLOW_MOCK_DEVICE"}
+    rc = run_py(env, "import sys; sys.path.insert(0, %r); import mpsort" % os.path.join(ROOT, "mp-sort_b200"))
+    assert rc.returncode != 0 and b"no CPU fallback" in rc.stdout, rc.stdout.decode()[-2000:]

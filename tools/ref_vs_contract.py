@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 sys.path.insert(0, os.path.join(ROOT, "mp-sort_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tests", "support"))
 import mpsort_oracle as O  # noqa: E402
-import hostflow_fuzz as F  # noqa: E402  (only its case generator; needs MPSORT_LIB or the built product library to import)
+import hostflow_fuzz as F  # noqa: E402  (only its case generator; importing it loads the product library, or the mock build with MPSORT_LIB + MPSORT_ALLOW_MOCK_DEVICE=1)
 
 
 def main():
