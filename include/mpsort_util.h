@@ -33,6 +33,20 @@ void   mpsort_util_dev_memset(int device, void * dst, int value, size_t nbytes);
 void   mpsort_util_generate(mpsort_comm_t comm, void * dst, size_t n, size_t elsize,
                             int kind, uint64_t seed);
 
+/* the same records as rank `rank` of `nranks` would generate (one GPU can then hold the
+ * input of a many-rank CPU run of the reference, chunk by chunk). Blocking. */
+void   mpsort_util_generate_as(mpsort_comm_t comm, void * dst, size_t n, size_t elsize,
+                               int kind, uint64_t seed, uint64_t rank, uint64_t nranks);
+
+/* Order-independent 64-bit multiset hash of whole records of a device or host buffer (local
+ * part): out2[0] = sum, out2[1] = xor over the records of h(record), h = the record's 8-byte
+ * little-endian words (the last one zero-padded) folded through mix64. Two buffers hold the
+ * same multiset of records iff (with overwhelming probability) both words agree; summed /
+ * xored over ranks it is the "records preserved" check of the full-size runs, which the
+ * reference's signed-byte sum cannot give (swapped payloads, permuted bytes). Blocking. */
+void   mpsort_util_multiset_hash(mpsort_comm_t comm, const void * base, size_t n, size_t elsize,
+                                 uint64_t * out2);
+
 /* order check of this rank's sorted output; returns the number of adjacent
  * violations (key order, and with check_ties the tag order inside equal keys) and
  * stores the first/last packed key words into firstlast[2*nw]. Blocking. */

@@ -84,11 +84,20 @@ void * mps_arena_get(struct mpsort_comm * c, int slot, size_t bytes)
 {
     if (bytes == 0) bytes = 256;
     if (c->slot[slot].cap >= bytes) return c->slot[slot].ptr;
-    if (c->slot[slot].ptr && slot == (c->p2p.pull ? MPS_S_SEND : MPS_S_RECV) && c->kind == MPS_T_NCCL && !c->p2p.disabled && c->p2p.nzombies < 64) {
-        /* peers may still have this buffer mapped (CUDA IPC): it is freed when the
-         * communicator is destroyed, not now. Growth is rare (grow-only, 25 % headroom). */
+    if (c->slot[slot].ptr && slot == (c->p2p.pull ? MPS_S_SEND : MPS_S_RECV) && c->kind == MPS_T_NCCL && !c->p2p.disabled) {
+        /* peers may still have this buffer mapped (CUDA IPC) and push into it by DMA: it is
+         * NEVER freed before the communicator is destroyed (so its address cannot be handed
+         * out again either). Growth is rare (grow-only, 25 % headroom). */
         CUDA_OK(c, cudaStreamSynchronize(c->stream));
+        if (c->p2p.nzombies == c->p2p.zombies_cap) {
+            const int cap = c->p2p.zombies_cap ? 2 * c->p2p.zombies_cap : 16;
+            void ** z = (void **) realloc(c->p2p.zombies, sizeof(void *) * (size_t) cap);
+            if (!z) mps_fatal(c, __FILE__, __LINE__, "out of host memory");
+            c->p2p.zombies = z;
+            c->p2p.zombies_cap = cap;
+        }
         c->p2p.zombies[c->p2p.nzombies++] = c->slot[slot].ptr;
+        c->p2p.generation++;
         c->slot[slot].ptr = NULL;
         c->slot[slot].cap = 0;
         bytes += bytes / 4;
@@ -282,6 +291,7 @@ void mpsort_comm_destroy(mpsort_comm_t c)
     if (c->kind == MPS_T_NCCL && c->size > 1) mpsort_comm_barrier(c);   /* everyone unmapped before anyone frees */
     if (c->peer.mine) cudaFree(c->peer.mine);
     for (s = 0; s < c->p2p.nzombies; s++) cudaFree(c->p2p.zombies[s]);
+    free(c->p2p.zombies);
     for (s = 0; s < MPS_NSLOTS; s++) if (c->slot[s].ptr) cudaFree(c->slot[s].ptr);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->p2p.d_flag) cudaFree(c->p2p.d_flag);
@@ -534,6 +544,7 @@ void mps_comm_recv_info(struct mpsort_comm * c, void * recvbuf, void * sendbuf, 
     void * buf = c->p2p.pull ? sendbuf : recvbuf;
     info->ptr = (uint64_t) (uintptr_t) buf;
     info->cap = c->slot[c->p2p.pull ? MPS_S_SEND : MPS_S_RECV].cap;
+    info->generation = c->p2p.generation;
     cudaIpcMemHandle_t hdl;
     if (cudaIpcGetMemHandle(&hdl, buf) != cudaSuccess) {
         cudaGetLastError();
@@ -551,16 +562,17 @@ int mps_comm_p2p_prepare(struct mpsort_comm * c, const struct mps_recv_info * al
     if (!ok) { c->p2p.disabled = 1; return 0; }
     for (j = 0; j < c->size; j++) {
         /* my own entry counts too: every rank must reach the same verdict */
-        if (c->p2p.peer_ptr[j] == all[j].ptr) continue;
+        if (c->p2p.peer_ptr[j] == all[j].ptr && c->p2p.peer_gen[j] == all[j].generation) continue;
         changed = 1;
     }
     /* every rank sees the same table and has the same history: `changed` agrees everywhere */
     if (!changed) return 1;
     int mine_ok = 1;
     c->p2p.peer_ptr[c->rank] = all[c->rank].ptr;
+    c->p2p.peer_gen[c->rank] = all[c->rank].generation;
     for (j = 0; j < c->size; j++) {
         if (j == c->rank) continue;
-        if (c->p2p.peer_ptr[j] == all[j].ptr && c->p2p.peer_base[j]) continue;
+        if (c->p2p.peer_ptr[j] == all[j].ptr && c->p2p.peer_gen[j] == all[j].generation && c->p2p.peer_base[j]) continue;
         if (c->p2p.peer_base[j]) { cudaIpcCloseMemHandle(c->p2p.peer_base[j]); c->p2p.peer_base[j] = NULL; }
         cudaIpcMemHandle_t hdl;
         memcpy(&hdl, all[j].handle, sizeof(hdl));
@@ -572,6 +584,7 @@ int mps_comm_p2p_prepare(struct mpsort_comm * c, const struct mps_recv_info * al
         }
         c->p2p.peer_base[j] = p;
         c->p2p.peer_ptr[j] = all[j].ptr;
+        c->p2p.peer_gen[j] = all[j].generation;
     }
     /* collective agreement: one rank that cannot map switches everyone back to NCCL */
     char flag = (char) mine_ok, flags[MPS_MAX_RANKS];

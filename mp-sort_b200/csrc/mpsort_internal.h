@@ -113,8 +113,11 @@ struct mpsort_comm {
         int pull;                              /* 1: read peers' send buffers, 0: write peers' receive buffers */
         void * peer_base[MPS_MAX_RANKS];       /* my mapping of rank j's exchange buffer */
         uint64_t peer_ptr[MPS_MAX_RANKS];      /* rank j's own pointer the mapping belongs to */
-        void * zombies[64];                    /* my old receive buffers peers may still have mapped */
-        int nzombies;
+        void ** zombies;                       /* my old receive buffers peers may still have mapped (never freed
+                                                * before the communicator is destroyed; the list grows as needed) */
+        int nzombies, zombies_cap;
+        uint64_t generation;                   /* bumped every time my exchange buffer is replaced */
+        uint64_t peer_gen[MPS_MAX_RANKS];      /* generation of rank j's buffer my mapping belongs to */
         int * d_flag;                          /* device word for the completion all-reduce */
         int copy_engine;                       /* 1: slices move by cudaMemcpyAsync (DMA engines, no SMs) */
         cudaStream_t ce_stream[8];             /* copy-engine mode: peer copies fan out over these */
@@ -124,7 +127,7 @@ struct mpsort_comm {
 };
 
 /* what every rank tells the others about its receive buffer during LayDistr */
-struct mps_recv_info { uint64_t ptr; uint64_t cap; unsigned char handle[64]; };
+struct mps_recv_info { uint64_t ptr; uint64_t cap; uint64_t generation; unsigned char handle[64]; };
 void mps_comm_recv_info(struct mpsort_comm * c, void * recvbuf, void * sendbuf, struct mps_recv_info * info);
 /* after the all-gather: (re)map peers whose buffer changed; returns 1 if the peer-store
  * exchange can be used by ALL ranks this call (collective decision) */

@@ -179,6 +179,11 @@ int mpsk_checksum(const void * base, size_t nbytes, uint64_t * sum, mpsk_stream_
 
 /* ---- bench / test support (not on the product path) ---- */
 
+/* Order-independent multiset hash of n whole records: out[0] += sum, out[1] ^= xor over the
+ * records of h(record) (the record's 8-byte little-endian words, last one zero-padded, folded
+ * through mix64). out = device u64[2], zeroed by the caller. */
+int mpsk_multiset_hash(const void * base, size_t n, size_t elsize, uint64_t * out, mpsk_stream_t stream);
+
 /* Synthetic records, SURVEY.md 8(d). kind:
  *  0 = uniform u64 key, 16-byte {key,payload}; payload = (rank<<40)+i
  *  1 = mostly sorted (1% perturbed) u64 key, 16-byte records

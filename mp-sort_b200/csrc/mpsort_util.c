@@ -64,6 +64,37 @@ void mpsort_util_generate(mpsort_comm_t c, void * dst, size_t n, size_t elsize, 
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
 }
 
+void mpsort_util_generate_as(mpsort_comm_t c, void * dst, size_t n, size_t elsize, int kind, uint64_t seed,
+        uint64_t rank, uint64_t nranks)
+{
+    CUDA_OK(c, cudaSetDevice(c->device));
+    KERN_OK(c, mpsk_generate(dst, n, elsize, kind, seed, rank, nranks, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+}
+
+void mpsort_util_multiset_hash(mpsort_comm_t c, const void * base, size_t n, size_t elsize, uint64_t * out2)
+{
+    uint64_t h[2] = { 0, 0 };
+    struct cudaPointerAttributes a;
+    CUDA_OK(c, cudaSetDevice(c->device));
+    int on_dev = 0;
+    if (cudaPointerGetAttributes(&a, base) == cudaSuccess)
+        on_dev = (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged);
+    else cudaGetLastError();
+    const void * src = base;
+    if (!on_dev && n) {
+        void * tmp = mps_arena_get(c, MPS_S_DIN, n * elsize);
+        CUDA_OK(c, cudaMemcpyAsync(tmp, base, n * elsize, cudaMemcpyHostToDevice, c->stream));
+        src = tmp;
+    }
+    uint64_t * d = (uint64_t *) mps_arena_get(c, MPS_S_MISC, 256);
+    CUDA_OK(c, cudaMemsetAsync(d, 0, 2 * sizeof(uint64_t), c->stream));
+    KERN_OK(c, mpsk_multiset_hash(src, n, elsize, d, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    out2[0] = h[0]; out2[1] = h[1];
+}
+
 uint64_t mpsort_util_check_sorted(mpsort_comm_t c, const void * base, size_t n, size_t elsize,
         const struct mpsort_radix_desc * desc, int check_ties, size_t tie_offset, uint64_t * firstlast)
 {

@@ -126,6 +126,8 @@ _proto("mpsort_util_host_free_pinned", None, c_void_p)
 _proto("mpsort_util_memcpy", None, c_int, c_void_p, c_void_p, c_size_t)
 _proto("mpsort_util_dev_memset", None, c_int, c_void_p, c_int, c_size_t)
 _proto("mpsort_util_generate", None, c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_u64)
+_proto("mpsort_util_generate_as", None, c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_u64, c_u64, c_u64)
+_proto("mpsort_util_multiset_hash", None, c_void_p, c_void_p, c_size_t, c_size_t, ctypes.POINTER(c_u64))
 _proto("mpsort_util_check_sorted", c_u64, c_void_p, c_void_p, c_size_t, c_size_t,
        ctypes.POINTER(RadixDesc), c_int, c_size_t, ctypes.POINTER(c_u64))
 _proto("mpsort_util_checksum", c_u64, c_void_p, c_void_p, c_size_t)
@@ -159,6 +161,13 @@ def last_stats(comm_handle, size):
     return d
 
 byref = ctypes.byref
+
+
+def multiset_hash(comm_handle, base, n, elsize):
+    """(sum, xor) over the records of mix64-folded record words: mpsort_util_multiset_hash"""
+    out = (c_u64 * 2)()
+    lib.mpsort_util_multiset_hash(comm_handle, base, n, elsize, out)
+    return int(out[0]), int(out[1])
 
 
 def kernel_times(comm_handle):

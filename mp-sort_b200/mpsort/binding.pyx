@@ -165,7 +165,11 @@ def sort(data, orderby=None, out=None, comm=None, tuning=[]):
 
     # process-global, like the reference (binding.pyx:193-204); rank-threads of one
     # process all write the same bits
-    mpsort_mpi_unset_options(-1)
+    # only the four tuning bits are reset per call: bits outside the reference's set (the
+    # MPSORT_VERIFY_CHECKSUM extension, also set from the environment, which is parsed once)
+    # stay as the caller or the environment left them
+    mpsort_mpi_unset_options(MPSORT_DISABLE_SPARSE_ALLTOALLV | MPSORT_DISABLE_GATHER_SORT
+                             | MPSORT_REQUIRE_GATHER_SORT | MPSORT_REQUIRE_SPARSE_ALLTOALLV)
     if 'DISABLE_SPARSE_ALLTOALLV' in tuning:
         mpsort_mpi_set_options(MPSORT_DISABLE_SPARSE_ALLTOALLV)
     if 'DISABLE_GATHER_SORT' in tuning:

@@ -129,6 +129,34 @@ def checksum(rec):
     return int(lib().oracle_checksum(rec.ctypes.data, rec.nbytes))
 
 
+def _mix64(x):
+    """splitmix64 finaliser on uint64 arrays (wrapping arithmetic), oracle/synth.h:mix64"""
+    with np.errstate(over="ignore"):
+        z = x + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def multiset_hash(rec):
+    """(sum, xor) over the records of h(record): the order-independent whole-record hash the
+    property checks use (mpsort_util_multiset_hash). h folds the record's 8-byte little-endian
+    words (the last one zero-padded) through mix64 from a fixed seed."""
+    rec = np.ascontiguousarray(rec)
+    n, elsize = rec.shape
+    nw = (elsize + 7) // 8
+    padded = np.zeros((n, nw * 8), np.uint8)
+    padded[:, :elsize] = rec
+    words = padded.view("<u8")
+    h = np.full(n, 0x243F6A8885A308D3, dtype=np.uint64)
+    for k in range(nw):
+        h = _mix64(h ^ words[:, k])
+    with np.errstate(over="ignore"):
+        s = int(np.add.reduce(h, dtype=np.uint64)) if n else 0
+    x = int(np.bitwise_xor.reduce(h)) if n else 0
+    return s, x
+
+
 def c_radix_sort(rec, desc):
     out = np.ascontiguousarray(rec).copy()
     lib().oracle_radix_sort(out.ctypes.data, len(out), out.shape[1], ctypes.byref(desc))
@@ -189,16 +217,27 @@ def ref_sort(recs, desc, outsizes=None, options=0, inplace=False, timeout=300):
         shutil.rmtree(d, ignore_errors=True)
 
 
-def run_bench16(np_ranks, n_per_rank, elsize=16, kind=0, reps=1, timeout=900):
+def run_bench16(np_ranks, n_per_rank, elsize=16, kind=0, reps=1, timeout=900, warmups=0, budget_s=0.0, outdir=None, total=0):
     """The reference's CPU run of the benchmark workload (bench-mpi's sibling for struct
-    records). Returns dict(best_seconds, records_per_second, phases, np)."""
+    records). Returns dict(best_seconds, mean_seconds, records_per_second, phases, np, ...).
+    warmups: repetitions left out of mean_seconds; budget_s: stop repeating after that many
+    seconds of sorting; outdir: every rank writes its sorted output there as out.<rank>;
+    total > 0: the ranks share `total` records as evenly as possible (n_per_rank is ignored)."""
     cmd = [os.path.join(REF_DIR, "mpirun-shim"), "-np", str(np_ranks), os.path.join(REF_DIR, "bench16"),
-           "-k", str(kind), "-e", str(elsize), "-r", str(reps), str(n_per_rank)]
+           "-k", str(kind), "-e", str(elsize), "-r", str(reps), "-w", str(warmups), "-t", "%g" % budget_s]
+    if outdir:
+        cmd += ["-o", outdir]
+    if total:
+        cmd += ["-T", str(int(total))]
+    cmd.append(str(n_per_rank))
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout)
     if proc.returncode != 0:
         raise RuntimeError("bench16 failed (%d): %s" % (proc.returncode, proc.stderr.decode()[-2000:]))
-    res = {"np": np_ranks, "phases": {}}
+    res = {"np": np_ranks, "phases": {}, "totals": []}
     for line in proc.stdout.decode().splitlines():
+        if line.startswith("MPSort total time:"):
+            res["totals"].append(float(line.split(":", 1)[1]))
+            continue
         if line.startswith("BENCH16"):
             for tok in line.split()[1:]:
                 k, v = tok.split("=")

@@ -79,6 +79,7 @@ int K(mpsk_merge_runs)(const void *, void *, size_t, size_t, uint32_t, uint32_t,
 int K(mpsk_p2p_alltoallv)(const void * const *, void * const *, const uint64_t *, const unsigned char *, int, mpsk_stream_t);
 int K(mpsk_p2p_gather_alltoallv)(const void *, const uint32_t * const *, void * const *, const uint64_t *, size_t, int, mpsk_stream_t);
 int K(mpsk_checksum)(const void *, size_t, uint64_t *, mpsk_stream_t);
+int K(mpsk_multiset_hash)(const void *, size_t, size_t, uint64_t *, mpsk_stream_t);
 int K(mpsk_generate)(void *, size_t, size_t, int, uint64_t, uint64_t, uint64_t, mpsk_stream_t);
 int K(mpsk_check_sorted)(const void *, size_t, size_t, size_t, uint32_t, uint32_t, int, int, size_t, uint64_t *, uint64_t *, mpsk_stream_t);
 }
@@ -523,6 +524,9 @@ int mpsk_p2p_gather_alltoallv(const void * base, const uint32_t * const * idx, v
 
 int mpsk_checksum(const void * base, size_t nbytes, uint64_t * sum, mpsk_stream_t stream)
 { LAUNCH(stream, K(mpsk_checksum)(base, nbytes, sum, stream)); }
+
+int mpsk_multiset_hash(const void * base, size_t n, size_t elsize, uint64_t * out, mpsk_stream_t stream)
+{ LAUNCH(stream, K(mpsk_multiset_hash)(base, n, elsize, out, stream)); }
 
 int mpsk_generate(void * dst, size_t n, size_t elsize, int kind, uint64_t seed, uint64_t rank, uint64_t nranks, mpsk_stream_t stream)
 { LAUNCH(stream, K(mpsk_generate)(dst, n, elsize, kind, seed, rank, nranks, stream)); }

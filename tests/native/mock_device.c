@@ -848,6 +848,34 @@ int mpsk_checksum(const void * base, size_t nbytes, uint64_t * sum, mpsk_stream_
     return 0;
 }
 
+static uint64_t mock_mix64(uint64_t x)
+{
+    uint64_t z = x + 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+int mpsk_multiset_hash(const void * base, size_t n, size_t elsize, uint64_t * out, mpsk_stream_t stream)
+{
+    size_t i, b, k;
+    (void) stream;
+    if (n == 0 || elsize == 0) return 0;
+    LAUNCHED();
+    for (i = 0; i < n; i++) {
+        const unsigned char * r = (const unsigned char *) base + i * elsize;
+        uint64_t h = 0x243F6A8885A308D3ULL;
+        for (b = 0; b < elsize; b += 8) {
+            uint64_t w = 0;
+            for (k = 0; k < 8 && b + k < elsize; k++) w |= (uint64_t) r[b + k] << (8 * k);
+            h = mock_mix64(h ^ w);
+        }
+        out[0] += h;
+        out[1] ^= h;
+    }
+    return 0;
+}
+
 int mpsk_generate(void * dst, size_t n, size_t elsize, int kind, uint64_t seed, uint64_t rank, uint64_t nranks, mpsk_stream_t stream)
 {
     size_t i;

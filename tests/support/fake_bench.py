@@ -3,7 +3,7 @@ library is replaced by a stand-in that returns plausible numbers, so that the co
 JSON line of bench.py are exercised on a CPU-only box. Prints the JSON line. `--pinfail` makes the
 pinned allocation fail (pageable fallback of the e2e leg)."""
 import sys, types, ctypes, json, io, contextlib
-sys.argv = ["bench.py", "--log2n", "10", "--steps", "2", "--warmup", "1", "--no-cpu-baseline"] + sys.argv[1:]
+sys.argv = ["bench.py", "--log2n", "10", "--steps", "2", "--warmup", "1", "--no-cpu-baseline", "--no-preflight"] + sys.argv[1:]
 PIN_FAIL = "--pinfail" in sys.argv
 if PIN_FAIL: sys.argv.remove("--pinfail")
 SIZE = 1
@@ -36,7 +36,8 @@ class RadixDesc(ctypes.Structure):
 capi.RadixDesc = RadixDesc
 capi.kernel_times = lambda h: {"extract_hist": (1.4, 8), "onesweep_pass_rec16": (16.0, 8), "hybrid_fixup": (2.4, 18), "merge_runs": (10.0, 48), "exchange": (11.0, 4)}
 capi.last_run = lambda: [("FirstSort", 0.010), ("Exchange", 0.005)]
-capi.last_stats = lambda h, s: {"first_sort_passes": 4, "second_sort_passes": 0, "record_mode": 1, "second_sort_merge_tiles": 10, "bytes_sent_remote": 1000, "p2p_exchange": 1, "exchange_phases": 2}
+capi.last_stats = lambda h, s: {"first_sort_passes": 4, "second_sort_passes": 0, "record_mode": 1, "second_sort_merge_tiles": 10, "bytes_sent_remote": 1000, "p2p_exchange": 1, "exchange_phases": 2, "hybrid": 1, "rebased": 0, "splitter_rounds": 8}
+capi.multiset_hash = lambda h, base, n, E: (777, 888)
 mp = types.ModuleType("mpsort")
 class Comm:
     rank, size, device, handle = 0, SIZE, 0, 1

@@ -54,6 +54,23 @@ def test_reference_arm_line():
     c = d["cpu_baseline"]
     assert c["kind"] == "reference" and c["cores"] >= 1 and c["value"] == d["value"] and "sample" in c
     assert d["config"]["workload"].startswith("uniform16: 2^28")
+    assert d["same_workload_as_gpu_arm"] is False and d["config"]["records_per_step"] == 32768
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
+def test_reference_arm_sorts_the_gpu_arms_workload_at_one_gpu():
+    """--gpus 1 without --ref-records: every sort is the GPU arm's full workload (here 2^16 records), the value is the
+    MEAN over the timed sorts and `config` is the GPU arm's `config`, key for key"""
+    d = run([os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "2", "--log2n", "16"])
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert d["config"] == b.make_config("uniform16", 16, 1)
+    assert d["same_workload_as_gpu_arm"] is True and d["sorts_timed"] == 4 and len(d["seconds_per_sort"]) == 5
+    mean = sum(d["seconds_per_sort"][1:]) / 4
+    assert abs(d["ms_per_step"] - mean * 1e3) < 1e-3 * d["ms_per_step"] + 1e-3
+    assert abs(d["value"] - (1 << 16) / mean) < 2e-3 * d["value"]
 
 
 def test_reference_arm_on_other_ranks_is_silent():
@@ -70,5 +87,8 @@ def test_gpu_arm_line_at_eight_ranks():
     per_gpu = d["config"]["records_per_gpu"]
     assert abs(d["value"] - 8 * per_gpu / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 8 * per_gpu * d["config"]["elsize"]
-    assert "NVLink" in d["config"]["transport"] and d["config"]["baseline_config"].startswith("configs[2]")
+    assert "NVLink" in d["transport"] and d["config"]["baseline_config"].startswith("configs[2]")
+    assert set(d["workloads"]) == {"mostly_sorted16", "particles48"}
+    for w in d["workloads"].values():
+        assert w["value"] > 0 and "kernels" in w and "exchange" in w and "config" in w
     assert d["exchange"]["gb_per_s_per_gpu"] > 0

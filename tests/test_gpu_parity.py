@@ -5,7 +5,9 @@ of rank threads sharing cuda:0, the way the reference's `mpirun -n 4/12` cases a
 run on one machine; NCCL process-per-GPU cases need >= 2 GPUs.
 
 Full-size cases (BASELINE.json: 2^28 16-byte records) are checked through
-size-independent properties: sortedness, tie order by tag, checksum of bytes."""
+size-independent properties -- sortedness, tie order by tag, an order-independent multiset
+hash of whole records -- and, for config B, byte for byte against the unmodified reference
+run on the host cores (oracle/_ref)."""
 import ctypes
 import os
 import subprocess
@@ -435,21 +437,60 @@ def test_verify_checksum_option():
 
 
 # ------------------------------------------------------------------ full size, by properties
+def test_multiset_hash_matches_oracle_and_sees_what_a_byte_sum_cannot():
+    """the whole-record multiset hash of the property checks: equal to the numpy restatement,
+    invariant under any reordering of records, and changed by a swap of two payloads between
+    keys or of two bytes inside a record -- both of which keep the reference's signed-byte
+    sum (mpsort-mpi.c:148-159)"""
+    comm = mpsort.Comm.self(0)
+    rng = np.random.default_rng(3)
+    for E in (16, 48, 8, 24, 7, 19):
+        a = rng.integers(0, 256, size=(50001, E), dtype=np.uint8)
+        h = C.multiset_hash(comm.handle, a.ctypes.data, len(a), E)
+        assert h == O.multiset_hash(a)
+        b = a[rng.permutation(len(a))].copy()
+        assert C.multiset_hash(comm.handle, b.ctypes.data, len(b), E) == h
+        c = a.copy()
+        if E >= 16:
+            c[[10, 20], 8:] = c[[20, 10], 8:]                   # payloads swapped between two keys
+        else:
+            c[10, [0, E - 1]] = c[10, [E - 1, 0]]                # two bytes swapped inside a record
+        if not np.array_equal(c, a):
+            assert O.checksum(c) == O.checksum(a)
+            assert C.multiset_hash(comm.handle, c.ctypes.data, len(c), E) != h
+    # device pointers, unaligned base
+    buf = lib.mpsort_util_dev_malloc(0, 16 * 1000 + 8)
+    a = rng.integers(0, 256, size=(1000, 16), dtype=np.uint8)
+    lib.mpsort_util_memcpy(0, ctypes.c_void_p(buf + 8), a.ctypes.data, a.nbytes)
+    assert C.multiset_hash(comm.handle, ctypes.c_void_p(buf + 8), 1000, 16) == O.multiset_hash(a)
+    lib.mpsort_util_dev_free(0, buf)
+    comm.destroy()
+
+
 def _property_check(comm, n, E, kind, desc, seed):
     buf = lib.mpsort_util_dev_malloc(0, n * E)
     lib.mpsort_util_generate(comm.handle, buf, n, E, kind, seed)
-    s1 = lib.mpsort_util_checksum(comm.handle, buf, n * E)
+    s1 = C.multiset_hash(comm.handle, buf, n, E)
     lib.mpsort_mpi_desc_impl(buf, n, E, ctypes.byref(desc), comm.handle, 0, b"fullsize")
-    s2 = lib.mpsort_util_checksum(comm.handle, buf, n * E)
+    s2 = C.multiset_hash(comm.handle, buf, n, E)
     fl = (ctypes.c_uint64 * 2)()
     bad = lib.mpsort_util_check_sorted(comm.handle, buf, n, E, ctypes.byref(desc), 1, 8, fl)
     # idempotence: sorting the sorted array changes nothing (stable)
     lib.mpsort_mpi_desc_impl(buf, n, E, ctypes.byref(desc), comm.handle, 0, b"fullsize")
-    s3 = lib.mpsort_util_checksum(comm.handle, buf, n * E)
+    s3 = C.multiset_hash(comm.handle, buf, n, E)
     bad2 = lib.mpsort_util_check_sorted(comm.handle, buf, n, E, ctypes.byref(desc), 1, 8, fl)
     lib.mpsort_util_dev_free(0, buf)
-    assert s1 == s2 == s3, "bytes changed"
+    assert s1 == s2 == s3, "the multiset of records changed"
     assert bad == 0 and bad2 == 0, "order or tie order violated"
+
+
+def _combine(hashes):
+    """multiset hashes of the ranks' parts -> hash of their union: sums add, xors xor"""
+    s = x = 0
+    for a, b in hashes:
+        s = (s + a) & ((1 << 64) - 1)
+        x ^= b
+    return s, x
 
 
 def test_full_size_config_b_by_properties():
@@ -457,6 +498,36 @@ def test_full_size_config_b_by_properties():
     comm = mpsort.Comm.self(0)
     _property_check(comm, 1 << 28, 16, 0, C.RadixDesc(0, 8, 1, 0, 0), 0x5EED0001)
     comm.destroy()
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref (the compiled reference) is not in this tree")
+def test_full_size_config_b_bytes_equal_the_reference(tmp_path):
+    """BASELINE.json configs[1] at FULL size, byte for byte: the unmodified reference
+    (oracle/_ref/bench16 -> mpsort_mpi_newarray, one MPI-shim rank per host core) and one B200
+    sort the same 2^28 16-byte records. The reference's R ranks generate R chunks; the GPU holds
+    their rank-order concatenation, whose stable sort is the reference's output contract."""
+    log2n, E = 28, 16
+    cores = os.cpu_count() or 1
+    R = 1
+    while R * 2 <= min(cores, 32):
+        R *= 2
+    n, per = 1 << log2n, (1 << log2n) // R
+    comm = mpsort.Comm.self(0)
+    buf = lib.mpsort_util_dev_malloc(0, n * E)
+    for r in range(R):
+        lib.mpsort_util_generate_as(comm.handle, ctypes.c_void_p(buf + r * per * E), per, E, 0, 0x5EED0001, r, R)
+    lib.mpsort_mpi_desc_impl(buf, n, E, ctypes.byref(C.RadixDesc(0, 8, 1, 0, 0)), comm.handle, 0, b"fullsize_ref")
+    assert C.last_stats(comm.handle, 1)["hybrid"] == 1
+    res = O.run_bench16(R, per, elsize=E, kind=0, reps=1, timeout=1500, outdir=str(tmp_path))
+    got = np.empty((per, E), np.uint8)
+    for r in range(R):
+        lib.mpsort_util_memcpy(0, got.ctypes.data, ctypes.c_void_p(buf + r * per * E), per * E)
+        exp = np.fromfile(str(tmp_path / ("out.%d" % r)), dtype=np.uint8).reshape(per, E)
+        assert np.array_equal(got, exp), "chunk %d of %d differs from the reference's output" % (r, R)
+        os.unlink(str(tmp_path / ("out.%d" % r)))
+    lib.mpsort_util_dev_free(0, buf)
+    comm.destroy()
+    print("reference: %d ranks, %.1f s per sort" % (R, res["best_seconds"]))
 
 
 def test_large_particles48_and_mostly_sorted_by_properties():
@@ -481,10 +552,10 @@ def test_large_multirank_hybrid_records_by_properties(phases, monkeypatch):
         buf = lib.mpsort_util_dev_malloc(0, n * E)
         out = lib.mpsort_util_dev_malloc(0, n * E)
         lib.mpsort_util_generate(comm.handle, buf, n, E, 0, 0x5EED0001)
-        s1 = lib.mpsort_util_checksum(comm.handle, buf, n * E)
+        s1 = C.multiset_hash(comm.handle, buf, n, E)
         lib.mpsort_mpi_newarray_desc_impl(buf, n, out, n, E, ctypes.byref(desc), comm.handle, 0, b"multirank16")
         st = C.last_stats(comm.handle, p)
-        s2 = lib.mpsort_util_checksum(comm.handle, out, n * E)
+        s2 = C.multiset_hash(comm.handle, out, n, E)
         fl = (ctypes.c_uint64 * 2)()
         bad = lib.mpsort_util_check_sorted(comm.handle, out, n, E, ctypes.byref(desc), 1, 8, fl)
         lib.mpsort_util_dev_free(0, buf)
@@ -492,8 +563,7 @@ def test_large_multirank_hybrid_records_by_properties(phases, monkeypatch):
         res[r] = (s1, s2, bad, fl[0], fl[1], st)
 
     mpsort.run_local(p, work)
-    mask = (1 << 64) - 1
-    assert sum(x[0] for x in res) & mask == sum(x[1] for x in res) & mask
+    assert _combine([x[0] for x in res]) == _combine([x[1] for x in res]), "the multiset of records changed"
     assert all(x[2] == 0 for x in res)
     assert all(res[r - 1][4] <= res[r][3] for r in range(1, p))
     assert all(x[5]["record_mode"] == 1 and x[5]["hybrid"] == 1 and x[5]["second_sort_merge_tiles"] > 0 for x in res)
@@ -511,9 +581,9 @@ def test_large_multirank_by_properties():
         r = comm.rank
         buf = lib.mpsort_util_dev_malloc(0, n * E)
         lib.mpsort_util_generate(comm.handle, buf, n, E, 2, 0x5EED0001)
-        s1 = lib.mpsort_util_checksum(comm.handle, buf, n * E)
+        s1 = C.multiset_hash(comm.handle, buf, n, E)
         lib.mpsort_mpi_desc_impl(buf, n, E, ctypes.byref(desc), comm.handle, 0, b"multirank")
-        s2 = lib.mpsort_util_checksum(comm.handle, buf, n * E)
+        s2 = C.multiset_hash(comm.handle, buf, n, E)
         fl = (ctypes.c_uint64 * 2)()
         bad = lib.mpsort_util_check_sorted(comm.handle, buf, n, E, ctypes.byref(desc), 1, 8, fl)
         first = np.zeros((1, E), np.uint8)
@@ -525,8 +595,7 @@ def test_large_multirank_by_properties():
         return None
 
     mpsort.run_local(p, work)
-    mask = (1 << 64) - 1
-    assert sum(x[0] for x in res) & mask == sum(x[1] for x in res) & mask
+    assert _combine([x[0] for x in res]) == _combine([x[1] for x in res]), "the multiset of records changed"
     assert all(x[2] == 0 for x in res)
     for r in range(1, p):
         a = res[r - 1][4].view("<i8").reshape(-1)

@@ -44,6 +44,7 @@ def test_mock_provides_every_symbol_the_host_code_uses(mock_env):
 
 # the two full-size property tests take minutes as CPU loops; their host flow is the same as the 2^22 cases below
 BIG = ["tests/test_gpu_parity.py::test_full_size_config_b_by_properties",
+       "tests/test_gpu_parity.py::test_full_size_config_b_bytes_equal_the_reference",
        "tests/test_gpu_parity.py::test_large_particles48_and_mostly_sorted_by_properties"]
 
 
@@ -94,7 +95,8 @@ def test_exchange_in_parts_at_2_22_records_per_rank(mock_env, E, kind, extra):
 def test_bench_gpu_arm_runs_end_to_end_on_the_mock(mock_env):
     """bench.py itself (not a stand-in for it): device-resident leg, e2e leg through mpsort.sort, verification,
     roofline bookkeeping, one JSON line. Numbers are meaningless here; the control flow is what is checked."""
-    rc = subprocess.run([sys.executable, "bench.py", "--log2n", "16", "--steps", "2", "--warmup", "1", "--no-cpu-baseline"],
+    rc = subprocess.run([sys.executable, "bench.py", "--log2n", "16", "--steps", "2", "--warmup", "1", "--no-cpu-baseline",
+                         "--preflight-log2n", "15", "--extra-steps", "1"],
                         cwd=ROOT, env=mock_env, timeout=600, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert rc.returncode == 0, rc.stderr.decode()[-3000:]
     lines = [l for l in rc.stdout.decode().splitlines() if l.startswith("{")]
@@ -102,6 +104,12 @@ def test_bench_gpu_arm_runs_end_to_end_on_the_mock(mock_env):
     d = json.loads(lines[0])
     assert d["n_gpus"] == 1 and d["steps"] == 2 and d["value"] > 0 and d["e2e"]["value"] > 0 and d["gpu_launches"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == (1 << 16) * 16 and d["roofline"]["bound"] == "hbm"
+    # the pre-flight ran all three workloads bit-exactly against the oracle; the other two workloads were timed and verified
+    pf = d["parity_preflight"]
+    assert pf["ok"] and [c["workload"] for c in pf["cases"]] == ["uniform16", "mostly_sorted16", "particles48"]
+    assert all(c["device_resident_equals_oracle"] and c["host_api_equals_oracle"] and c["generator_equals_oracle"] for c in pf["cases"])
+    assert set(d["workloads"]) == {"mostly_sorted16", "particles48"} and all(w["value"] > 0 for w in d["workloads"].values())
+    assert d["workloads"]["particles48"]["local_sort"]["record_mode"] is False
 
 
 # ---- the NCCL transport (mpsort_comm_init_rank), one rank per thread of the worker ------------------

@@ -344,3 +344,27 @@ def test_device_arrays(comm):
     R = numpy.concatenate(comm.allgather(dev.to_host()))
     dev.free()
     assert_array_equal(R, S)
+
+
+def test_verify_checksum_survives_the_python_call():
+    """MPSORT_VERIFY_CHECKSUM (mpsort.h; the reference checksums every call, mpsort-mpi.c:193,324) is not
+    one of the four tuning bits the binding resets on every call: set once, it stays in force through
+    mpsort.sort -- two checksum launches per sort, the bit still set afterwards."""
+    from mpsort import _capi as C
+    comm = mpsort.Comm.self(0)
+    s = numpy.int64(numpy.random.default_rng(1).integers(-99999, 99999, size=20000))
+    C.lib.mpsort_mpi_set_options(C.MPSORT_VERIFY_CHECKSUM)
+    try:
+        C.lib.mpsort_util_kernel_timing(comm.handle, 1)
+        r = s.copy()
+        mpsort.sort(r, orderby=None, comm=comm, tuning=['DISABLE_GATHER_SORT'])
+        mpsort.sort(r, orderby=None, comm=comm)
+        kt = C.kernel_times(comm.handle)
+        assert C.lib.mpsort_mpi_has_options(C.MPSORT_VERIFY_CHECKSUM)
+        assert kt["checksum"][1] == 4
+        assert not C.lib.mpsort_mpi_has_options(C.MPSORT_DISABLE_GATHER_SORT)     # the tuning bits are per call
+        assert_array_equal(r, numpy.sort(s))
+    finally:
+        C.lib.mpsort_util_kernel_timing(comm.handle, 0)
+        C.lib.mpsort_mpi_unset_options(C.MPSORT_VERIFY_CHECKSUM)
+        comm.destroy()
