@@ -229,7 +229,6 @@ struct mpsort_last_stats {
     uint32_t rebased;            /* 1: keys were sorted relative to their minimum (fewer passes) */
     uint32_t p2p_exchange;       /* 1: records moved by peer stores (CUDA IPC), 0: ncclSend/ncclRecv or copies */
     uint32_t exchange_phases;    /* parts the exchange + merge were pipelined in (1 = not pipelined) */
-    uint32_t merge_bucket_fallback_tiles; /* MPSORT_MERGE_BUCKET=1 (candidate): merge tiles that took the merge-path rounds */
 };
 void mpsort_comm_last_stats(mpsort_comm_t comm, struct mpsort_last_stats * st,
                             int64_t * sendcounts, int max);

@@ -81,6 +81,14 @@ void   mpsort_util_kernel_timing(mpsort_comm_t comm, int on);
 int    mpsort_util_kernel_times(mpsort_comm_t comm, const char ** names, double * ms,
                                 uint64_t * launches, int max);
 
+/* The SecondSort merge alone (replaces the second radix_sort, mpsort-mpi.c:597): `runs` holds p
+ * sorted runs, run r = records [rdispl[r], rdispl[r+1]) with rdispl[0] == 0, all in device memory;
+ * their stable p-way merge (ties: lower run first) goes to `out`. One GPU can thus time and
+ * profile the merge of the 8-GPU configuration at full size. Blocking. Returns 0 if the merge ran,
+ * 1 if these runs would take the radix re-sort fallback (multi-word keys, p > 32, tiny inputs). */
+int    mpsort_util_merge_runs(mpsort_comm_t comm, int p, const void * runs, const int64_t * rdispl,
+                              void * out, size_t elsize, const struct mpsort_radix_desc * desc);
+
 /* free/total device memory in bytes */
 void   mpsort_util_mem_info(int device, size_t * free_bytes, size_t * total_bytes);
 

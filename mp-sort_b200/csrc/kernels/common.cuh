@@ -2,7 +2,6 @@
  * Part of the single translation unit mpsort_kernels.cu (included there, first). */
 
 #include "mpsort_kernels.h"
-#include "mpsort_merge_bucket.cuh"
 
 typedef unsigned long long u64;
 typedef unsigned int u32;

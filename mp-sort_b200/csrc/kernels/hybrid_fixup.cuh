@@ -26,20 +26,87 @@ __device__ __forceinline__ u64 rec_key(const uint4 & it, u32 khi, u64 flip)
     return (khi ? (((u64) it.w << 32) | it.z) : (((u64) it.y << 32) | it.x)) ^ flip;
 }
 
+#ifndef FIX_MINBLOCKS
+#define FIX_MINBLOCKS 8
+#endif
+
+/* what one entry of the compacted list (a position that is not a run of its own) has to do:
+ * returns the position its record moves to (0xffffffff: it stays) and reads the record */
+template <typename ITEM>
+__device__ __forceinline__ u32 fixup_entry(const ITEM * __restrict__ recs, size_t t0, u32 i, u32 cnt,
+        const u64 * s_key, const u32 * s_head, int nwords, u64 lomask, u32 lobits,
+        u32 * __restrict__ worklist, u32 * __restrict__ nwork, u32 cap, ITEM & moved)
+{
+    (void) lobits;
+    /* run start: last head at or before i */
+    int w = (int) (i >> 5);
+    u32 bits = s_head[w] & (0xffffffffu >> (31 - (i & 31)));
+    while (bits == 0 && w > 0) { w--; bits = s_head[w]; }
+    if (bits == 0) return 0xffffffffu;                    /* continuation of a run owned by an earlier tile */
+    const u32 rs = (u32) w * 32 + (31 - __clz(bits));
+    if (rs >= (u32) FIX_T) return 0xffffffffu;            /* head lies in the look-ahead: the next tile owns it */
+    /* run end: first head after i (the sentinel counts) */
+    u32 w2 = (i + 1) >> 5;
+    u32 b2 = s_head[w2] & (0xffffffffu << ((i + 1) & 31));
+    while (b2 == 0 && w2 + 1 < (u32) nwords && (w2 + 1) * 32 <= cnt + 31) { w2++; b2 = s_head[w2]; }
+    const u32 re = b2 ? (w2 * 32 + (__ffs(b2) - 1)) : 0xffffffffu;
+    if (re == 0xffffffffu || re > cnt || re - rs > (u32) FIX_HALO) {
+        /* too long for this kernel: the run head reports it */
+        if (i == rs) {
+            const u32 slot = atomicAdd(nwork, 1u);
+            if (slot < cap) worklist[slot] = (u32) (t0 + rs);
+        }
+        return 0xffffffffu;
+    }
+    if (re - rs < 2) return 0xffffffffu;
+    const u64 mine = s_key[i + 1] & lomask;
+    u32 rank = 0;
+    for (u32 j = rs; j < re; j++) {
+        const u64 other = s_key[j + 1] & lomask;
+        rank += (other < mine) || (other == mine && j < i);
+    }
+    if (rs + rank == i) return 0xffffffffu;
+    moved = recs[t0 + i];
+    return rs + rank;
+}
+
+/* bit b set: position 32 w + b of the tile is inside the data and NOT a run of its own */
+__device__ __forceinline__ u32 fixup_votes(const u32 * s_head, u32 cnt, u32 w)
+{
+    const u32 H = s_head[w], Hn = s_head[w + 1];
+    const u32 single = H & ((H >> 1) | (Hn << 31));
+    const u32 first = w * 32;
+    const u32 inside = first >= cnt ? 0u : (cnt - first >= 32 ? 0xffffffffu : ((1u << (cnt - first)) - 1u));
+    return ~single & inside;
+}
+
 template <typename ITEM, bool KHI>
-__global__ void __launch_bounds__(FIX_THREADS)
+__global__ void __launch_bounds__(FIX_THREADS, FIX_MINBLOCKS)
 fixup_rec_kernel(ITEM * __restrict__ recs, u32 n, u64 flip, u32 lobits,
                    u32 * __restrict__ worklist, u32 * __restrict__ nwork, u32 cap)
 {
     constexpr int CAP = FIX_T + FIX_HALO;
-    constexpr int WORDS = (CAP + 31) / 32 + 1;
+    constexpr int NW = CAP / 32;                  /* head words that describe positions of this tile */
+    constexpr int WORDS = NW + 1;
     constexpr int NLD = CAP / FIX_THREADS;
     static_assert(CAP % FIX_THREADS == 0, "tile + halo must be a multiple of the block size");
-    /* only the keys are staged: the few records that move are re-read from global */
+    static_assert(NW == NLD * (FIX_THREADS / 32), "one warp row per head word");
+    static_assert(NW <= 96, "the list offsets are scanned by one warp, three words per lane");
+    static_assert(FIX_HALO <= FIX_THREADS, "a run must not span more than two rounds of the move phase");
+    static_assert(CAP < 65536, "list entries are 16-bit positions");
+    /* Only the keys are staged: the few records that move are re-read from global. 23 KB of shared
+     * memory and <= 32 registers: eight CTAs per SM keep enough key loads in flight for what is, for
+     * random keys, ONE read of the array (6 % of the records move). The first version held a moved
+     * record per load round in registers (64 of them, four CTAs per SM) and ran at 54 % of the HBM rate
+     * of a plain read (1.22 ms per 2^28 records, profiles/r02_call1_tests_candidates_bench_n1.log). */
     __shared__ u64 s_key[CAP + 1];            /* [0] = key of the record before the tile */
     __shared__ u32 s_head[WORDS];
+    __shared__ u32 s_off[96];                 /* per head word: positions on the list before it */
+    __shared__ unsigned short s_list[CAP];
+    __shared__ u32 s_nlist;
 
     const u32 tid = threadIdx.x;
+    const u32 lane = tid & 31u;
     const size_t t0 = (size_t) blockIdx.x * FIX_T;
     const u32 avail = (u32) ((size_t) n - t0);
     const u32 cnt = avail < (u32) CAP ? avail : (u32) CAP;
@@ -55,12 +122,12 @@ fixup_rec_kernel(ITEM * __restrict__ recs, u32 n, u64 flip, u32 lobits,
             const u32 i = tid + k * FIX_THREADS;
             if (i < cnt) tmp[k] = keys[W * (t0 + i)];
         }
+        if (tid == 0) s_key[0] = t0 ? (keys[W * (t0 - 1)] ^ flip) : 0ULL;
 #pragma unroll
         for (int k = 0; k < NLD; k++) {
             const u32 i = tid + k * FIX_THREADS;
             if (i < cnt) s_key[i + 1] = tmp[k] ^ flip;
         }
-        if (tid == 0) s_key[0] = t0 ? (keys[W * (t0 - 1)] ^ flip) : 0ULL;
     }
     __syncthreads();
     /* head flags: the high part differs from the predecessor's. A warp handles 32
@@ -73,80 +140,61 @@ fixup_rec_kernel(ITEM * __restrict__ recs, u32 n, u64 flip, u32 lobits,
             if (i == cnt) head = at_end;                      /* sentinel: the data ends here */
             else if (i < cnt) head = ((s_key[i] >> lobits) != (s_key[i + 1] >> lobits)) || (i == 0 && t0 == 0);
             const u32 word = __ballot_sync(FULL_MASK, head);
-            if ((tid & 31) == 0) s_head[i >> 5] = word;
+            if (lane == 0) s_head[i >> 5] = word;
         }
     }
     __syncthreads();
-    /* ---- compact the positions that are NOT a run of their own (6 % for random keys):
-     * the expensive part below then runs with full warps */
-    __shared__ u32 s_list[CAP];
-    __shared__ u32 s_nlist;
-    if (tid == 0) s_nlist = 0;
+    /* ---- the positions that are NOT a run of their own (6 % for random keys) are compacted into a list
+     * IN POSITION ORDER, so that the expensive part below runs with full warps. Position i is a run of its
+     * own when head bits i and i+1 are both set: a whole word of positions is decided by two loads and a
+     * few word operations. 1: count per word; 2: one warp scans the counts; 3: write the list. */
+    if (tid < 32) {
+        u32 c[3], t = 0;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const u32 w = 3 * tid + j;
+            c[j] = w < (u32) NW ? (u32) __popc(fixup_votes(s_head, cnt, w)) : 0u;
+            t += c[j];
+        }
+        u32 incl = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 y = __shfl_up_sync(FULL_MASK, incl, o);
+            if (lane >= (u32) o) incl += y;
+        }
+        u32 run = incl - t;
+#pragma unroll
+        for (int j = 0; j < 3; j++) { s_off[3 * tid + j] = run; run += c[j]; }
+        if (tid == 31) s_nlist = incl;
+    }
     __syncthreads();
-    /* a warp's 32 positions of round k are exactly the bits of head word (warp + 8k):
-     * position i is a run of its own when bits i and i+1 are both set, so the whole
-     * row is decided by two broadcast loads and a few word operations */
 #pragma unroll
     for (int k = 0; k < NLD; k++) {
         const u32 w = (tid >> 5) + k * (FIX_THREADS / 32);
-        const u32 H = s_head[w], Hn = s_head[w + 1];
-        const u32 single = H & ((H >> 1) | (Hn << 31));
-        const u32 first = w * 32;
-        const u32 inside = first >= cnt ? 0u : (cnt - first >= 32 ? 0xffffffffu : ((1u << (cnt - first)) - 1u));
-        const u32 votes = ~single & inside;
-        if (votes) {
-            u32 base = 0;
-            if ((tid & 31) == 0) base = atomicAdd(&s_nlist, (u32) __popc(votes));
-            base = __shfl_sync(FULL_MASK, base, 0);
-            if ((votes >> (tid & 31)) & 1u) s_list[base + __popc(votes & lanemask_lt())] = first + (tid & 31);
-        }
+        const u32 votes = fixup_votes(s_head, cnt, w);
+        if ((votes >> lane) & 1u) s_list[s_off[w] + __popc(votes & lanemask_lt())] = (unsigned short) (w * 32 + lane);
     }
     __syncthreads();
+    /* ---- the move phase, in rounds of FIX_THREADS list entries (one round for random keys). A run's
+     * positions are consecutive on the list and there are at most FIX_HALO <= FIX_THREADS of them, so a
+     * run spans at most two consecutive rounds: the records of round r+1 are read before the barrier that
+     * precedes the writes of round r, and whatever round r writes belongs to runs that rounds r-1, r and
+     * r+1 have read by then. Two moved records per thread instead of one per load round. */
     const u32 nlist = s_nlist;
-    ITEM moved[NLD];
-    u32 tgts[NLD];
-#pragma unroll
-    for (int k = 0; k < NLD; k++) {
-        tgts[k] = 0xffffffffu;
-        const u32 e = tid + k * FIX_THREADS;
-        if (e >= nlist) continue;
-        const u32 i = s_list[e];
-        /* run start: last head at or before i */
-        int w = (int) (i >> 5);
-        u32 bits = s_head[w] & (0xffffffffu >> (31 - (i & 31)));
-        while (bits == 0 && w > 0) { w--; bits = s_head[w]; }
-        if (bits == 0) continue;                          /* continuation of a run owned by an earlier tile */
-        const u32 rs = (u32) w * 32 + (31 - __clz(bits));
-        if (rs >= (u32) FIX_T) continue;                  /* head lies in the look-ahead: the next tile owns it */
-        /* run end: first head after i (the sentinel counts) */
-        u32 w2 = (i + 1) >> 5;
-        u32 b2 = s_head[w2] & (0xffffffffu << ((i + 1) & 31));
-        while (b2 == 0 && w2 + 1 < (u32) WORDS && (w2 + 1) * 32 <= cnt + 31) { w2++; b2 = s_head[w2]; }
-        const u32 re = b2 ? (w2 * 32 + (__ffs(b2) - 1)) : 0xffffffffu;
-        if (re == 0xffffffffu || re > cnt || re - rs > (u32) FIX_HALO) {
-            /* too long for this kernel: the run head reports it */
-            if (i == rs) {
-                const u32 slot = atomicAdd(nwork, 1u);
-                if (slot < cap) worklist[slot] = (u32) (t0 + rs);
-            }
-            continue;
-        }
-        if (re - rs < 2) continue;
-        const u64 mine = s_key[i + 1] & lomask;
-        u32 rank = 0;
-        for (u32 j = rs; j < re; j++) {
-            const u64 other = s_key[j + 1] & lomask;
-            rank += (other < mine) || (other == mine && j < i);
-        }
-        if (rs + rank != i) {
-            tgts[k] = rs + rank;
-            moved[k] = recs[t0 + i];                      /* read before anyone of this CTA writes */
-        }
+    ITEM mv_a, mv_b;
+    u32 tgt_a = 0xffffffffu;
+    if (tid < nlist)
+        tgt_a = fixup_entry<ITEM>(recs, t0, s_list[tid], cnt, s_key, s_head, WORDS, lomask, lobits, worklist, nwork, cap, mv_a);
+    for (u32 base = 0; base < nlist; base += FIX_THREADS) {
+        u32 tgt_b = 0xffffffffu;
+        const u32 e = base + FIX_THREADS + tid;
+        if (e < nlist)
+            tgt_b = fixup_entry<ITEM>(recs, t0, s_list[e], cnt, s_key, s_head, WORDS, lomask, lobits, worklist, nwork, cap, mv_b);
+        __syncthreads();
+        if (tgt_a != 0xffffffffu) recs[t0 + tgt_a] = mv_a;
+        tgt_a = tgt_b;
+        mv_a = mv_b;
     }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < NLD; k++)
-        if (tgts[k] != 0xffffffffu) recs[t0 + tgts[k]] = moved[k];
 }
 
 /* extent of every long run on the work list: first index whose high part differs */

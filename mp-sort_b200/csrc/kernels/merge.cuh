@@ -1,4 +1,4 @@
-/* kernels/merge.cuh -- K7: stable p-way merge of the received runs (samples, bounds, tile kernels; bucket candidate).
+/* kernels/merge.cuh -- K7: stable p-way merge of the received runs (samples, their merged order, bounds, tile kernels).
  * Part of the single translation unit mpsort_kernels.cu (included there, in order). */
 /* ========================================================================= */
 /* K7: stable p-way merge of the received runs (replaces the second radix_sort, */
@@ -8,8 +8,8 @@
  * The receive buffer holds p sorted runs (run r = records [rdispl[r], rdispl[r+1])).
  * 1. merge_sample_kernel: every S-th key of every run (the last key of each full
  *    block of S) -> samples in (run, position) order.
- * 2. the samples are sorted stably by key with the onesweep sort (host side), which
- *    orders them by (key, run, position).
+ * 2. merge_rank_samples_kernel puts the samples in (key, run, position) order: every sample
+ *    finds its rank by binary searches in the other runs' (sorted) sample lists.
  * 3. merge_bounds_kernel: every k-th merged sample is a tile boundary; its cut
  *    position in every run is found by binary search (upper bound in lower runs,
  *    lower bound in higher runs: ties go to the lower run first, like the stable
@@ -51,6 +51,40 @@ merge_sample_kernel(const unsigned char * __restrict__ recv, KeyDesc d, bool fas
         const u32 j = s - m.sstart[r];
         const size_t pos = (size_t) m.rdispl[r] + (size_t) (j + 1) * m.S - 1;
         skeys[s] = load_key_any(recv + pos * d.elsize, d, fast8);
+    }
+}
+
+/*
+ * 2. the merged order of the samples WITHOUT a sort: every run's samples are already sorted, so the
+ * position of sample (run r, index j, key k) among all samples, ties by (run, index), is
+ *      j + sum over r' < r of #{samples of r' with key <= k} + sum over r' > r of #{... with key < k},
+ * p - 1 binary searches in arrays that sit in L2 (ns = n / S keys). One launch instead of the
+ * eight-pass radix sort of the samples and its host round trip -- the fixed cost of every exchange part.
+ */
+__global__ void __launch_bounds__(256)
+merge_rank_samples_kernel(const u64 * __restrict__ skeys, MergeRuns m, u64 * __restrict__ sorted_skeys,
+                          u32 * __restrict__ sorted_sid)
+{
+    const u32 ns = m.sstart[m.p];
+    for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < ns; s += gridDim.x * blockDim.x) {
+        u32 r = 0;
+        while (s >= m.sstart[r + 1]) r++;
+        const u64 k = skeys[s];
+        u32 rank = s - m.sstart[r];
+        for (u32 q = 0; q < m.p; q++) {
+            if (q == r) continue;
+            const u64 * a = skeys + m.sstart[q];
+            u32 lo = 0, hi = m.sstart[q + 1] - m.sstart[q];
+            const bool upper = q < r;               /* lower runs win ties: count their equal keys too */
+            while (lo < hi) {
+                const u32 mid = lo + ((hi - lo) >> 1);
+                const u64 v = a[mid];
+                if (upper ? (v <= k) : (v < k)) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        sorted_skeys[rank] = k;
+        sorted_sid[rank] = s;
     }
 }
 
@@ -380,6 +414,21 @@ extern "C" int mpsk_merge_samples(const void * recv, size_t elsize, size_t offse
     return 0;
 }
 
+extern "C" int mpsk_merge_rank_samples(const uint64_t * skeys, uint32_t p, const uint32_t * sstart,
+        uint64_t * sorted_skeys, uint32_t * sorted_sid, mpsk_stream_t stream)
+{
+    if (p > MPSK_MERGE_MAX_RUNS) return (int) cudaErrorInvalidValue;
+    MergeRuns m; m.p = p; m.S = 0; m.k = 0;
+    for (u32 r = 0; r <= p; r++) { m.rdispl[r] = 0; m.sstart[r] = sstart[r]; }
+    const u32 ns = sstart[p];
+    if (ns == 0) return 0;
+    u32 blocks = (ns + 255) / 256;
+    if (blocks > (u32) num_sms() * 8) blocks = (u32) num_sms() * 8;
+    merge_rank_samples_kernel<<<blocks, 256, 0, (cudaStream_t) stream>>>((const u64 *) skeys, m, (u64 *) sorted_skeys, sorted_sid);
+    CUDA_LAUNCH_CHECK();
+    return 0;
+}
+
 template <typename V>
 static int launch_merge_tiles(const void * recv, KeyDesc d, bool fast8, const MergeRuns & m, const u32 * cut,
                               void * out, u32 * overflow, u32 ntiles, cudaStream_t stream)
@@ -391,273 +440,6 @@ static int launch_merge_tiles(const void * recv, KeyDesc d, bool fast8, const Me
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
         if (e != cudaSuccess) return (int) e; \
         kern<<<ntiles, MPSK_MERGE_THREADS, smem, stream>>>((const unsigned char *) recv, d, m, cut, \
-                                                           (unsigned char *) out, overflow); } while (0)
-    if (fast8 && lpr1) MERGE_LAUNCH(true, true);
-    else if (fast8) MERGE_LAUNCH(true, false);
-    else if (lpr1) MERGE_LAUNCH(false, true);
-    else MERGE_LAUNCH(false, false);
-#undef MERGE_LAUNCH
-    CUDA_LAUNCH_CHECK();
-    return 0;
-}
-
-/*
- * CANDIDATE, off by default (MPSORT_MERGE_BUCKET=1 selects it) and not yet run on a GPU: the tile
- * merge in ONE round by interpolation buckets instead of log2(p) merge-path rounds; the idea, its
- * exactness argument and the arithmetic are in mpsort_merge_bucket.cuh (that part is checked on the
- * CPU by tests/test_merge_bucket_emul.py). Same grid, threads, shared-memory size and tile bounds
- * as merge_tile_kernel. Keys and source positions stay in registers from the load to the scatter;
- * a tile that fails the spread test (bucket longer than CMAX, key outside the boundary keys, first
- * or last tile of a part whose range is open) stages them like merge_tile_kernel and runs that
- * kernel's rounds. overflow[1] counts those tiles.
- */
-template <typename V, bool FAST8, bool LPR1>
-__global__ void __launch_bounds__(MPSK_MERGE_THREADS, 2)
-merge_tile_bucket_kernel(const unsigned char * __restrict__ recv, KeyDesc d, MergeRuns m,
-                         const u32 * __restrict__ cut, const u64 * __restrict__ bkeys, u32 ntiles,
-                         unsigned char * __restrict__ out, u32 * __restrict__ overflow)
-{
-    constexpr int VT = MPSK_MERGE_TILE / MPSK_MERGE_THREADS;      /* items per thread */
-    static_assert(mbk::NB / 16 == MPSK_MERGE_THREADS, "one thread scans 16 consecutive bucket counters");
-    static_assert(VT <= 8 && mbk::CMAX <= 16, "arrival slots are packed as nibbles of one word");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    /* bucket path */
-    u32 * cntp = (u32 *) smem_raw;                                  /* [NBP] counters, later bucket starts */
-    u64 * skey = (u64 *) (smem_raw + mbk::NBP * 4);                 /* [TILE] keys in bucket order */
-    u32 * ssrc = (u32 *) (skey + MPSK_MERGE_TILE);                  /* [TILE] their source positions */
-    u32 * osrc = ssrc + MPSK_MERGE_TILE;                            /* [TILE] source positions in merged order */
-    static_assert((mbk::NBP * 4) % 16 == 0, "skey must stay 8-byte aligned");
-    static_assert(mbk::NBP * 4 + MPSK_MERGE_TILE * (8 + 4 + 4) <= MPSK_MERGE_PADDED * (8 + 8 + 4 + 4), "fits the merge kernel's shared memory");
-    /* fallback: the layout of merge_tile_kernel (aliases the above, which is dead by then) */
-    u64 * kA = (u64 *) smem_raw;
-    u64 * kB = kA + MPSK_MERGE_PADDED;
-    u32 * sA = (u32 *) (kB + MPSK_MERGE_PADDED);
-    u32 * sB = sA + MPSK_MERGE_PADDED;
-    __shared__ u32 seqoff[MPSK_MERGE_MAX_RUNS + 1];
-    __shared__ u32 srcbase[MPSK_MERGE_MAX_RUNS];
-    __shared__ u32 s_outstart;
-    __shared__ u64 s_bound[2];
-    __shared__ u32 s_wsum[MPSK_MERGE_THREADS / 32];
-
-    const u32 t = blockIdx.x, p = m.p, tid = threadIdx.x;
-    if (tid < 32) {
-        u32 c0 = 0, c1 = 0;
-        if (tid < p) { c0 = cut[t * p + tid]; c1 = cut[(t + 1) * p + tid]; }
-        const u32 len = c1 - c0;
-        u32 incl = len, sum0 = c0;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const u32 y = __shfl_up_sync(FULL_MASK, incl, o);
-            if (tid >= (u32) o) incl += y;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum0 += __shfl_xor_sync(FULL_MASK, sum0, o);
-        if (tid < p) { seqoff[tid] = incl - len; srcbase[tid] = m.rdispl[tid] + c0; }
-        if (tid == p - 1) seqoff[p] = incl;
-        if (tid == 0) s_outstart = sum0;
-    } else if (tid == 32) {
-        /* the tile's keys lie between the boundary samples of its two cuts (merge_bounds_kernel);
-         * the first and the last tile of a part are open on one side */
-        s_bound[0] = t > 0 ? bkeys[(size_t) t * m.k - 1] : 0ULL;
-        s_bound[1] = t + 1 < ntiles ? bkeys[(size_t) (t + 1) * m.k - 1] : ~0ULL;
-    }
-    for (u32 i = tid; i < mbk::NBP; i += MPSK_MERGE_THREADS) cntp[i] = 0;
-    __syncthreads();
-    const u32 cnt = seqoff[p];
-    if (cnt > MPSK_MERGE_TILE) {            /* cannot happen (tile bound); never corrupt memory */
-        if (tid == 0) atomicAdd(overflow, 1u);
-        return;
-    }
-    const u64 klo = s_bound[0], khi = s_bound[1];
-    const u32 sh = mbk::shift_for(klo, khi);
-
-    /* ---- load the keys of the p sub-ranges, run-major (as merge_tile_kernel); they stay in registers */
-    u32 src[VT];
-    u64 key[VT];
-    {
-        u32 r = 0;
-#pragma unroll
-        for (int k = 0; k < VT; k++) {
-            const u32 i = tid + k * MPSK_MERGE_THREADS;
-            src[k] = 0;
-            if (i < cnt) {
-                while (i >= seqoff[r + 1]) r++;
-                src[k] = srcbase[r] + (i - seqoff[r]);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < VT; k++) {
-            const u32 i = tid + k * MPSK_MERGE_THREADS;
-            key[k] = 0;
-            if (i < cnt) key[k] = load_key_any(recv + (size_t) src[k] * d.elsize, d, FAST8);
-        }
-    }
-    /* ---- count: arrival slot of every record in its bucket */
-    u32 slots = 0;
-    bool bad = false;
-#pragma unroll
-    for (int k = 0; k < VT; k++) {
-        const u32 i = tid + k * MPSK_MERGE_THREADS;
-        if (i < cnt) {
-            const bool ok = mbk::in_range(key[k], klo, khi);
-            bad |= !ok;
-            const u32 b = ok ? mbk::bucket_of(key[k], klo, sh) : 0u;
-            const u32 s = atomicAdd(&cntp[mbk::padc(b < mbk::NB ? b : mbk::NB - 1)], 1u);
-            slots |= (s < 15u ? s : 15u) << (4 * k);
-        }
-    }
-    __syncthreads();
-    /* ---- exclusive scan of the counters; thread tid owns buckets [16 tid, 16 tid + 16) */
-    u32 tot = 0, mx = 0;
-    {
-        const u32 * mine = cntp + 17 * tid;
-#pragma unroll
-        for (int j = 0; j < 16; j++) { const u32 c = mine[j]; tot += c; mx = c > mx ? c : mx; }
-    }
-    u32 incl = tot;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const u32 y = __shfl_up_sync(FULL_MASK, incl, o);
-        if ((tid & 31u) >= (u32) o) incl += y;
-    }
-    if ((tid & 31u) == 31u) s_wsum[tid >> 5] = incl;
-    const int fallback = __syncthreads_or((bad || mx > mbk::CMAX) ? 1 : 0);
-
-    const u32 lpr = LPR1 ? 1u : (u32) (d.elsize / sizeof(V));
-    const V * in = (const V *) recv;
-    V * o = (V *) out + (size_t) s_outstart * lpr;
-    const u32 totalv = cnt * lpr;
-
-    if (fallback) {
-        /* ---- not spread enough: the merge-path rounds of merge_tile_kernel */
-        if (tid == 0) atomicAdd(overflow + 1, 1u);
-#pragma unroll
-        for (int k = 0; k < VT; k++) {
-            const u32 i = tid + k * MPSK_MERGE_THREADS;
-            if (i < cnt) { kA[MPD(i)] = key[k]; sA[MPD(i)] = src[k]; }
-        }
-        __syncthreads();
-        for (u32 w = 1; w < p; w <<= 1) {
-            u32 oo = tid * VT;
-            const u32 end = min(oo + (u32) VT, cnt);
-            u32 g = 0;
-            while (oo < end) {
-                while (seqoff[min((2 * g + 2) * w, p)] <= oo) g++;
-                const u32 a0 = seqoff[min(2 * g * w, p)];
-                const u32 a1 = seqoff[min((2 * g + 1) * w, p)];
-                const u32 b1 = seqoff[min((2 * g + 2) * w, p)];
-                const u32 lenA = a1 - a0, lenB = b1 - a1;
-                const u32 seg_end = min(end, b1);
-                const u32 diag = oo - a0;
-                u32 lo = diag > lenB ? diag - lenB : 0, hi = min(diag, lenA);
-                while (lo < hi) {
-                    const u32 mid = (lo + hi) >> 1;
-                    if (kA[MPD(a0 + mid)] <= kA[MPD(a1 + diag - 1 - mid)]) lo = mid + 1; else hi = mid;
-                }
-                u32 ai = a0 + lo, bi = a1 + (diag - lo);
-                u64 ka = kA[MPD(min(ai, b1 - 1))], kb = kA[MPD(min(bi, b1 - 1))];
-                u32 sa = sA[MPD(min(ai, b1 - 1))], sb = sA[MPD(min(bi, b1 - 1))];
-                for (; oo < seg_end; oo++) {
-                    const bool takeA = (bi >= b1) || (ai < a1 && ka <= kb);
-                    kB[MPD(oo)] = takeA ? ka : kb;
-                    sB[MPD(oo)] = takeA ? sa : sb;
-                    ai += takeA ? 1u : 0u;
-                    bi += takeA ? 0u : 1u;
-                    const u32 nxt = min(takeA ? ai : bi, b1 - 1);
-                    const u64 nk = kA[MPD(nxt)];
-                    const u32 ns = sA[MPD(nxt)];
-                    ka = takeA ? nk : ka; sa = takeA ? ns : sa;
-                    kb = takeA ? kb : nk; sb = takeA ? sb : ns;
-                }
-            }
-            __syncthreads();
-            u64 * tk = kA; kA = kB; kB = tk;
-            u32 * ts = sA; sA = sB; sB = ts;
-        }
-        for (u32 x0 = 0; x0 < totalv; x0 += VT * MPSK_MERGE_THREADS) {
-            V v[VT];
-#pragma unroll
-            for (int k = 0; k < VT; k++) {
-                const u32 x = x0 + tid + k * MPSK_MERGE_THREADS;
-                if (x < totalv) {
-                    if (LPR1) {
-                        v[k] = in[sA[MPD(x)]];
-                    } else {
-                        const u32 i = x / lpr, part = x - i * lpr;
-                        v[k] = in[(size_t) sA[MPD(i)] * lpr + part];
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < VT; k++) {
-                const u32 x = x0 + tid + k * MPSK_MERGE_THREADS;
-                if (x < totalv) o[x] = v[k];
-            }
-        }
-        return;
-    }
-
-    /* ---- bucket starts (second read of the counters keeps the register count down) */
-    {
-        u32 run = incl - tot;
-        for (u32 w = 0; w < (tid >> 5); w++) run += s_wsum[w];
-        u32 * mine = cntp + 17 * tid;
-#pragma unroll
-        for (int j = 0; j < 16; j++) { const u32 c = mine[j]; mine[j] = run; run += c; }
-    }
-    __syncthreads();
-    /* ---- scatter (key, source position) to bucket order */
-#pragma unroll
-    for (int k = 0; k < VT; k++) {
-        const u32 i = tid + k * MPSK_MERGE_THREADS;
-        if (i < cnt) {
-            const u32 pos = cntp[mbk::padc(mbk::bucket_of(key[k], klo, sh))] + ((slots >> (4 * k)) & 15u);
-            skey[pos] = key[k];
-            ssrc[pos] = src[k];
-        }
-    }
-    __syncthreads();
-    /* ---- rank inside the bucket: the merged order of the source positions */
-#pragma unroll
-    for (int k = 0; k < VT; k++) {
-        const u32 pos = tid + k * MPSK_MERGE_THREADS;
-        if (pos < cnt) osrc[mbk::merged_position(cntp, skey, ssrc, pos, cnt, klo, sh)] = ssrc[pos];
-    }
-    __syncthreads();
-    /* ---- write the records in merged order (as merge_tile_kernel) */
-    for (u32 x0 = 0; x0 < totalv; x0 += VT * MPSK_MERGE_THREADS) {
-        V v[VT];
-#pragma unroll
-        for (int k = 0; k < VT; k++) {
-            const u32 x = x0 + tid + k * MPSK_MERGE_THREADS;
-            if (x < totalv) {
-                if (LPR1) {
-                    v[k] = in[osrc[x]];
-                } else {
-                    const u32 i = x / lpr, part = x - i * lpr;
-                    v[k] = in[(size_t) osrc[i] * lpr + part];
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < VT; k++) {
-            const u32 x = x0 + tid + k * MPSK_MERGE_THREADS;
-            if (x < totalv) o[x] = v[k];
-        }
-    }
-}
-
-template <typename V>
-static int launch_merge_bucket_tiles(const void * recv, KeyDesc d, bool fast8, const MergeRuns & m, const u32 * cut,
-                                     const u64 * bkeys, void * out, u32 * overflow, u32 ntiles, cudaStream_t stream)
-{
-    const int smem = MPSK_MERGE_PADDED * (8 + 8 + 4 + 4);
-    const bool lpr1 = d.elsize == sizeof(V);
-#define MERGE_LAUNCH(F8, L1) do { \
-        auto kern = merge_tile_bucket_kernel<V, F8, L1>; \
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
-        if (e != cudaSuccess) return (int) e; \
-        kern<<<ntiles, MPSK_MERGE_THREADS, smem, stream>>>((const unsigned char *) recv, d, m, cut, bkeys, ntiles, \
                                                            (unsigned char *) out, overflow); } while (0)
     if (fast8 && lpr1) MERGE_LAUNCH(true, true);
     else if (fast8) MERGE_LAUNCH(true, false);
@@ -704,14 +486,6 @@ extern "C" int mpsk_merge_runs(const void * recv, void * out, size_t elsize, siz
         return 0;
     }
     const uintptr_t a = ((uintptr_t) recv) | ((uintptr_t) out) | (uintptr_t) elsize;
-    static int bucket = -1;
-    if (bucket < 0) { const char * e = getenv("MPSORT_MERGE_BUCKET"); bucket = (e && atoi(e) > 0) ? 1 : 0; }
-    if (bucket) {
-        /* candidate: one-round bucket merge (16- and 8-byte pieces only; others keep the rounds) */
-        const u64 * bk = (const u64 *) sorted_skeys;
-        if ((a & 15) == 0) return launch_merge_bucket_tiles<uint4>(recv, d, fast8, m, cut, bk, out, overflow, ntiles, stream);
-        if ((a & 7) == 0) return launch_merge_bucket_tiles<u64>(recv, d, fast8, m, cut, bk, out, overflow, ntiles, stream);
-    }
     if ((a & 15) == 0) return launch_merge_tiles<uint4>(recv, d, fast8, m, cut, out, overflow, ntiles, stream);
     if ((a & 7) == 0) return launch_merge_tiles<u64>(recv, d, fast8, m, cut, out, overflow, ntiles, stream);
     if ((a & 3) == 0) return launch_merge_tiles<u32>(recv, d, fast8, m, cut, out, overflow, ntiles, stream);

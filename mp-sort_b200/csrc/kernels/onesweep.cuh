@@ -179,7 +179,7 @@ struct SweepCfg {
  * ranked in (warp, round j, lane) order, which is exactly the order they were
  * loaded in (position = warp*IPT*32 + j*32 + lane).
  */
-template <int THREADS, int IPT, bool IOTA>
+template <int THREADS, int IPT, bool IOTA, bool TICKET>
 __global__ void __launch_bounds__(THREADS, MPSK_SWEEP_MINBLOCKS)
 onesweep_kernel(const u64 * __restrict__ kin, const u32 * __restrict__ vin,
                 u64 * __restrict__ kout, u32 * __restrict__ vout,
@@ -203,11 +203,13 @@ onesweep_kernel(const u64 * __restrict__ kin, const u32 * __restrict__ vin,
     const u32 lane = tid & 31u;
     const u32 warp = tid >> 5;
 
-    if (tid == 0) s_misc[0] = atomicAdd(ticket, 1u);
-    for (u32 i = tid; i < WARPS * 256; i += THREADS) s_whist[i] = 0;
-    __syncthreads();
-
-    const u32 tile = s_misc[0];
+    /* tile = blockIdx.x unless tickets were asked for (see onesweep_rec_kernel) */
+    u32 tile = blockIdx.x;
+    if (TICKET) {
+        if (tid == 0) s_misc[0] = atomicAdd(ticket, 1u);
+        __syncthreads();
+        tile = s_misc[0];
+    }
     const u32 tile_base = tile * (u32) TILE;
     const u32 remaining = n - tile_base;
     const u32 valid = remaining < (u32) TILE ? remaining : (u32) TILE;
@@ -230,6 +232,10 @@ onesweep_kernel(const u64 * __restrict__ kin, const u32 * __restrict__ vin,
     u32 rank[IPT];
     u32 * my_hist = s_whist + warp * 256;
     const u32 lt = lanemask_lt();
+    /* every warp zeroes its own histogram while its loads are in flight */
+#pragma unroll
+    for (int k = 0; k < 8; k++) my_hist[lane + 32 * k] = 0;
+    __syncwarp();
     u32 peers_of[IPT];                 /* all ballots first: off the serial histogram chain */
 #pragma unroll
     for (int j = 0; j < IPT; j++) peers_of[j] = match_digit((u32) (key[j] >> shift) & 255u);
@@ -342,6 +348,15 @@ onesweep_kernel(const u64 * __restrict__ kin, const u32 * __restrict__ vin,
 
 typedef SweepCfg<MPSK_SWEEP_THREADS, MPSK_SWEEP_IPT> TheSweep;
 
+/* run-time switches of the onesweep passes (read once): MPSORT_TICKET_TILES=1 hands tiles out by an
+ * atomic ticket instead of blockIdx.x; MPSORT_PREFETCH_TILES=d (record passes) prefetches tile + d into L2 */
+static int sweep_ticket_tiles()
+{
+    static int v = -1;
+    if (v < 0) { const char * e = getenv("MPSORT_TICKET_TILES"); v = (e && atoi(e) > 0) ? 1 : 0; }
+    return v;
+}
+
 extern "C" size_t mpsk_onesweep_tile_items(void) { return TheSweep::TILE; }
 
 extern "C" size_t mpsk_onesweep_scratch_bytes(size_t n)
@@ -368,19 +383,16 @@ extern "C" int mpsk_onesweep_pass(const uint64_t * kin, const uint32_t * vin,
     lb.blktotal = lb.tiles + ntiles * 256;
     lb.blkincl = lb.blktotal + ((ntiles + LB_BLOCK - 1) / LB_BLOCK) * 256;
     /* the attribute is per device: set it on every launch (local groups span devices) */
-    if (vin == NULL) {
-        auto kern = onesweep_kernel<MPSK_SWEEP_THREADS, MPSK_SWEEP_IPT, true>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TheSweep::SMEM);
-        if (e != cudaSuccess) return (int) e;
-        kern<<<(unsigned) ntiles, MPSK_SWEEP_THREADS, TheSweep::SMEM, stream>>>(
-            (const u64 *) kin, vin, (u64 *) kout, vout, (u32) n, (u32) shift, bins, lb, ticket);
-    } else {
-        auto kern = onesweep_kernel<MPSK_SWEEP_THREADS, MPSK_SWEEP_IPT, false>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TheSweep::SMEM);
-        if (e != cudaSuccess) return (int) e;
-        kern<<<(unsigned) ntiles, MPSK_SWEEP_THREADS, TheSweep::SMEM, stream>>>(
-            (const u64 *) kin, vin, (u64 *) kout, vout, (u32) n, (u32) shift, bins, lb, ticket);
-    }
+#define SWEEP_LAUNCH(IOTA_, TICKET_) do { \
+        auto kern = onesweep_kernel<MPSK_SWEEP_THREADS, MPSK_SWEEP_IPT, IOTA_, TICKET_>; \
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TheSweep::SMEM); \
+        if (e != cudaSuccess) return (int) e; \
+        kern<<<(unsigned) ntiles, MPSK_SWEEP_THREADS, TheSweep::SMEM, stream>>>( \
+            (const u64 *) kin, vin, (u64 *) kout, vout, (u32) n, (u32) shift, bins, lb, ticket); } while (0)
+    const bool tickets = sweep_ticket_tiles() != 0;
+    if (vin == NULL) { if (tickets) SWEEP_LAUNCH(true, true); else SWEEP_LAUNCH(true, false); }
+    else { if (tickets) SWEEP_LAUNCH(false, true); else SWEEP_LAUNCH(false, false); }
+#undef SWEEP_LAUNCH
     CUDA_LAUNCH_CHECK();
     return 0;
 }

@@ -77,7 +77,7 @@ void MPIU_Set_verbose_malloc(mpsort_comm_t comm)
 static const char * slot_names[MPS_NSLOTS] = {
     "din", "dout", "keywords", "keys_b", "keys_a", "idx_a", "idx_b", "sortedkeys",
     "hist", "lookback", "sendbuf", "recvbuf", "splitters", "stage", "stage2", "misc",
-    "merge_samples", "merge_cuts"
+    "merge_samples", "merge_cuts", "merge_sorted_samples", "merge_sample_ids"
 };
 
 void * mps_arena_get(struct mpsort_comm * c, int slot, size_t bytes)
@@ -124,6 +124,32 @@ void * mps_arena_get(struct mpsort_comm * c, int slot, size_t bytes)
     c->slot[slot].ptr = p;
     c->slot[slot].cap = cap;
     return p;
+}
+
+void mps_merge_ovf_begin(struct mpsort_comm * c)
+{
+    if (!c->d_merge_ovf) {
+        CUDA_OK(c, cudaMalloc((void **) &c->d_merge_ovf, 256));
+        CUDA_OK(c, cudaMallocHost((void **) &c->h_merge_ovf, 256));
+    }
+    c->h_merge_ovf[0] = c->h_merge_ovf[1] = 0;
+    c->merge_ovf_pending = 0;
+    CUDA_OK(c, cudaMemsetAsync(c->d_merge_ovf, 0, 2 * sizeof(uint32_t), c->stream));
+}
+
+void mps_merge_ovf_fetch(struct mpsort_comm * c)
+{
+    if (!c->d_merge_ovf) return;
+    CUDA_OK(c, cudaMemcpyAsync(c->h_merge_ovf, c->d_merge_ovf, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    c->merge_ovf_pending = 1;
+}
+
+void mps_merge_ovf_check(struct mpsort_comm * c)
+{
+    if (!c->merge_ovf_pending) return;
+    c->merge_ovf_pending = 0;
+    if (c->h_merge_ovf[0] != 0)
+        mps_fatal(c, __FILE__, __LINE__, "serious bug: %u merge tiles exceeded their bound", c->h_merge_ovf[0]);
 }
 
 void * mps_host_stage(struct mpsort_comm * c, size_t bytes)
@@ -239,6 +265,9 @@ mpsort_comm_t mpsort_comm_init_rank(int rank, int size, const void * unique_id, 
     c->p2p.copy_engine = getenv("MPSORT_P2P_CE") ? atoi(getenv("MPSORT_P2P_CE")) : 1;
     if (c->p2p.copy_engine < 0) c->p2p.copy_engine = 0;
     if (c->p2p.copy_engine > 7) c->p2p.copy_engine = 7;
+    c->p2p.split = getenv("MPSORT_P2P_SPLIT") ? atoi(getenv("MPSORT_P2P_SPLIT")) : 1;
+    if (c->p2p.split < 1) c->p2p.split = 1;
+    if (c->p2p.split > 7) c->p2p.split = 7;
     return c;
 }
 
@@ -294,6 +323,8 @@ void mpsort_comm_destroy(mpsort_comm_t c)
     free(c->p2p.zombies);
     for (s = 0; s < MPS_NSLOTS; s++) if (c->slot[s].ptr) cudaFree(c->slot[s].ptr);
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->d_merge_ovf) cudaFree(c->d_merge_ovf);
+    if (c->h_merge_ovf) cudaFreeHost(c->h_merge_ovf);
     if (c->p2p.d_flag) cudaFree(c->p2p.d_flag);
     if (c->p2p.ce_created) {
         for (s = 0; s < 8; s++) cudaStreamDestroy(c->p2p.ce_stream[s]);
@@ -658,14 +689,40 @@ static void exchange_p2p(struct mpsort_comm * c, const void * sendbuf, const int
              * up to here) and the main stream then waits for every one of them -- stream 7 included,
              * whatever p is (it used to be left out for p < 8: found by the CPU stream model,
              * tests/native/mock_async.cpp). */
+            /* A large remote slice may be cut into `split` pieces that move at the same time on
+             * different copy streams (MPSORT_P2P_SPLIT; with two GPUs one copy per direction does not
+             * fill the 18 links). Piece i of the slice dealt to lane l goes to stream l * split + i;
+             * lanes * split <= 7 keeps stream 7 for the own slice. */
+            const int lanes = c->p2p.copy_engine;
+            int split = c->p2p.split;
+            while (split > 1 && lanes * split > 7) split--;
             unsigned used = 0;
-            for (k = 0; k < p; k++) if (rbytes[k]) used |= 1u << (rrem[k] ? k % c->p2p.copy_engine : 7);
+            for (k = 0; k < p; k++) {
+                if (!rbytes[k]) continue;
+                if (!rrem[k]) { used |= 1u << 7; continue; }
+                const int pieces = (rbytes[k] >= ((uint64_t) 8 << 20)) ? split : 1;
+                int i;
+                for (i = 0; i < pieces; i++) used |= 1u << ((k % lanes) * split + i);
+            }
             CUDA_OK(c, cudaEventRecord(c->p2p.ce_ev[8], c->stream));
             for (k = 0; k < 8; k++) if ((used >> k) & 1u) CUDA_OK(c, cudaStreamWaitEvent(c->p2p.ce_stream[k], c->p2p.ce_ev[8], 0));
-            for (k = 0; k < p; k++)
-                if (rbytes[k])
-                    CUDA_OK(c, cudaMemcpyAsync(rdst[k], rsrc[k], (size_t) rbytes[k], cudaMemcpyDeviceToDevice,
-                                               c->p2p.ce_stream[rrem[k] ? k % c->p2p.copy_engine : 7]));
+            for (k = 0; k < p; k++) {
+                if (!rbytes[k]) continue;
+                if (!rrem[k]) {
+                    CUDA_OK(c, cudaMemcpyAsync(rdst[k], rsrc[k], (size_t) rbytes[k], cudaMemcpyDeviceToDevice, c->p2p.ce_stream[7]));
+                    continue;
+                }
+                const int pieces = (rbytes[k] >= ((uint64_t) 8 << 20)) ? split : 1;
+                /* pieces are whole records: cut at multiples of elsize */
+                const uint64_t nrec = rbytes[k] / elsize, per = (nrec + (uint64_t) pieces - 1) / (uint64_t) pieces;
+                int i;
+                for (i = 0; i < pieces; i++) {
+                    const uint64_t r0 = per * (uint64_t) i, r1 = (r0 + per < nrec) ? r0 + per : nrec;
+                    if (r0 >= r1) break;
+                    CUDA_OK(c, cudaMemcpyAsync((char *) rdst[k] + r0 * elsize, (const char *) rsrc[k] + r0 * elsize, (size_t) ((r1 - r0) * elsize),
+                                               cudaMemcpyDeviceToDevice, c->p2p.ce_stream[(k % lanes) * split + i]));
+                }
+            }
             for (k = 0; k < 8; k++) {
                 if (!((used >> k) & 1u)) continue;
                 CUDA_OK(c, cudaEventRecord(c->p2p.ce_ev[k], c->p2p.ce_stream[k]));

@@ -517,10 +517,9 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
  * stable p-way merge that prefers the lower run on ties gives the same bytes with
  * E read + E write per record instead of a full radix sort.
  * Returns 0 if the merge ran, 1 if the caller must use the radix path. */
-static int merge_received_runs(struct mpsort_comm * c, const void * recvbuf, const int64_t * rdispl,
+static int merge_received_runs(struct mpsort_comm * c, int p, const void * recvbuf, const int64_t * rdispl,
         void * dout, size_t outn, size_t elsize, const struct mpsort_radix_desc * desc)
 {
-    const int p = c->size;
     const size_t T = mpsk_merge_tile_items_for(recvbuf, dout, elsize, desc->offset, desc->width, desc->nwords, (uint32_t) p);
     int r;
     if (key_words(desc) != 1 || p > 32 || p < 2 || outn < 4 * mpsk_merge_tile_items() || outn > 0xfffffff0u) return 1;
@@ -540,28 +539,37 @@ static int merge_received_runs(struct mpsort_comm * c, const void * recvbuf, con
     const uint32_t ntiles = ns == 0 ? 1 : (ns + k - 1) / k;
 
     uint64_t * skeys = (uint64_t *) mps_arena_get(c, MPS_S_MERGE_SAMP, (size_t) (ns ? ns : 1) * sizeof(uint64_t));
+    uint64_t * sorted_skeys = (uint64_t *) mps_arena_get(c, MPS_S_MERGE_SORTED, (size_t) (ns ? ns : 1) * sizeof(uint64_t));
+    uint32_t * sorted_sid = (uint32_t *) mps_arena_get(c, MPS_S_MERGE_SID, (size_t) (ns ? ns : 1) * sizeof(uint32_t));
     uint32_t * cut = (uint32_t *) mps_arena_get(c, MPS_S_MERGE_CUT, ((size_t) ntiles + 1) * p * sizeof(uint32_t) + 256);
-    uint32_t * overflow = cut + ((size_t) ntiles + 1) * p;
-    CUDA_OK(c, cudaMemsetAsync(overflow, 0, 2 * sizeof(uint32_t), c->stream));   /* [1]: tiles the bucket candidate handed to the rounds */
+    /* three launches and no host round trip: samples -> their merged order (sample keys are packed,
+     * i.e. sign-flipped, already; every run's samples are sorted, so each one ranks itself by binary
+     * searches in the other runs' lists) -> tile bounds + tiles. Tiles that break their bound (never
+     * happens) are counted in c->d_merge_ovf and looked at once, after the sort's final synchronisation. */
     KERN_T(c, MPS_K_MERGE, mpsk_merge_samples(recvbuf, elsize, desc->offset, desc->width, desc->nwords, desc->is_signed,
                                               (uint32_t) p, S, k, rd, ss, skeys, c->stream));
-    /* sample keys are already packed (sign-flipped): sort them as bare unsigned u64 records */
-    struct sorted_view sv;
-    const struct mpsort_radix_desc sdesc = { 0, 8, 1, 0, 0 };
-    c->kt.force_cls = MPS_K_MERGE;      /* the sample sort is part of the merge, not a full-size pass */
-    local_sort(c, skeys, ns, sizeof(uint64_t), &sdesc, 1, 0, &sv);
-    c->kt.force_cls = 0;
+    KERN_T(c, MPS_K_MERGE, mpsk_merge_rank_samples(skeys, (uint32_t) p, ss, sorted_skeys, sorted_sid, c->stream));
     KERN_T(c, MPS_K_MERGE, mpsk_merge_runs(recvbuf, dout, elsize, desc->offset, desc->width, desc->nwords, desc->is_signed,
-                                           (uint32_t) p, S, k, rd, ss, sv.skeys, sv.idx, ntiles, cut, overflow, c->stream));
-    {
-        uint32_t * h = (uint32_t *) mps_host_stage(c, 2 * sizeof(uint32_t));
-        CUDA_OK(c, cudaMemcpyAsync(h, overflow, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-        CUDA_OK(c, cudaStreamSynchronize(c->stream));
-        if (h[0] != 0) mps_fatal(c, __FILE__, __LINE__, "serious bug: %u merge tiles exceeded their bound", h[0]);
-        c->stats.merge_bucket_fallback_tiles += h[1];
-    }
+                                           (uint32_t) p, S, k, rd, ss, sorted_skeys, sorted_sid, ntiles, cut, c->d_merge_ovf, c->stream));
     c->stats.second_sort_merge_tiles += ntiles;
     return 0;
+}
+
+/* bench / test support (include/mpsort_util.h): the SecondSort merge alone, on p sorted runs
+ * that already sit in device memory -- one GPU can then time and profile the merge of the
+ * 8-GPU configuration at full size. Blocking. Returns 0 if the merge ran, 1 if these runs
+ * would take the radix fallback. */
+int mpsort_util_merge_runs(mpsort_comm_t c, int p, const void * runs, const int64_t * rdispl,
+        void * out, size_t elsize, const struct mpsort_radix_desc * desc)
+{
+    CUDA_OK(c, cudaSetDevice(c->device));
+    mps_merge_ovf_begin(c);
+    const int rc = merge_received_runs(c, p, runs, rdispl, out, (size_t) (rdispl[p] - rdispl[0]), elsize, desc);
+    mps_merge_ovf_fetch(c);
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    mps_merge_ovf_check(c);
+    mps_kt_collect(c);
+    return rc;
 }
 
 /* ------------------------------------------------------------------------- */
@@ -914,6 +922,7 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
     if (v1.sorted_recs != sendbuf && !pack_pipe && !fused_pack)
         KERN_T(c, MPS_K_GATHER_RECORDS, mpsk_gather_records(dbase, v1.idx, sendbuf, n, elsize, c->stream));
     timer_mark(c, "Pack");
+    mps_merge_ovf_begin(c);
     const int dense = mpsort_mpi_has_options(MPSORT_DISABLE_SPARSE_ALLTOALLV)
                       && !mpsort_mpi_has_options(MPSORT_REQUIRE_SPARSE_ALLTOALLV);
     c->stats.dense_exchange = (uint32_t) dense;
@@ -983,7 +992,7 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
             if (Q > 1) CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->phase_ev[fused_pack ? Q - 1 : q], 0));
             char * part_in = (char *) recvbuf + (size_t) base * elsize;
             char * part_out = (char *) dout + (size_t) base * elsize;
-            if (merge_received_runs(c, part_in, rdispl, part_out, (size_t) cnt, elsize, desc) != 0) {
+            if (merge_received_runs(c, p, part_in, rdispl, part_out, (size_t) cnt, elsize, desc) != 0) {
                 struct sorted_view v2;
                 local_sort(c, part_in, (size_t) cnt, elsize, desc, 0, 1, &v2);
                 KERN_T(c, MPS_K_GATHER_RECORDS, mpsk_gather_records(part_in, v2.idx, part_out, (size_t) cnt, elsize, c->stream));
@@ -996,6 +1005,7 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
             CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->phase_ev[MPS_MAX_RANKS], 0));
         }
     }
+    mps_merge_ovf_fetch(c);
     timer_mark(c, "SecondSort");
     timer_mark(c, "END");
 #undef CUTV
@@ -1071,6 +1081,7 @@ void mpsort_mpi_newarray_desc_impl(void * base, size_t nmemb,
     if (!out_dev && outnmemb > 0)
         CUDA_OK(c, cudaMemcpyAsync(out, dout, outnmemb * elsize, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    mps_merge_ovf_check(c);
     mps_kt_collect(c);
     timer_publish(c);
 }

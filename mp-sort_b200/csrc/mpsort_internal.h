@@ -41,6 +41,8 @@ enum mps_slot {
     MPS_S_MISC,        /* checksum / small outputs                     */
     MPS_S_MERGE_SAMP,  /* merge: sample keys                           */
     MPS_S_MERGE_CUT,   /* merge: per-tile cut positions                */
+    MPS_S_MERGE_SORTED,/* merge: sample keys in merged order            */
+    MPS_S_MERGE_SID,   /* merge: their sample ids                       */
     MPS_NSLOTS
 };
 
@@ -96,6 +98,11 @@ struct mpsort_comm {
     int64_t sendcounts[MPS_MAX_RANKS];
     struct mps_ktimes kt;
     cudaStream_t stream2;                      /* merges of the pipelined exchange run here */
+    /* merge tiles that broke their bound (never happens) are counted on the device and looked at
+     * once per sort, after the final synchronisation, instead of once per exchange part */
+    uint32_t * d_merge_ovf;                    /* device u32: tiles that broke their bound */
+    uint32_t * h_merge_ovf;                    /* pinned copy */
+    int merge_ovf_pending;
     cudaEvent_t phase_ev[MPS_MAX_RANKS + 1];
     int phase_ev_created;
 
@@ -119,7 +126,8 @@ struct mpsort_comm {
         uint64_t generation;                   /* bumped every time my exchange buffer is replaced */
         uint64_t peer_gen[MPS_MAX_RANKS];      /* generation of rank j's buffer my mapping belongs to */
         int * d_flag;                          /* device word for the completion all-reduce */
-        int copy_engine;                       /* 1: slices move by cudaMemcpyAsync (DMA engines, no SMs) */
+        int copy_engine;                       /* >= 1: slices move by cudaMemcpyAsync (DMA engines, no SMs), that many at a time */
+        int split;                             /* pieces a large slice is cut into, moved concurrently (MPSORT_P2P_SPLIT) */
         cudaStream_t ce_stream[8];             /* copy-engine mode: peer copies fan out over these */
         cudaEvent_t ce_ev[9];
         int ce_created;
@@ -155,6 +163,11 @@ extern __thread int mps_caller_line;
 /* ---- host allocations of significance go through the mpiu_set_malloc hook ---- */
 void * mps_host_malloc(const char * name, size_t size, const char * file, int line);
 void mps_host_free(void * ptr, const char * file, int line);
+
+/* merge overflow words: zeroed at the start of a sort, checked after its final synchronisation */
+void mps_merge_ovf_begin(struct mpsort_comm * c);
+void mps_merge_ovf_fetch(struct mpsort_comm * c);     /* async copy to the pinned words on c->stream */
+void mps_merge_ovf_check(struct mpsort_comm * c);     /* after the stream was synchronised */
 
 /* ---- arena ---- */
 void * mps_arena_get(struct mpsort_comm * c, int slot, size_t bytes);

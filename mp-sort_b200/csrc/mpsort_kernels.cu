@@ -22,10 +22,8 @@
  *   p2p_copy_kernel                   MPIU_Alltoallv                  mp-mpiu.c:69-236
  *   checksum_kernel                   checksum()                      mpsort-mpi.c:148-159
  * Candidates, off by default (each names its switch where it is defined):
- *   merge_tile_bucket_kernel          the second radix_sort           mpsort-mpi.c:597
  *   splitter_descent_peer_kernel      the bisection loop + Allreduce  mpsort-mpi.c:385-437
  *   p2p_gather_kernel                 record moves + MPIU_Alltoallv   stdlib/msort.c:153-173, mp-mpiu.c:69-236
- *   onesweep_rec_persist_kernel       mpsort_qsort_r (compile-time)   stdlib/msort.c:177-314
  */
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -142,7 +142,7 @@ int mpsk_sum_u64(uint64_t * dst, const uint64_t * const * srcs, int nsrc, size_t
  * (k + p) * S <= mpsk_merge_tile_items(); sstart[r] = first sample id of run r
  * (run r has (len_r / S) samples).
  *   mpsk_merge_samples  writes the sample keys skeys[sstart[p]] in (run, position) order;
- *   the caller sorts them stably by key (sorted_skeys, sorted_sid = permutation);
+ *   mpsk_merge_rank_samples orders them stably by key (sorted_skeys, sorted_sid = permutation);
  *   mpsk_merge_runs     computes cut[(ntiles+1)*p] and merges tile by tile into out.
  * *overflow (device, zeroed by the caller) counts tiles that exceeded the bound
  * (never happens; such a tile is left unwritten instead of corrupting memory). */
@@ -153,6 +153,10 @@ size_t mpsk_merge_tile_items_for(const void * recv, const void * out, size_t els
 int mpsk_merge_samples(const void * recv, size_t elsize, size_t offset, uint32_t width,
         uint32_t nwords, int is_signed, uint32_t p, uint32_t S, uint32_t k,
         const uint32_t * rdispl, const uint32_t * sstart, uint64_t * skeys, mpsk_stream_t stream);
+/* sorted_skeys / sorted_sid = the samples in (key, run, position) order and their sample ids;
+ * each run's samples are sorted already, so every sample ranks itself by p - 1 binary searches */
+int mpsk_merge_rank_samples(const uint64_t * skeys, uint32_t p, const uint32_t * sstart,
+        uint64_t * sorted_skeys, uint32_t * sorted_sid, mpsk_stream_t stream);
 int mpsk_merge_runs(const void * recv, void * out, size_t elsize, size_t offset, uint32_t width,
         uint32_t nwords, int is_signed, uint32_t p, uint32_t S, uint32_t k,
         const uint32_t * rdispl, const uint32_t * sstart,

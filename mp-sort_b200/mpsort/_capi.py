@@ -60,8 +60,7 @@ class LastStats(ctypes.Structure):
                 ("bytes_sent_remote", c_u64), ("second_sort_merge_tiles", ctypes.c_uint32),
                 ("record_mode", ctypes.c_uint32), ("hybrid", ctypes.c_uint32),
                 ("hybrid_long_runs", ctypes.c_uint32), ("rebased", ctypes.c_uint32),
-                ("p2p_exchange", ctypes.c_uint32), ("exchange_phases", ctypes.c_uint32),
-                ("merge_bucket_fallback_tiles", ctypes.c_uint32)]
+                ("p2p_exchange", ctypes.c_uint32), ("exchange_phases", ctypes.c_uint32)]
 
 
 def _proto(name, restype, *argtypes):
@@ -141,6 +140,8 @@ _proto("mpsort_util_launch_count", c_u64, c_int)
 _proto("mpsort_util_kernel_timing", None, c_void_p, c_int)
 _proto("mpsort_util_kernel_times", c_int, c_void_p, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_double),
        ctypes.POINTER(c_u64), c_int)
+_proto("mpsort_util_merge_runs", c_int, c_void_p, c_int, c_void_p, ctypes.POINTER(c_i64), c_void_p, c_size_t,
+       ctypes.POINTER(RadixDesc))
 _proto("mpsort_util_mem_info", None, c_int, ctypes.POINTER(c_size_t), ctypes.POINTER(c_size_t))
 
 

@@ -787,6 +787,27 @@ int mpsk_merge_samples(const void * recv, size_t elsize, size_t offset, uint32_t
     return 0;
 }
 
+/* the samples in (key, run, position) order: same contract as the kernel, as a p-way merge of the runs' sorted lists */
+int mpsk_merge_rank_samples(const uint64_t * skeys, uint32_t p, const uint32_t * sstart, uint64_t * sorted_skeys,
+        uint32_t * sorted_sid, mpsk_stream_t stream)
+{
+    uint32_t head[64], r, o;
+    (void) stream;
+    if (p > 32) return 1;
+    if (sstart[p] == 0) return 0;
+    LAUNCHED();
+    for (r = 0; r < p; r++) head[r] = sstart[r];
+    for (o = 0; o < sstart[p]; o++) {
+        int best = -1;
+        for (r = 0; r < p; r++)
+            if (head[r] < sstart[r + 1] && (best < 0 || skeys[head[r]] < skeys[head[best]])) best = (int) r;
+        sorted_skeys[o] = skeys[head[best]];
+        sorted_sid[o] = head[best];
+        head[best]++;
+    }
+    return 0;
+}
+
 int mpsk_merge_runs(const void * recv, void * out, size_t elsize, size_t offset, uint32_t width, uint32_t nwords, int is_signed,
         uint32_t p, uint32_t S, uint32_t k, const uint32_t * rdispl, const uint32_t * sstart,
         const uint64_t * sorted_skeys, const uint32_t * sorted_sid, uint32_t ntiles, uint32_t * cut, uint32_t * overflow,

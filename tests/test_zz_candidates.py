@@ -2,7 +2,6 @@
 at hand (end of round 1). They run only with MPSORT_TEST_CANDIDATES=1, so that the default suite
 states what the shipped paths do; tools/candidates_ab.sh runs them and times each candidate.
 
-  MPSORT_MERGE_BUCKET=1   one-round bucket merge of the received runs (merge_tile_bucket_kernel)
   MPSORT_PACK_PIPELINE=1  index mode: pack of exchange part q+1 beside the transfer of part q
   MPSORT_HYBRID_DEPTH5=1  five high-digit passes when four leave long runs of equal high parts
   MPSORT_FUSED_PACK=1     index mode: gather by sorted index + peer stores in one kernel (needs >= 2 GPUs)
@@ -46,15 +45,14 @@ for p, n, E, kind, signed in ((4, 60000, 16, 0, 0), (8, 40000, 16, 1, 0), (3, 50
         return C.last_stats(comm.handle, p)
     stats = mpsort.run_local(p, work)
     good = all(np.array_equal(outs[r], exp[r]) for r in range(p))
-    print("p", p, "E", E, "kind", kind, "->", good, "merge tiles", [s["second_sort_merge_tiles"] for s in stats],
-          "to the rounds", [s["merge_bucket_fallback_tiles"] for s in stats])
+    print("p", p, "E", E, "kind", kind, "->", good, "merge tiles", [s["second_sort_merge_tiles"] for s in stats])
     ok &= good and all(s["second_sort_merge_tiles"] > 0 for s in stats)
 print("CANDIDATE OK" if ok else "CANDIDATE FAILED")
 sys.exit(0 if ok else 1)
 """
 
 
-@pytest.mark.parametrize("switch", ["MPSORT_MERGE_BUCKET", "MPSORT_PEER_SPLITTER"])
+@pytest.mark.parametrize("switch", ["MPSORT_PEER_SPLITTER"])
 def test_candidate_matches_oracle(switch):
     """bit-exact against the oracle on 2-8 rank threads, 16/24/48-byte records, all three key kinds"""
     env = dict(os.environ, **{switch: "1"})
@@ -90,7 +88,7 @@ mask = (1 << 64) - 1
 ok = (sum(x[0] for x in res) & mask) == (sum(x[1] for x in res) & mask) and all(x[2] == 0 for x in res)
 ok = ok and all(res[r - 1][4] <= res[r][3] for r in range(1, p))
 print("phases", [x[5]["exchange_phases"] for x in res], "merge tiles", [x[5]["second_sort_merge_tiles"] for x in res],
-      "to the rounds", [x[5]["merge_bucket_fallback_tiles"] for x in res], "record mode", [x[5]["record_mode"] for x in res],
+      "record mode", [x[5]["record_mode"] for x in res],
       "passes", [x[5]["first_sort_passes"] for x in res])
 ok = ok and all(x[5]["exchange_phases"] == 2 for x in res)
 if %(passes)d:
@@ -103,12 +101,10 @@ sys.exit(0 if ok else 1)
 
 @pytest.mark.parametrize("E,kind,extra", [(48, 2, {"MPSORT_PACK_PIPELINE": "1"}),
                                           (24, 3, {"MPSORT_PACK_PIPELINE": "1"}),
-                                          (16, 0, {"MPSORT_MERGE_BUCKET": "1"}),
-                                          (48, 2, {"MPSORT_MERGE_BUCKET": "1", "MPSORT_PACK_PIPELINE": "1"}),
                                           (16, 0, {"MPSORT_PEER_SPLITTER": "1"})])
 def test_candidates_at_2_22_records_per_rank_by_properties(E, kind, extra):
     """4 rank threads x 2^22 records, exchange in two parts: global order, tie order (tags), checksum
-    of checksums -- with the pipelined pack (index mode) and / or the bucket merge switched on"""
+    of checksums -- with the pipelined pack (index mode) or the peer splitter kernel switched on"""
     env = dict(os.environ, MPSORT_EXCHANGE_PHASES="2", **extra)
     rc = subprocess.run([sys.executable, "-c", WORKER_PROPS % {"root": ROOT, "E": E, "kind": kind, "log2n": 22, "passes": 0}],
                         env=env, timeout=900, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)

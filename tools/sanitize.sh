@@ -10,13 +10,13 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 CS=${COMPUTE_SANITIZER:-/usr/local/cuda/bin/compute-sanitizer}
 # small inputs only: record mode + hybrid needs 2^22 records (one case), everything else a few thousand
-SEL='test_radix_sort_desc_matches_oracle or test_radix_sort_desc_stable_on_duplicates or test_golden_vectors or test_second_sort_merge_path or test_distributed_sort_other_key_shapes or test_all_empty_and_single_rank or test_record_mode_bare_8_byte_keys or test_range_compression'
-for TOOL in memcheck racecheck synccheck initcheck; do
+SEL=${SEL:-'test_radix_sort_desc_matches_oracle or test_radix_sort_desc_stable_on_duplicates or test_golden_vectors or test_second_sort_merge_path or test_distributed_sort_other_key_shapes or test_all_empty_and_single_rank or test_record_mode_bare_8_byte_keys or test_range_compression'}
+for TOOL in ${TOOLS:-memcheck racecheck synccheck initcheck}; do
   LOG=gpurun_out/sanitize_$TOOL.log
   EXTRA=""
   [ "$TOOL" = memcheck ] && EXTRA="--leak-check full"
   [ "$TOOL" = initcheck ] && EXTRA="--track-unused-memory no"
-  timeout 1500 $CS --tool $TOOL $EXTRA --target-processes all --error-exitcode 66 --log-file $LOG \
+  timeout ${SANITIZE_TIMEOUT:-1500} $CS --tool $TOOL $EXTRA --target-processes all --error-exitcode 66 --log-file $LOG \
       python -m pytest tests/test_gpu_parity.py -q -x -m gpu -k "$SEL" > gpurun_out/sanitize_$TOOL.pytest.log 2>&1
   echo "== $TOOL: exit $? ; $(grep -c 'ERROR SUMMARY' $LOG 2>/dev/null) summaries ; $(grep 'ERROR SUMMARY' $LOG 2>/dev/null | sort | uniq -c | tr '\n' ';')"
   tail -2 gpurun_out/sanitize_$TOOL.pytest.log

@@ -19,7 +19,12 @@ comm = lib.mpsort_comm_self(0)
 desc = C.RadixDesc(0, 8, 1, 1 if kind == 2 else 0, 0)
 din = lib.mpsort_util_dev_malloc(0, n * E)
 dout = lib.mpsort_util_dev_malloc(0, n * E)
-lib.mpsort_util_generate(comm, din, n, E, kind, 0x5EED0001)
+# SWEEP_AS="r,p": the records rank r of p would hold (mostly-sorted keys then span the range of a p-GPU run)
+if os.environ.get("SWEEP_AS"):
+    r_, p_ = [int(x) for x in os.environ["SWEEP_AS"].split(",")]
+    lib.mpsort_util_generate_as(comm, din, n, E, kind, 0x5EED0001, r_, p_)
+else:
+    lib.mpsort_util_generate(comm, din, n, E, kind, 0x5EED0001)
 for _ in range(2):
     lib.mpsort_mpi_newarray_desc_impl(din, n, dout, n, E, ctypes.byref(desc), comm, 0, b"sweep")
 lib.mpsort_util_kernel_timing(comm, 1)
@@ -33,6 +38,8 @@ lib.mpsort_util_event_record(comm, e1)
 ms = lib.mpsort_util_event_elapsed_ms(comm, e0, e1) / K
 kt = C.kernel_times(comm)
 bad = lib.mpsort_util_check_sorted(comm, dout, n, E, ctypes.byref(desc), 1 if E >= 16 else 0, 8, None)
-print("%-28s n=2^%d E=%d kind=%d  step %.3f ms  %.2f Grec/s  bad=%d  | " % (
-    os.path.basename(os.environ.get("MPSORT_LIB", "default")), log2n, E, kind, ms, n / ms / 1e6, bad) +
+tag = " ".join("%s=%s" % (k[7:], v) for k, v in sorted(os.environ.items()) if k.startswith("MPSORT_") and k != "MPSORT_LIB")
+st = C.last_stats(comm, 1)
+print("%-28s n=2^%d E=%d kind=%d %s passes=%d hybrid=%d step %.3f ms  %.2f Grec/s  bad=%d  | " % (
+    os.path.basename(os.environ.get("MPSORT_LIB", "default")), log2n, E, kind, tag, st["first_sort_passes"], st["hybrid"], ms, n / ms / 1e6, bad) +
     "  ".join("%s %.3f/%d" % (k, v[0] / K, v[1] // K) for k, v in kt.items() if v[1]))
