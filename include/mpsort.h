@@ -159,6 +159,12 @@ void mpsort_mpi_newarray_desc_impl(void * base, size_t nmemb,
 void radix_sort_desc(void * base, size_t nmemb, size_t size,
         const struct mpsort_radix_desc * desc, int device);
 
+/* radix_sort_desc and radix_sort have no communicator argument: they use a size-1 communicator
+ * (stream + grow-only device arena, several times nmemb * size after a large call) cached per
+ * calling thread and device. mpsort_release_cached() destroys the calling thread's cached
+ * communicators and gives their device memory back; a thread that exits releases its own. */
+void mpsort_release_cached(void);
+
 /* ------------------------------------------------------------------------- */
 /* The reference's OWN signatures (mpsort.h:1-4, :25-47), for callers that keep a host
  * radix() callback: e.g. test-issue7.c:12-17 builds its key from two separate fields,

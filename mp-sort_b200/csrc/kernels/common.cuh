@@ -33,6 +33,15 @@ extern "C" uint64_t mpsk_launch_count(int reset)
     return (uint64_t) v;
 }
 
+/* splitmix64 finaliser: the hash of the predictor's table */
+__host__ __device__ __forceinline__ u64 mset_hash64(u64 x)
+{
+    u64 z = x + 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
 __device__ __forceinline__ u32 lanemask_lt()
 {
     u32 m;

@@ -29,6 +29,9 @@ __device__ __forceinline__ u64 rec_key(const uint4 & it, u32 khi, u64 flip)
 #ifndef FIX_MINBLOCKS
 #define FIX_MINBLOCKS 8
 #endif
+#ifndef FIX_PREFETCH_TILES
+#define FIX_PREFETCH_TILES 0
+#endif
 
 /* what one entry of the compacted list (a position that is not a run of its own) has to do:
  * returns the position its record moves to (0xffffffff: it stays) and reads the record */
@@ -83,7 +86,7 @@ __device__ __forceinline__ u32 fixup_votes(const u32 * s_head, u32 cnt, u32 w)
 template <typename ITEM, bool KHI>
 __global__ void __launch_bounds__(FIX_THREADS, FIX_MINBLOCKS)
 fixup_rec_kernel(ITEM * __restrict__ recs, u32 n, u64 flip, u32 lobits,
-                   u32 * __restrict__ worklist, u32 * __restrict__ nwork, u32 cap)
+                   u32 * __restrict__ worklist, u32 * __restrict__ nwork, u32 cap, u32 pf_dist)
 {
     constexpr int CAP = FIX_T + FIX_HALO;
     constexpr int NW = CAP / 32;                  /* head words that describe positions of this tile */
@@ -115,6 +118,15 @@ fixup_rec_kernel(ITEM * __restrict__ recs, u32 n, u64 flip, u32 lobits,
     constexpr u32 W = sizeof(ITEM) / 8;                            /* u64 words per record */
     const u64 * keys = (const u64 *) recs + (KHI ? 1 : 0);       /* key of record i at keys[W*i] */
 
+    /* tile + pf_dist is asked into L2 while this one is worked on (cp.async.bulk.prefetch.L2) */
+    if (pf_dist && tid == 0) {
+        const u64 first = ((u64) blockIdx.x + pf_dist) * (u64) FIX_T;
+        if (first < (u64) n) {
+            const u64 left = ((u64) n - first) * sizeof(ITEM);
+            const u32 bytes = (u32) (left < (u64) FIX_T * sizeof(ITEM) ? (left & ~15ULL) : (u64) FIX_T * sizeof(ITEM));
+            if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(recs + first), "r"(bytes) : "memory");
+        }
+    }
     {
         u64 tmp[NLD];
 #pragma unroll
@@ -223,15 +235,17 @@ extern "C" int mpsk_fixup_rec(void * recs, size_t n, size_t elsize, int key_in_h
 {
     if (n == 0) return 0;
     const size_t tiles = (n + FIX_T - 1) / FIX_T;
+    static int pf = -1;                  /* MPSORT_PREFETCH_FIXUP_TILES: eight CTAs per SM, a wave is 1184 tiles */
+    if (pf < 0) { const char * e = getenv("MPSORT_PREFETCH_FIXUP_TILES"); pf = e ? atoi(e) : FIX_PREFETCH_TILES; if (pf < 0) pf = 0; }
     if (elsize == 8)
         fixup_rec_kernel<u64, false><<<(unsigned) tiles, FIX_THREADS, 0, (cudaStream_t) stream>>>(
-            (u64 *) recs, (u32) n, (u64) flip, lobits, worklist, nwork, cap);
+            (u64 *) recs, (u32) n, (u64) flip, lobits, worklist, nwork, cap, (u32) pf);
     else if (key_in_high)
         fixup_rec_kernel<uint4, true><<<(unsigned) tiles, FIX_THREADS, 0, (cudaStream_t) stream>>>(
-            (uint4 *) recs, (u32) n, (u64) flip, lobits, worklist, nwork, cap);
+            (uint4 *) recs, (u32) n, (u64) flip, lobits, worklist, nwork, cap, (u32) pf);
     else
         fixup_rec_kernel<uint4, false><<<(unsigned) tiles, FIX_THREADS, 0, (cudaStream_t) stream>>>(
-            (uint4 *) recs, (u32) n, (u64) flip, lobits, worklist, nwork, cap);
+            (uint4 *) recs, (u32) n, (u64) flip, lobits, worklist, nwork, cap, (u32) pf);
     CUDA_LAUNCH_CHECK();
     return 0;
 }
@@ -246,46 +260,54 @@ extern "C" int mpsk_fixup_extents(const void * recs, size_t n, size_t elsize, in
     return 0;
 }
 
-/* predictor: the high parts of `s` evenly spaced records, as bare u64 "records" */
-__global__ void sample_prefix_kernel(const u64 * __restrict__ recs, u32 W, size_t n, u32 s, u32 khi, u64 flip, u32 lobits,
-                                     u64 * __restrict__ out)
-{
-    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= s) return;
-    const size_t pos = (size_t) (((unsigned __int128) i * n) / s);
-    out[i] = rec_key_at(recs, pos, W, khi, flip) >> lobits;
-}
+/* predictor: equal PAIRS among the high parts of `s` evenly spaced records, for up to two values of lobits
+ * at once. Every sample is inserted into an open-addressing hash table (keys + counts, in L2): the count its
+ * slot held before is the number of equal samples inserted earlier, and those sum to k(k-1)/2 per value
+ * whatever the order. One launch; the sort of the samples that used to do this took a dozen and a host
+ * round trip. */
+struct PredArgs { u32 lobits[2]; u32 nl; };
 
-/* number of equal PAIRS in a sorted array: sum over values of k(k-1)/2 */
-__global__ void count_equal_pairs_kernel(const u64 * __restrict__ sorted, u32 s, u64 * __restrict__ count)
+__global__ void __launch_bounds__(256)
+prefix_pairs_kernel(const u64 * __restrict__ recs, u32 W, size_t n, u32 s, u32 khi, u64 flip, PredArgs a,
+                    u64 * __restrict__ table, u32 log2t, u64 * __restrict__ pairs)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    u64 pairs = 0;
+    const u64 tsize = 1ULL << log2t, mask = tsize - 1;
+    u64 found[2] = { 0, 0 };
     if (i < s) {
-        const u64 v = sorted[i];
-        u32 lo = 0, hi = i;                               /* first index holding v */
-        while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (sorted[mid] < v) lo = mid + 1; else hi = mid; }
-        pairs = i - lo;
+        const size_t pos = (size_t) (((unsigned __int128) i * n) / s);
+        const u64 key = rec_key_at(recs, pos, W, khi, flip);
+        for (u32 j = 0; j < a.nl; j++) {
+            const u64 hi = (a.lobits[j] >= 64 ? 0ULL : key >> a.lobits[j]) + 1ULL;      /* 0 = empty slot */
+            unsigned long long * tk = (unsigned long long *) table + (size_t) j * 2 * tsize;
+            unsigned long long * tc = tk + tsize;
+            u64 h = mset_hash64(hi) & mask;
+            for (u64 probe = 0; probe < tsize; probe++) {
+                const unsigned long long prev = atomicCAS(&tk[h], 0ULL, (unsigned long long) hi);
+                if (prev == 0ULL || prev == hi) { found[j] = atomicAdd(&tc[h], 1ULL); break; }
+                h = (h + 1) & mask;
+            }
+        }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) pairs += __shfl_xor_sync(FULL_MASK, pairs, o);
-    if ((threadIdx.x & 31) == 0 && pairs) atomicAdd(count, pairs);
+    for (int j = 0; j < 2; j++) {
+        u64 v = found[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd((unsigned long long *) &pairs[j], (unsigned long long) v);
+    }
 }
 
-extern "C" int mpsk_sample_prefix_rec(const void * recs, size_t n, size_t elsize, uint32_t s, int key_in_high, uint64_t flip,
-        uint32_t lobits, uint64_t * out, mpsk_stream_t stream)
+extern "C" int mpsk_prefix_pairs(const void * recs, size_t n, size_t elsize, uint32_t s, int key_in_high, uint64_t flip,
+        const uint32_t * lobits, uint32_t nl, uint64_t * table, uint32_t log2_tsize, uint64_t * pairs, mpsk_stream_t stream)
 {
-    if (s == 0) return 0;
-    sample_prefix_kernel<<<(s + 255) / 256, 256, 0, (cudaStream_t) stream>>>(
-        (const u64 *) recs, (u32) (elsize / 8), n, s, (key_in_high && elsize == 16) ? 1u : 0u, (u64) flip, lobits, (u64 *) out);
-    CUDA_LAUNCH_CHECK();
-    return 0;
-}
-
-extern "C" int mpsk_count_equal_pairs(const uint64_t * sorted, uint32_t s, uint64_t * count, mpsk_stream_t stream)
-{
-    if (s == 0) return 0;
-    count_equal_pairs_kernel<<<(s + 255) / 256, 256, 0, (cudaStream_t) stream>>>((const u64 *) sorted, s, (u64 *) count);
+    if (s == 0 || nl == 0 || n == 0) return 0;
+    if (nl > 2 || ((size_t) 1 << log2_tsize) < 2 * (size_t) s) return (int) cudaErrorInvalidValue;
+    PredArgs a;
+    a.nl = nl; a.lobits[0] = lobits[0]; a.lobits[1] = nl > 1 ? lobits[1] : 0;
+    prefix_pairs_kernel<<<(s + 255) / 256, 256, 0, (cudaStream_t) stream>>>(
+        (const u64 *) recs, (u32) (elsize / 8), n, s, (key_in_high && elsize == 16) ? 1u : 0u, (u64) flip, a,
+        (u64 *) table, log2_tsize, (u64 *) pairs);
     CUDA_LAUNCH_CHECK();
     return 0;
 }

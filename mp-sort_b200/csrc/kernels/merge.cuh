@@ -126,6 +126,23 @@ merge_bounds_kernel(const unsigned char * __restrict__ recv, KeyDesc d, bool fas
     }
 }
 
+/* lane r < p asks the bulk-copy engine to bring sub-range r of tile tt into L2 (a hint: the range is
+ * shrunk to 16-byte alignment on both sides) */
+__device__ __forceinline__ void merge_prefetch_tile(const unsigned char * recv, size_t elsize, const MergeRuns & m,
+        const u32 * __restrict__ cut, u32 tt, u32 ntiles, u32 r, u32 pf_dist)
+{
+    if (pf_dist == 0 || tt >= ntiles || r >= m.p) return;
+    const u32 c0 = cut[tt * m.p + r], c1 = cut[(tt + 1) * m.p + r];
+    if (c1 <= c0) return;
+    uintptr_t a0 = (uintptr_t) (recv + ((size_t) m.rdispl[r] + c0) * elsize);
+    uintptr_t a1 = (uintptr_t) (recv + ((size_t) m.rdispl[r] + c1) * elsize);
+    a0 = (a0 + 15) & ~(uintptr_t) 15;
+    a1 &= ~(uintptr_t) 15;
+    if (a1 <= a0) return;
+    const u32 bytes = (u32) (a1 - a0);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a0), "r"(bytes) : "memory");
+}
+
 /* shared-memory index with one pad slot per 8 items: a thread's 8 consecutive outputs
  * are 64 bytes apart from its neighbour's, which would be a 16-way bank conflict */
 #define MPD(i) ((i) + ((i) >> 3))
@@ -136,7 +153,8 @@ merge_bounds_kernel(const unsigned char * __restrict__ recv, KeyDesc d, bool fas
 template <typename V, bool FAST8, bool LPR1>
 __global__ void __launch_bounds__(MPSK_MERGE_THREADS, 2)
 merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, MergeRuns m,
-                  const u32 * __restrict__ cut, unsigned char * __restrict__ out, u32 * __restrict__ overflow)
+                  const u32 * __restrict__ cut, unsigned char * __restrict__ out, u32 * __restrict__ overflow,
+                  u32 ntiles, u32 pf_dist)
 {
     constexpr int VT = MPSK_MERGE_TILE / MPSK_MERGE_THREADS;      /* items per thread */
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -166,6 +184,10 @@ merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, MergeRuns 
         if (tid < p) { seqoff[tid] = incl - len; srcbase[tid] = m.rdispl[tid] + c0; }
         if (tid == p - 1) seqoff[p] = incl;
         if (tid == 0) s_outstart = sum0;
+    } else if (tid < 64) {
+        /* the p sub-ranges of tile t + pf_dist are asked into L2 (cp.async.bulk.prefetch.L2, one lane per
+         * run): this kernel waits for its scattered key loads more than for anything else */
+        merge_prefetch_tile(recv, d.elsize, m, cut, t + pf_dist, ntiles, tid - 32, pf_dist);
     }
     __syncthreads();
     const u32 cnt = seqoff[p];
@@ -279,7 +301,8 @@ merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, MergeRuns 
 template <bool KHI>
 __global__ void __launch_bounds__(MPSK_MERGE16_THREADS, 3)
 merge_tile_rec16_kernel(const uint4 * __restrict__ recv, u64 flip, MergeRuns m,
-                        const u32 * __restrict__ cut, uint4 * __restrict__ out, u32 * __restrict__ overflow)
+                        const u32 * __restrict__ cut, uint4 * __restrict__ out, u32 * __restrict__ overflow,
+                        u32 ntiles, u32 pf_dist)
 {
     constexpr int VT = MPSK_MERGE16_TILE / MPSK_MERGE16_THREADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -307,6 +330,8 @@ merge_tile_rec16_kernel(const uint4 * __restrict__ recv, u64 flip, MergeRuns m,
         if (tid < p) { seqoff[tid] = incl - len; srcbase[tid] = m.rdispl[tid] + c0; }
         if (tid == p - 1) seqoff[p] = incl;
         if (tid == 0) s_outstart = sum0;
+    } else if (tid < 64) {
+        merge_prefetch_tile((const unsigned char *) recv, 16, m, cut, t + pf_dist, ntiles, tid - 32, pf_dist);
     }
     __syncthreads();
     const u32 cnt = seqoff[p];
@@ -429,6 +454,17 @@ extern "C" int mpsk_merge_rank_samples(const uint64_t * skeys, uint32_t p, const
     return 0;
 }
 
+/* MPSORT_PREFETCH_MERGE_TILES=d: tile + d is asked into L2 when a tile starts (two or three CTAs per SM) */
+#ifndef MPSK_MERGE_PREFETCH_TILES
+#define MPSK_MERGE_PREFETCH_TILES 0
+#endif
+static u32 merge_prefetch_tiles()
+{
+    static int v = -1;
+    if (v < 0) { const char * e = getenv("MPSORT_PREFETCH_MERGE_TILES"); v = e ? atoi(e) : MPSK_MERGE_PREFETCH_TILES; if (v < 0) v = 0; }
+    return (u32) v;
+}
+
 template <typename V>
 static int launch_merge_tiles(const void * recv, KeyDesc d, bool fast8, const MergeRuns & m, const u32 * cut,
                               void * out, u32 * overflow, u32 ntiles, cudaStream_t stream)
@@ -440,7 +476,7 @@ static int launch_merge_tiles(const void * recv, KeyDesc d, bool fast8, const Me
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
         if (e != cudaSuccess) return (int) e; \
         kern<<<ntiles, MPSK_MERGE_THREADS, smem, stream>>>((const unsigned char *) recv, d, m, cut, \
-                                                           (unsigned char *) out, overflow); } while (0)
+                                                           (unsigned char *) out, overflow, ntiles, merge_prefetch_tiles()); } while (0)
     if (fast8 && lpr1) MERGE_LAUNCH(true, true);
     else if (fast8) MERGE_LAUNCH(true, false);
     else if (lpr1) MERGE_LAUNCH(false, true);
@@ -475,12 +511,12 @@ extern "C" int mpsk_merge_runs(const void * recv, void * out, size_t elsize, siz
             auto kern = merge_tile_rec16_kernel<true>;
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return (int) e;
-            kern<<<ntiles, MPSK_MERGE16_THREADS, smem, stream>>>((const uint4 *) recv, flip, m, cut, (uint4 *) out, overflow);
+            kern<<<ntiles, MPSK_MERGE16_THREADS, smem, stream>>>((const uint4 *) recv, flip, m, cut, (uint4 *) out, overflow, ntiles, merge_prefetch_tiles());
         } else {
             auto kern = merge_tile_rec16_kernel<false>;
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return (int) e;
-            kern<<<ntiles, MPSK_MERGE16_THREADS, smem, stream>>>((const uint4 *) recv, flip, m, cut, (uint4 *) out, overflow);
+            kern<<<ntiles, MPSK_MERGE16_THREADS, smem, stream>>>((const uint4 *) recv, flip, m, cut, (uint4 *) out, overflow, ntiles, merge_prefetch_tiles());
         }
         CUDA_LAUNCH_CHECK();
         return 0;

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(THREADS, MPSK_SWEEP_MINBLOCKS)
 onesweep_kernel(const u64 * __restrict__ kin, const u32 * __restrict__ vin,
                 u64 * __restrict__ kout, u32 * __restrict__ vout,
                 u32 n, u32 shift, const u32 * __restrict__ bins,
-                LookbackBufs lb, u32 * ticket)
+                LookbackBufs lb, u32 * ticket, u32 pf_dist)
 {
     typedef SweepCfg<THREADS, IPT> Cfg;
     constexpr int TILE = Cfg::TILE;
@@ -209,6 +209,16 @@ onesweep_kernel(const u64 * __restrict__ kin, const u32 * __restrict__ vin,
         if (tid == 0) s_misc[0] = atomicAdd(ticket, 1u);
         __syncthreads();
         tile = s_misc[0];
+    }
+    /* tile + pf_dist is asked into L2 (see onesweep_rec_kernel): its keys, and its values unless they are 0..n-1 */
+    if (pf_dist && tid == 0) {
+        const u64 first = ((u64) tile + pf_dist) * (u64) TILE;
+        if (first < (u64) n) {
+            const u64 left = (u64) n - first, items = left < (u64) TILE ? left : (u64) TILE;
+            const u32 kb = (u32) ((items * 8) & ~15ULL), vb = (u32) ((items * 4) & ~15ULL);
+            if (kb) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(kin + first), "r"(kb) : "memory");
+            if (!IOTA && vb) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(vin + first), "r"(vb) : "memory");
+        }
     }
     const u32 tile_base = tile * (u32) TILE;
     const u32 remaining = n - tile_base;
@@ -357,6 +367,17 @@ static int sweep_ticket_tiles()
     return v;
 }
 
+/* index passes: MPSORT_PREFETCH_INDEX_TILES (tiles are 6144 pairs, two CTAs per SM: a wave is 296 tiles) */
+#ifndef MPSK_SWEEP_PREFETCH_TILES
+#define MPSK_SWEEP_PREFETCH_TILES 0
+#endif
+static u32 sweep_prefetch_index_tiles()
+{
+    static int v = -1;
+    if (v < 0) { const char * e = getenv("MPSORT_PREFETCH_INDEX_TILES"); v = e ? atoi(e) : MPSK_SWEEP_PREFETCH_TILES; if (v < 0) v = 0; }
+    return (u32) v;
+}
+
 extern "C" size_t mpsk_onesweep_tile_items(void) { return TheSweep::TILE; }
 
 extern "C" size_t mpsk_onesweep_scratch_bytes(size_t n)
@@ -388,7 +409,7 @@ extern "C" int mpsk_onesweep_pass(const uint64_t * kin, const uint32_t * vin,
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TheSweep::SMEM); \
         if (e != cudaSuccess) return (int) e; \
         kern<<<(unsigned) ntiles, MPSK_SWEEP_THREADS, TheSweep::SMEM, stream>>>( \
-            (const u64 *) kin, vin, (u64 *) kout, vout, (u32) n, (u32) shift, bins, lb, ticket); } while (0)
+            (const u64 *) kin, vin, (u64 *) kout, vout, (u32) n, (u32) shift, bins, lb, ticket, sweep_prefetch_index_tiles()); } while (0)
     const bool tickets = sweep_ticket_tiles() != 0;
     if (vin == NULL) { if (tickets) SWEEP_LAUNCH(true, true); else SWEEP_LAUNCH(true, false); }
     else { if (tickets) SWEEP_LAUNCH(false, true); else SWEEP_LAUNCH(false, false); }

@@ -25,8 +25,11 @@
 #ifndef MPSK_REC_TMA_STORE
 #define MPSK_REC_TMA_STORE 1
 #endif
+/* tile + 148 is asked into L2 when a tile starts (one CTA wave of 3 per SM is 444 tiles): a record pass
+ * takes 1.91 ms without, 1.78 ms with 148 or 296, 1.80 with 444, 1.87 with 592 and 2.05 with 888 and more
+ * (profiles/r02_call2_static_prefetch_fixup_merge.log) */
 #ifndef MPSK_REC_PREFETCH_TILES
-#define MPSK_REC_PREFETCH_TILES 0
+#define MPSK_REC_PREFETCH_TILES 148
 #endif
 
 template <int THREADS, int IPT, int ITEMBYTES>

@@ -77,7 +77,7 @@ void MPIU_Set_verbose_malloc(mpsort_comm_t comm)
 static const char * slot_names[MPS_NSLOTS] = {
     "din", "dout", "keywords", "keys_b", "keys_a", "idx_a", "idx_b", "sortedkeys",
     "hist", "lookback", "sendbuf", "recvbuf", "splitters", "stage", "stage2", "misc",
-    "merge_samples", "merge_cuts", "merge_sorted_samples", "merge_sample_ids"
+    "merge_samples", "merge_cuts", "merge_sorted_samples", "merge_sample_ids", "predictor"
 };
 
 void * mps_arena_get(struct mpsort_comm * c, int slot, size_t bytes)
@@ -291,17 +291,30 @@ int mpsort_comm_init_local_group(int size, const int * devices, mpsort_comm_t * 
         comms[i] = comm_alloc(MPS_T_LOCAL, i, size, devices[i]);
         comms[i]->grp = g;
     }
-    /* kernels of one rank read buffers of the others: enable peer access between
-     * distinct devices (same-device ranks need nothing) */
+    /* kernels of one rank read buffers of the others (the in-process all-reduce, the pull
+     * exchange): peer access between distinct devices is a REQUIREMENT of this transport, so a pair
+     * that cannot have it is an error here, at construction, not an illegal-address fault in the
+     * middle of a sort (same-device ranks need nothing) */
     for (i = 0; i < size; i++) {
         for (j = 0; j < size; j++) {
             if (devices[i] == devices[j]) continue;
             int can = 0;
-            cudaDeviceCanAccessPeer(&can, devices[i], devices[j]);
-            if (!can) continue;
-            cudaSetDevice(devices[i]);
-            cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
-            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            cudaError_t e = cudaDeviceCanAccessPeer(&can, devices[i], devices[j]);
+            if (e == cudaSuccess && can) {
+                cudaSetDevice(devices[i]);
+                e = cudaDeviceEnablePeerAccess(devices[j], 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            } else if (e == cudaSuccess) e = cudaErrorPeerAccessUnsupported;
+            if (e != cudaSuccess) {
+                fprintf(stderr, "MPSort: devices %d and %d of an in-process group cannot access each other's memory (%s); "
+                                "use one process per GPU (mpsort_comm_init_rank)\n", devices[i], devices[j], cudaGetErrorString(e));
+                cudaGetLastError();
+                for (i = 0; i < size; i++) { comms[i]->grp = NULL; comms[i]->kind = MPS_T_SELF; mpsort_comm_destroy(comms[i]); comms[i] = NULL; }
+                pthread_barrier_destroy(&g->barrier);
+                pthread_mutex_destroy(&g->lock);
+                free(g);
+                return -3;
+            }
         }
     }
     return 0;

@@ -337,33 +337,31 @@ static void rec16_passes(struct mpsort_comm * c, const void * src, size_t n, siz
 static void local_sort(struct mpsort_comm * c, const void * dbase, size_t n, size_t elsize,
         const struct mpsort_radix_desc * desc, int want_keys, int allow_rebase, struct sorted_view * out);
 
-/* Does the high part (key >> lobits) look nearly distinct? Sorts 65536 evenly spaced
- * high parts and counts equal pairs c: E[c] = s^2/(2n) * (mean length of the run a
- * random record sits in). The run fix-up costs that many comparisons per record, so
- * the hybrid is taken while the estimate stays below 16. */
-static int hybrid_predictor(struct mpsort_comm * c, const void * dbase, size_t n, size_t E,
-        const struct mpsort_radix_desc * desc, uint32_t lobits, double * mean_run)
+/* The predictor of the hybrid sort. Does the high part (key >> lobits) look nearly distinct?
+ * mpsk_prefix_pairs counts the equal PAIRS c among the high parts of 65536 evenly spaced
+ * records (a hash table in L2, one launch, for up to two values of lobits at once):
+ * E[c] = s^2/(2n) * (mean length of the run a random record sits in, minus one).
+ * The run fix-up costs about that many comparisons per record. */
+#define MPS_PRED_LOG2_TABLE 18u
+struct predictor { uint32_t lobits[2]; int nl; uint64_t * d_pairs; };
+
+static void predictor_launch(struct mpsort_comm * c, const void * dbase, size_t n, size_t E,
+        const struct mpsort_radix_desc * desc, struct predictor * pr)
 {
     const uint64_t flip = desc->is_signed ? (1ULL << 63) : 0ULL;
-    const uint32_t s = MPS_HYBRID_SAMPLES;
-    uint64_t * samp = (uint64_t *) mps_arena_get(c, MPS_S_MERGE_SAMP, (size_t) s * sizeof(uint64_t));
-    uint64_t * dcount = (uint64_t *) mps_arena_get(c, MPS_S_MISC, 256);
-    const int saved = c->kt.force_cls;
-    c->kt.force_cls = MPS_K_HYBRID;
-    KERN_T(c, MPS_K_HYBRID, mpsk_sample_prefix_rec(dbase, n, E, s, desc->offset == 8, flip, lobits, samp, c->stream));
-    struct sorted_view sv;
-    const struct mpsort_radix_desc sdesc = { 0, 8, 1, 0, 0 };
-    local_sort(c, samp, s, sizeof(uint64_t), &sdesc, 1, 0, &sv);
-    CUDA_OK(c, cudaMemsetAsync(dcount, 0, sizeof(uint64_t), c->stream));
-    KERN_T(c, MPS_K_HYBRID, mpsk_count_equal_pairs(sv.skeys, s, dcount, c->stream));
-    c->kt.force_cls = saved;
-    uint64_t * h = (uint64_t *) mps_host_stage(c, sizeof(uint64_t));
-    CUDA_OK(c, cudaMemcpyAsync(h, dcount, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_OK(c, cudaStreamSynchronize(c->stream));
-    const double limit = 8.0 * (double) s * (double) s / (double) n;
-    /* pairs = s^2/(2n) * mean run length */
-    if (mean_run) *mean_run = (double) *h * 2.0 * (double) n / ((double) s * (double) s);
-    return (double) *h <= (limit < 8.0 ? 8.0 : limit);
+    const size_t tbytes = (size_t) pr->nl * 2 * ((size_t) 1 << MPS_PRED_LOG2_TABLE) * sizeof(uint64_t);
+    uint64_t * tab = (uint64_t *) mps_arena_get(c, MPS_S_PRED, tbytes + 64);
+    pr->d_pairs = tab + tbytes / sizeof(uint64_t);
+    CUDA_OK(c, cudaMemsetAsync(tab, 0, tbytes + 64, c->stream));
+    KERN_T(c, MPS_K_HYBRID, mpsk_prefix_pairs(dbase, n, E, MPS_HYBRID_SAMPLES, desc->offset == 8, flip, pr->lobits, (uint32_t) pr->nl,
+                                              tab, MPS_PRED_LOG2_TABLE, pr->d_pairs, c->stream));
+}
+
+/* pairs -> estimated mean run length */
+static double predictor_mean_run(uint64_t pairs, size_t n)
+{
+    const double s = (double) MPS_HYBRID_SAMPLES;
+    return 1.0 + (double) pairs * 2.0 * (double) n / (s * s);
 }
 
 static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t n, size_t E,
@@ -389,36 +387,49 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
     const int hybrid_ok = n >= MPS_HYBRID_MIN_ITEMS && !getenv("MPSORT_NO_HYBRID");
     CUDA_OK(c, cudaMemsetAsync(hist, 0, 8 * 256 * sizeof(uint32_t), c->stream));
     CUDA_OK(c, cudaMemsetAsync(ddiff, 0, sizeof(uint64_t), c->stream));
-    /* The hybrid sort only needs the counts of the four most significant digits, and
-     * counting four digits instead of eight makes the histogram pass HBM-bound. A preview
-     * over 4096 evenly spaced keys says whether that is where this input is heading: bytes
-     * that vary in the sample vary in the whole array. */
+    /* The hybrid sort only needs the counts of the four (or five) most significant digits, and
+     * counting four digits instead of eight makes the histogram pass HBM-bound. A preview over
+     * 4096 evenly spaced keys says whether that is where this input is heading (bytes that vary
+     * in the sample vary in the whole array) and which high parts the predictor should look at:
+     * the predictor then runs beside the histogram pass and both are read back together --
+     * two host round trips before the passes instead of five. */
     int have_low = 1;
+    struct predictor pr;
+    memset(&pr, 0, sizeof(pr));
     if (hybrid_ok && !getenv("MPSORT_NO_HIST4")) {
         uint64_t * hd = (uint64_t *) mps_host_stage(c, sizeof(uint64_t));
         KERN_T(c, MPS_K_EXTRACT, mpsk_rec_sample_diff(dbase, n, E, khi, 4096, ddiff, c->stream));
         CUDA_OK(c, cudaMemcpyAsync(hd, ddiff, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
         CUDA_OK(c, cudaMemsetAsync(ddiff, 0, sizeof(uint64_t), c->stream));
         CUDA_OK(c, cudaStreamSynchronize(c->stream));
-        int vary = 0, top4 = 1;
+        int vary = 0, top4 = 1, pd[8];
         for (d = 0; d < 8; d++) {
             const int v = ((*hd >> (8 * d)) & 255u) != 0;
-            vary += v;
+            if (v) pd[vary++] = (int) d;
             if (d >= 4 && !v) top4 = 0;
         }
         if (top4 && vary >= 6) have_low = 0;
+        if (vary >= 6) {
+            /* the high parts the exact digit list will most likely ask about */
+            pr.lobits[pr.nl++] = 8u * (uint32_t) pd[vary - 4];
+            if (vary >= 7) pr.lobits[pr.nl++] = 8u * (uint32_t) pd[vary - 5];
+        }
     }
     if (have_low) KERN_T(c, MPS_K_EXTRACT, mpsk_rec_histograms(dbase, n, E, khi, flip, 0, 8, hist, ddiff, c->stream));
     else KERN_T(c, MPS_K_EXTRACT, mpsk_rec_histograms(dbase, n, E, khi, flip, 4, 4, hist, ddiff, c->stream));
     KERN_T(c, MPS_K_EXTRACT, mpsk_scan_histograms(hist, bins, 8, c->stream));
-    uint32_t * hhist = (uint32_t *) mps_host_stage(c, 8 * 256 * sizeof(uint32_t) + sizeof(uint64_t));
-    CUDA_OK(c, cudaMemcpyAsync(hhist, hist, 8 * 256 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_OK(c, cudaMemcpyAsync(hhist + 8 * 256, ddiff, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    if (pr.nl) predictor_launch(c, dbase, n, E, desc, &pr);
+    const size_t hbytes = 8 * 256 * sizeof(uint32_t);
+    uint32_t * hhist = (uint32_t *) mps_host_stage(c, hbytes + 4 * sizeof(uint64_t));
+    uint64_t * htail = (uint64_t *) ((char *) hhist + hbytes);      /* [0] diff, [1..2] predictor pairs */
+    CUDA_OK(c, cudaMemcpyAsync(hhist, hist, hbytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(htail, ddiff, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    if (pr.nl) CUDA_OK(c, cudaMemcpyAsync(htail + 1, pr.d_pairs, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
     int digits[8], P = 0;
+    uint64_t pairs_of[2] = { htail[1], htail[2] };
     {
-        uint64_t diff;
-        memcpy(&diff, hhist + 8 * 256, sizeof(diff));
+        const uint64_t diff = htail[0];
         for (d = 0; d < 8; d++) if ((diff >> (8 * d)) & 255u) digits[P++] = (int) d;
     }
     out->npasses = (uint32_t) P;
@@ -432,36 +443,32 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
         KERN_T(c, MPS_K_EXTRACT, mpsk_scan_histograms(hist, bins, 8, c->stream)); \
         have_low = 1; } } while (0)
 
-    /* ---- hybrid: four passes over the most significant digits + run fix-up */
+    /* ---- hybrid: passes over the four (or five) most significant digits + run fix-up */
     if (P >= 6 && hybrid_ok) {
+        /* mean run length left by the top four / five digits: from the speculated launch when it asked
+         * the right question, else now (one more round trip; only when the preview missed a varying byte) */
+        uint32_t want[2] = { 8u * (uint32_t) digits[P - 4], P >= 7 ? 8u * (uint32_t) digits[P - 5] : 0u };
+        const int nwant = P >= 7 ? 2 : 1;
+        if (pr.nl < nwant || pr.lobits[0] != want[0] || (nwant == 2 && pr.lobits[1] != want[1])) {
+            pr.nl = nwant; pr.lobits[0] = want[0]; pr.lobits[1] = want[1];
+            predictor_launch(c, dbase, n, E, desc, &pr);
+            uint64_t * h = (uint64_t *) mps_host_stage(c, hbytes + 4 * sizeof(uint64_t)) + hbytes / sizeof(uint64_t);
+            CUDA_OK(c, cudaMemcpyAsync(h + 1, pr.d_pairs, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_OK(c, cudaStreamSynchronize(c->stream));
+            pairs_of[0] = h[1]; pairs_of[1] = h[2];
+        }
+        const double run4 = predictor_mean_run(pairs_of[0], n);
+        const double run5 = nwant == 2 ? predictor_mean_run(pairs_of[1], n) : 1e30;
+        /* A pass costs about what the fix-up of runs nine records longer costs (1.8 ms per pass; fix-up
+         * 1.0 ms for singleton runs, 4.0 ms for runs of 16: profiles/r02_call2_static_prefetch_fixup_merge.log):
+         * a fifth pass pays when it turns long runs into (nearly) singletons -- mostly sorted ids. */
         int H = 4;
-        uint32_t lobits = 8u * (uint32_t) digits[P - H];
-        if (digits[P - H] < 4) ENSURE_LOW_HISTOGRAMS();
-        uint32_t hsave[8 * 256];
-        memcpy(hsave, hhist, sizeof(hsave));
-        double mean_run = 0.0;
-        int yes = hybrid_predictor(c, dbase, n, E, desc, lobits, &mean_run);
-        /* CANDIDATE, off by default (MPSORT_HYBRID_DEPTH5=1; not yet run on a GPU): keys whose four
-         * top digits leave runs of ~16 (mostly sorted ids: fix-up 4.3 ms) are nearly distinct in five;
-         * a fifth pass (1.9 ms) then leaves the fix-up its 1.2 ms. Any depth gives the same bytes. */
-        if (P >= 7 && mean_run > 8.0 && getenv("MPSORT_HYBRID_DEPTH5")) {
-            const uint32_t lobits5 = 8u * (uint32_t) digits[P - 5];
-            double mean_run5 = 0.0;
-            if (hybrid_predictor(c, dbase, n, E, desc, lobits5, &mean_run5) && mean_run5 <= 4.0) {
-                H = 5; lobits = lobits5; yes = 1;
-            }
-        }
-        {
-            /* the predictor's sample sort reused the histogram slot and the host stage:
-             * put the big array's histograms and scanned bins back */
-            uint32_t * hs = (uint32_t *) mps_host_stage(c, sizeof(hsave));
-            memcpy(hs, hsave, sizeof(hsave));
-            CUDA_OK(c, cudaMemcpyAsync(hist, hs, sizeof(hsave), cudaMemcpyHostToDevice, c->stream));
-            KERN_T(c, MPS_K_EXTRACT, mpsk_scan_histograms(hist, bins, 8, c->stream));
-            CUDA_OK(c, cudaStreamSynchronize(c->stream));   /* the stage is reused below */
-        }
-        if (yes && digits[P - H] < 4) ENSURE_LOW_HISTOGRAMS();   /* only ever true for the five-pass depth */
+        if (nwant == 2 && run4 > 10.0 && run5 <= 2.0 && !getenv("MPSORT_NO_HYBRID5")) H = 5;
+        const double run = H == 4 ? run4 : run5;
+        const int yes = run <= 17.0;
+        const uint32_t lobits = 8u * (uint32_t) digits[P - H];
         if (yes) {
+            if (digits[P - H] < 4) ENSURE_LOW_HISTOGRAMS();
             rec16_passes(c, dbase, n, E, desc, dest, digits + (P - H), H, bins, scratch);
             uint32_t * wl = (uint32_t *) mps_arena_get(c, MPS_S_MERGE_CUT, (2 * MPS_HYBRID_MAX_LONG_RUNS + 64) * sizeof(uint32_t));
             uint32_t * nwork = wl + 2 * MPS_HYBRID_MAX_LONG_RUNS;
@@ -1094,13 +1101,42 @@ void mpsort_mpi_desc_impl(void * base, size_t nmemb, size_t elsize,
 }
 
 /* one cached size-1 communicator (stream + arena) per device and thread, shared by
- * radix_sort_desc and radix_sort */
+ * radix_sort_desc and radix_sort. Its arenas only grow (several times nmemb * size after a large
+ * call): mpsort_release_cached() gives them back for the calling thread; a thread that exits
+ * releases its own. */
+static pthread_key_t g_cache_key;
+static pthread_once_t g_cache_once = PTHREAD_ONCE_INIT;
+
+static void cache_destroy(void * p)
+{
+    mpsort_comm_t * self = (mpsort_comm_t *) p;
+    int d;
+    if (!self) return;
+    for (d = 0; d < 64; d++) if (self[d]) mpsort_comm_destroy(self[d]);
+    free(self);
+}
+
+static void cache_make_key(void) { pthread_key_create(&g_cache_key, cache_destroy); }
+
 static mpsort_comm_t cached_self_comm(int device)
 {
-    static __thread mpsort_comm_t self[64];
     if (device < 0 || device >= 64) { fprintf(stderr, "MPSort: bad device %d\n", device); abort(); }
+    pthread_once(&g_cache_once, cache_make_key);
+    mpsort_comm_t * self = (mpsort_comm_t *) pthread_getspecific(g_cache_key);
+    if (!self) {
+        self = (mpsort_comm_t *) calloc(64, sizeof(mpsort_comm_t));
+        if (!self) { fprintf(stderr, "MPSort: out of host memory\n"); abort(); }
+        pthread_setspecific(g_cache_key, self);
+    }
     if (!self[device]) self[device] = mpsort_comm_self(device);
     return self[device];
+}
+
+void mpsort_release_cached(void)
+{
+    pthread_once(&g_cache_once, cache_make_key);
+    void * p = pthread_getspecific(g_cache_key);
+    if (p) { pthread_setspecific(g_cache_key, NULL); cache_destroy(p); }
 }
 
 void radix_sort_desc(void * base, size_t nmemb, size_t size,

@@ -43,6 +43,7 @@ enum mps_slot {
     MPS_S_MERGE_CUT,   /* merge: per-tile cut positions                */
     MPS_S_MERGE_SORTED,/* merge: sample keys in merged order            */
     MPS_S_MERGE_SID,   /* merge: their sample ids                       */
+    MPS_S_PRED,        /* hybrid predictor: hash tables + pair counts   */
     MPS_NSLOTS
 };
 

@@ -78,12 +78,12 @@ int mpsk_fixup_rec(void * recs, size_t n, size_t elsize, int key_in_high, uint64
         uint32_t * worklist, uint32_t * nwork, uint32_t cap, mpsk_stream_t stream);
 int mpsk_fixup_extents(const void * recs, size_t n, size_t elsize, int key_in_high, uint64_t flip, uint32_t lobits,
         const uint32_t * worklist, uint32_t nwork, uint32_t * lengths, mpsk_stream_t stream);
-/* predictor of the hybrid sort: high parts of s evenly spaced records (as u64), and
- * the number of equal pairs (sum of k(k-1)/2 over values) of a sorted u64 array, added
- * to *count. */
-int mpsk_sample_prefix_rec(const void * recs, size_t n, size_t elsize, uint32_t s, int key_in_high, uint64_t flip,
-        uint32_t lobits, uint64_t * out, mpsk_stream_t stream);
-int mpsk_count_equal_pairs(const uint64_t * sorted, uint32_t s, uint64_t * count, mpsk_stream_t stream);
+/* predictor of the hybrid sort: pairs[j] += the number of equal PAIRS (sum of k(k-1)/2 over values)
+ * among the high parts (key ^ flip) >> lobits[j] of s evenly spaced records, for j < nl <= 2 at once.
+ * table: device u64[nl][2 << log2_tsize], zeroed by the caller, 1 << log2_tsize >= 2 s; pairs: device
+ * u64[2], zeroed by the caller. lobits is a host array. */
+int mpsk_prefix_pairs(const void * recs, size_t n, size_t elsize, uint32_t s, int key_in_high, uint64_t flip,
+        const uint32_t * lobits, uint32_t nl, uint64_t * table, uint32_t log2_tsize, uint64_t * pairs, mpsk_stream_t stream);
 
 /* dst[i] = src[idx[i]] for 64-bit words (key words of multi-word keys). If hist is
  * non-NULL nothing is accumulated (histograms are permutation invariant). */

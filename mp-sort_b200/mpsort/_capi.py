@@ -101,6 +101,7 @@ _proto("radix_sort", None, c_void_p, c_size_t, c_size_t, RadixFunc, c_size_t, c_
 _proto("mpsort_callback_desc", c_int, c_size_t, ctypes.POINTER(RadixDesc), ctypes.POINTER(c_size_t))
 _proto("mpsort_callback_pack", None, c_void_p, c_size_t, c_size_t, RadixFunc, c_size_t, c_void_p, c_void_p)
 _proto("mpsort_callback_unpack", None, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p)
+_proto("mpsort_release_cached", None)
 _proto("mpsort_mpi_report_last_run", None)
 _proto("mpsort_mpi_get_last_run", c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_double), c_int)
 _proto("mpsort_comm_last_stats", None, c_void_p, ctypes.POINTER(LastStats), ctypes.POINTER(c_i64), c_int)

@@ -191,11 +191,24 @@ def run_local(size, fn, devices=None, timeout=600):
     for t in threads:
         t.start()
     deadline = time.time() + timeout
-    for t in threads:
-        t.join(max(0.0, deadline - time.time()))
+    # poll: a rank that raised while the others sit in a collective must not cost the whole timeout.
+    # After its exception the others get a short grace period (they may be about to finish), then the
+    # group is abandoned: its threads are daemons blocked inside the library, its communicators are
+    # NOT destroyed (a destroy would wait for them) -- the group is unusable from then on.
+    failed_at = None
+    while any(t.is_alive() for t in threads):
+        now = time.time()
+        if failed_at is None and any(e is not None for e in errors):
+            failed_at = now
+        if now > deadline or (failed_at is not None and now > failed_at + 5.0):
+            break
+        time.sleep(0.002)
     hung = [t for t in threads if t.is_alive()]
     for e in errors:
         if e is not None:
+            if not hung:
+                for c in comms:
+                    c.destroy()
             raise e
     if hung:
         raise RuntimeError("mpsort.run_local: %d rank threads did not finish in %g s" % (len(hung), timeout))

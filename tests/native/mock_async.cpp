@@ -65,8 +65,7 @@ int K(mpsk_onesweep_pass)(const uint64_t *, const uint32_t *, uint64_t *, uint32
 int K(mpsk_onesweep_pass_rec)(const void *, void *, size_t, size_t, int, int, uint64_t, const uint32_t *, void *, mpsk_stream_t);
 int K(mpsk_fixup_rec)(void *, size_t, size_t, int, uint64_t, uint32_t, uint32_t *, uint32_t *, uint32_t, mpsk_stream_t);
 int K(mpsk_fixup_extents)(const void *, size_t, size_t, int, uint64_t, uint32_t, const uint32_t *, uint32_t, uint32_t *, mpsk_stream_t);
-int K(mpsk_sample_prefix_rec)(const void *, size_t, size_t, uint32_t, int, uint64_t, uint32_t, uint64_t *, mpsk_stream_t);
-int K(mpsk_count_equal_pairs)(const uint64_t *, uint32_t, uint64_t *, mpsk_stream_t);
+int K(mpsk_prefix_pairs)(const void *, size_t, size_t, uint32_t, int, uint64_t, const uint32_t *, uint32_t, uint64_t *, uint32_t, uint64_t *, mpsk_stream_t);
 int K(mpsk_gather_u64)(const uint64_t *, const uint32_t *, uint64_t *, size_t, mpsk_stream_t);
 int K(mpsk_gather_records)(const void *, const uint32_t *, void *, size_t, size_t, mpsk_stream_t);
 int K(mpsk_splitter_count)(struct mpsk_keyview, size_t, uint32_t, const uint64_t *, int, int, uint64_t *, mpsk_stream_t);
@@ -445,12 +444,13 @@ int mpsk_fixup_extents(const void * recs, size_t n, size_t elsize, int khi, uint
         const uint32_t * worklist, uint32_t nwork, uint32_t * lengths, mpsk_stream_t stream)
 { LAUNCH(stream, K(mpsk_fixup_extents)(recs, n, elsize, khi, flip, lobits, worklist, nwork, lengths, stream)); }
 
-int mpsk_sample_prefix_rec(const void * recs, size_t n, size_t elsize, uint32_t s, int khi, uint64_t flip, uint32_t lobits,
-        uint64_t * out, mpsk_stream_t stream)
-{ LAUNCH(stream, K(mpsk_sample_prefix_rec)(recs, n, elsize, s, khi, flip, lobits, out, stream)); }
-
-int mpsk_count_equal_pairs(const uint64_t * sorted, uint32_t s, uint64_t * count, mpsk_stream_t stream)
-{ LAUNCH(stream, K(mpsk_count_equal_pairs)(sorted, s, count, stream)); }
+int mpsk_prefix_pairs(const void * recs, size_t n, size_t elsize, uint32_t s, int khi, uint64_t flip,
+        const uint32_t * lobits, uint32_t nl, uint64_t * table, uint32_t log2_tsize, uint64_t * pairs, mpsk_stream_t stream)
+{
+    if (nl > 2) return (int) cudaErrorInvalidValue;
+    auto lb = snap(lobits, (size_t) (nl ? nl : 1));
+    LAUNCH(stream, K(mpsk_prefix_pairs)(recs, n, elsize, s, khi, flip, lb->data(), nl, table, log2_tsize, pairs, stream));
+}
 
 int mpsk_gather_u64(const uint64_t * src, const uint32_t * idx, uint64_t * dst, size_t n, mpsk_stream_t stream)
 { LAUNCH(stream, K(mpsk_gather_u64)(src, idx, dst, n, stream)); }

@@ -569,27 +569,40 @@ int mpsk_fixup_extents(const void * recs, size_t n, size_t elsize, int khi, uint
     return 0;
 }
 
-int mpsk_sample_prefix_rec(const void * recs, size_t n, size_t elsize, uint32_t s, int khi, uint64_t flip, uint32_t lobits,
-        uint64_t * out, mpsk_stream_t stream)
+static int cmp_u64(const void * a, const void * b)
 {
-    uint32_t i;
-    (void) stream;
-    if (s == 0) return 0;
-    LAUNCHED();
-    for (i = 0; i < s; i++) out[i] = rec_key(recs, (size_t) (((unsigned __int128) i * n) / s), elsize, khi, flip) >> lobits;
-    return 0;
+    const uint64_t x = *(const uint64_t *) a, y = *(const uint64_t *) b;
+    return (x > y) - (x < y);
 }
 
-int mpsk_count_equal_pairs(const uint64_t * sorted, uint32_t s, uint64_t * count, mpsk_stream_t stream)
+int mpsk_prefix_pairs(const void * recs, size_t n, size_t elsize, uint32_t s, int khi, uint64_t flip,
+        const uint32_t * lobits, uint32_t nl, uint64_t * table, uint32_t log2_tsize, uint64_t * pairs, mpsk_stream_t stream)
 {
-    uint32_t i, first = 0;
-    (void) stream;
-    if (s == 0) return 0;
+    /* same contract, by sorting the sampled high parts (the table is left alone) */
+    uint32_t i, j;
+    (void) stream; (void) table; (void) log2_tsize;
+    if (s == 0 || nl == 0 || n == 0) return 0;
+    if (nl > 2) return 1;
     LAUNCHED();
-    for (i = 0; i < s; i++) {
-        if (sorted[i] != sorted[first]) first = i;
-        *count += i - first;
+    uint64_t * v = (uint64_t *) malloc(sizeof(uint64_t) * s);
+    for (j = 0; j < nl; j++) {
+        for (i = 0; i < s; i++) {
+            const size_t pos = (size_t) (((unsigned __int128) i * n) / s);
+            uint64_t k;
+            memcpy(&k, (const unsigned char *) recs + pos * elsize + ((khi && elsize == 16) ? 8 : 0), 8);
+            k ^= flip;
+            v[i] = lobits[j] >= 64 ? 0 : k >> lobits[j];
+        }
+        qsort(v, s, sizeof(uint64_t), cmp_u64);
+        uint64_t c = 0;
+        uint32_t run = 0;
+        for (i = 1; i < s; i++) {
+            run = (v[i] == v[i - 1]) ? run + 1 : 0;
+            c += run;
+        }
+        pairs[j] += c;
     }
+    free(v);
     return 0;
 }
 

@@ -188,10 +188,11 @@ def test_host_code_under_address_and_ub_sanitizers(tmp_path, mock_env):
     assert rc.returncode == 0 and "AddressSanitizer" not in out and "runtime error" not in out, out[-4000:]
 
 
-@pytest.mark.parametrize("extra,passes", [({}, 4), ({"MPSORT_HYBRID_DEPTH5": "1"}, 5), ({"MPSORT_NO_HYBRID": "1"}, 7)])
+@pytest.mark.parametrize("extra,passes", [({}, 5), ({"MPSORT_NO_HYBRID5": "1"}, 4), ({"MPSORT_NO_HYBRID": "1"}, 7)])
 def test_hybrid_depth_decisions(mock_env, extra, passes):
-    """record mode, 2^22 keys with runs of 16 equal high parts: four passes + fix-up by default, five with the
-    candidate switch, seven plain passes without the hybrid; one long run through the work list; same bytes"""
+    """record mode, 2^22 keys with runs of 16 equal high parts that a fifth digit separates: five passes + fix-up
+    (the predictor's choice), four when the fifth is switched off, seven plain passes without the hybrid; one long
+    run through the work list; same bytes"""
     rc = run_py(mock_env, [os.path.join(ROOT, "tests", "support", "hybrid_depth_worker.py")], **extra)
     out = rc.stdout.decode()
     assert rc.returncode == 0 and ("passes=%d " % passes) in out and "equal=True" in out, out[-2000:]

@@ -3,7 +3,6 @@ at hand (end of round 1). They run only with MPSORT_TEST_CANDIDATES=1, so that t
 states what the shipped paths do; tools/candidates_ab.sh runs them and times each candidate.
 
   MPSORT_PACK_PIPELINE=1  index mode: pack of exchange part q+1 beside the transfer of part q
-  MPSORT_HYBRID_DEPTH5=1  five high-digit passes when four leave long runs of equal high parts
   MPSORT_FUSED_PACK=1     index mode: gather by sorted index + peer stores in one kernel (needs >= 2 GPUs)
   MPSORT_PEER_SPLITTER=1  all levels of the splitter descent in one kernel, sums over mapped peer memory
 """
@@ -107,15 +106,6 @@ def test_candidates_at_2_22_records_per_rank_by_properties(E, kind, extra):
     of checksums -- with the pipelined pack (index mode) or the peer splitter kernel switched on"""
     env = dict(os.environ, MPSORT_EXCHANGE_PHASES="2", **extra)
     rc = subprocess.run([sys.executable, "-c", WORKER_PROPS % {"root": ROOT, "E": E, "kind": kind, "log2n": 22, "passes": 0}],
-                        env=env, timeout=900, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
-    assert rc.returncode == 0 and b"CANDIDATE OK" in rc.stdout, rc.stdout.decode()[-4000:]
-
-
-def test_hybrid_five_passes_on_mostly_sorted_keys():
-    """MPSORT_HYBRID_DEPTH5=1: 4 rank threads x 2^27 mostly sorted 16-byte records (2^29 in total, so that
-    seven key bytes vary and four top digits leave runs of 16): five passes + fix-up, same properties"""
-    env = dict(os.environ, MPSORT_EXCHANGE_PHASES="2", MPSORT_HYBRID_DEPTH5="1")
-    rc = subprocess.run([sys.executable, "-c", WORKER_PROPS % {"root": ROOT, "E": 16, "kind": 1, "log2n": 27, "passes": 5}],
                         env=env, timeout=900, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     assert rc.returncode == 0 and b"CANDIDATE OK" in rc.stdout, rc.stdout.decode()[-4000:]
 
