@@ -18,6 +18,8 @@ extern "C" {
 #endif
 
 int    mpsort_util_device_count(void);
+/* "0000:1b:00.0"-style PCI address of a CUDA device (for NUMA placement of its host buffers); 0 on success */
+int    mpsort_util_device_pci_bus_id(int device, char * buf, int len);
 void * mpsort_util_dev_malloc(int device, size_t nbytes);
 void   mpsort_util_dev_free(int device, void * ptr);
 /* page-locked host memory; NULL if it cannot be pinned */

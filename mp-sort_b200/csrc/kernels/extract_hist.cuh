@@ -188,12 +188,12 @@ extern "C" int mpsk_extract_keys(const void * base, size_t n, size_t elsize,
 template <int NH>
 __global__ void __launch_bounds__(512)
 rec_hist_kernel(const u64 * __restrict__ words, u32 W, u32 koff, size_t n, u64 flip, u32 d0,
-                u32 * __restrict__ hist, unsigned long long * __restrict__ diff)
+                u32 * __restrict__ hist, unsigned long long * __restrict__ diff, const u64 * __restrict__ ref)
 {
     __shared__ u32 sh[NH * 256];
     for (u32 t = threadIdx.x; t < NH * 256; t += blockDim.x) sh[t] = 0;
     __syncthreads();
-    const u64 k0 = words[koff] ^ flip;
+    const u64 k0 = ref[koff] ^ flip;
     const size_t per_block = (size_t) blockDim.x * EXTRACT_BATCH;
     const size_t nblocks_total = (n + per_block - 1) / per_block;
     const bool lane0 = (threadIdx.x & 31) == 0;
@@ -267,10 +267,11 @@ rec_sample_diff_kernel(const u64 * __restrict__ words, u32 W, u32 koff, size_t n
 }
 
 extern "C" int mpsk_rec_histograms(const void * recs, size_t n, size_t elsize, int key_in_high, uint64_t flip,
-        uint32_t d0, uint32_t nh, uint32_t * hist, uint64_t * diff, mpsk_stream_t stream)
+        uint32_t d0, uint32_t nh, uint32_t * hist, uint64_t * diff, const void * ref, mpsk_stream_t stream)
 {
     if (n == 0) return 0;
     if ((elsize != 8 && elsize != 16) || (nh != 4 && nh != 8) || d0 + nh > 8) return (int) cudaErrorInvalidValue;
+    if (!ref) ref = recs;
     const int threads = 512;
     size_t blocks = (n + (size_t) threads * EXTRACT_BATCH - 1) / ((size_t) threads * EXTRACT_BATCH);
     const size_t maxb = (size_t) num_sms() * 8;
@@ -278,10 +279,10 @@ extern "C" int mpsk_rec_histograms(const void * recs, size_t n, size_t elsize, i
     const u32 W = (u32) (elsize / 8), koff = (key_in_high && elsize == 16) ? 1u : 0u;
     if (nh == 4)
         rec_hist_kernel<4><<<(unsigned) blocks, threads, 0, (cudaStream_t) stream>>>(
-            (const u64 *) recs, W, koff, n, (u64) flip, d0, hist, (unsigned long long *) diff);
+            (const u64 *) recs, W, koff, n, (u64) flip, d0, hist, (unsigned long long *) diff, (const u64 *) ref);
     else
         rec_hist_kernel<8><<<(unsigned) blocks, threads, 0, (cudaStream_t) stream>>>(
-            (const u64 *) recs, W, koff, n, (u64) flip, d0, hist, (unsigned long long *) diff);
+            (const u64 *) recs, W, koff, n, (u64) flip, d0, hist, (unsigned long long *) diff, (const u64 *) ref);
     CUDA_LAUNCH_CHECK();
     return 0;
 }

@@ -29,8 +29,10 @@ __device__ __forceinline__ u64 rec_key(const uint4 & it, u32 khi, u64 flip)
 #ifndef FIX_MINBLOCKS
 #define FIX_MINBLOCKS 8
 #endif
+/* tile + 444 is asked into L2 when a tile starts: 0.92 -> 0.83 ms per 2^28 records with 296 or 592,
+ * 0.87 with 1184, 1.28 with 2368 (profiles/r02_call3_predictor_prefetch_distances.log) */
 #ifndef FIX_PREFETCH_TILES
-#define FIX_PREFETCH_TILES 0
+#define FIX_PREFETCH_TILES 444
 #endif
 
 /* what one entry of the compacted list (a position that is not a run of its own) has to do:
@@ -86,7 +88,7 @@ __device__ __forceinline__ u32 fixup_votes(const u32 * s_head, u32 cnt, u32 w)
 template <typename ITEM, bool KHI>
 __global__ void __launch_bounds__(FIX_THREADS, FIX_MINBLOCKS)
 fixup_rec_kernel(ITEM * __restrict__ recs, u32 n, u64 flip, u32 lobits,
-                   u32 * __restrict__ worklist, u32 * __restrict__ nwork, u32 cap, u32 pf_dist)
+                   u32 * __restrict__ worklist, u32 * __restrict__ nwork, u32 cap, u32 pf_dist, u32 tile0)
 {
     constexpr int CAP = FIX_T + FIX_HALO;
     constexpr int NW = CAP / 32;                  /* head words that describe positions of this tile */
@@ -110,7 +112,7 @@ fixup_rec_kernel(ITEM * __restrict__ recs, u32 n, u64 flip, u32 lobits,
 
     const u32 tid = threadIdx.x;
     const u32 lane = tid & 31u;
-    const size_t t0 = (size_t) blockIdx.x * FIX_T;
+    const size_t t0 = ((size_t) blockIdx.x + tile0) * FIX_T;
     const u32 avail = (u32) ((size_t) n - t0);
     const u32 cnt = avail < (u32) CAP ? avail : (u32) CAP;
     const bool at_end = (t0 + cnt == n);
@@ -120,7 +122,7 @@ fixup_rec_kernel(ITEM * __restrict__ recs, u32 n, u64 flip, u32 lobits,
 
     /* tile + pf_dist is asked into L2 while this one is worked on (cp.async.bulk.prefetch.L2) */
     if (pf_dist && tid == 0) {
-        const u64 first = ((u64) blockIdx.x + pf_dist) * (u64) FIX_T;
+        const u64 first = ((u64) blockIdx.x + tile0 + pf_dist) * (u64) FIX_T;
         if (first < (u64) n) {
             const u64 left = ((u64) n - first) * sizeof(ITEM);
             const u32 bytes = (u32) (left < (u64) FIX_T * sizeof(ITEM) ? (left & ~15ULL) : (u64) FIX_T * sizeof(ITEM));
@@ -230,22 +232,27 @@ __global__ void fixup_extent_kernel(const u64 * __restrict__ recs, u32 W, u32 n,
     lengths[e] = lo - start;
 }
 
+extern "C" size_t mpsk_fixup_tile_items(void) { return FIX_T; }
+
 extern "C" int mpsk_fixup_rec(void * recs, size_t n, size_t elsize, int key_in_high, uint64_t flip, uint32_t lobits,
-        uint32_t * worklist, uint32_t * nwork, uint32_t cap, mpsk_stream_t stream)
+        uint32_t * worklist, uint32_t * nwork, uint32_t cap, size_t tile0, size_t ntiles, mpsk_stream_t stream)
 {
     if (n == 0) return 0;
-    const size_t tiles = (n + FIX_T - 1) / FIX_T;
+    const size_t all = (n + FIX_T - 1) / FIX_T;
+    if (tile0 >= all) return 0;
+    size_t tiles = all - tile0;
+    if (ntiles != 0 && ntiles < tiles) tiles = ntiles;
     static int pf = -1;                  /* MPSORT_PREFETCH_FIXUP_TILES: eight CTAs per SM, a wave is 1184 tiles */
     if (pf < 0) { const char * e = getenv("MPSORT_PREFETCH_FIXUP_TILES"); pf = e ? atoi(e) : FIX_PREFETCH_TILES; if (pf < 0) pf = 0; }
     if (elsize == 8)
         fixup_rec_kernel<u64, false><<<(unsigned) tiles, FIX_THREADS, 0, (cudaStream_t) stream>>>(
-            (u64 *) recs, (u32) n, (u64) flip, lobits, worklist, nwork, cap, (u32) pf);
+            (u64 *) recs, (u32) n, (u64) flip, lobits, worklist, nwork, cap, (u32) pf, (u32) tile0);
     else if (key_in_high)
         fixup_rec_kernel<uint4, true><<<(unsigned) tiles, FIX_THREADS, 0, (cudaStream_t) stream>>>(
-            (uint4 *) recs, (u32) n, (u64) flip, lobits, worklist, nwork, cap, (u32) pf);
+            (uint4 *) recs, (u32) n, (u64) flip, lobits, worklist, nwork, cap, (u32) pf, (u32) tile0);
     else
         fixup_rec_kernel<uint4, false><<<(unsigned) tiles, FIX_THREADS, 0, (cudaStream_t) stream>>>(
-            (uint4 *) recs, (u32) n, (u64) flip, lobits, worklist, nwork, cap, (u32) pf);
+            (uint4 *) recs, (u32) n, (u64) flip, lobits, worklist, nwork, cap, (u32) pf, (u32) tile0);
     CUDA_LAUNCH_CHECK();
     return 0;
 }
@@ -267,30 +274,42 @@ extern "C" int mpsk_fixup_extents(const void * recs, size_t n, size_t elsize, in
  * round trip. */
 struct PredArgs { u32 lobits[2]; u32 nl; };
 
+/* one insertion: the number of equal values inserted before this one */
+__device__ __forceinline__ u64 pred_insert(unsigned long long * tk, unsigned long long * tc, u64 tsize, u64 value)
+{
+    const u64 mask = tsize - 1;
+    const u64 v = value + 1ULL;                                   /* 0 = empty slot */
+    u64 h = mset_hash64(v) & mask;
+    for (u64 probe = 0; probe < tsize; probe++) {
+        const unsigned long long prev = atomicCAS(&tk[h], 0ULL, (unsigned long long) v);
+        if (prev == 0ULL || prev == v) return atomicAdd(&tc[h], 1ULL);
+        h = (h + 1) & mask;
+    }
+    return 0;
+}
+
 __global__ void __launch_bounds__(256)
 prefix_pairs_kernel(const u64 * __restrict__ recs, u32 W, size_t n, u32 s, u32 khi, u64 flip, PredArgs a,
                     u64 * __restrict__ table, u32 log2t, u64 * __restrict__ pairs)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    const u64 tsize = 1ULL << log2t, mask = tsize - 1;
-    u64 found[2] = { 0, 0 };
+    const u64 tsize = 1ULL << log2t;
+    u64 found[3] = { 0, 0, 0 };
     if (i < s) {
-        const size_t pos = (size_t) (((unsigned __int128) i * n) / s);
+        /* pseudo-random positions over the WHOLE array: the estimate counts samples that fall into the same run,
+         * and evenly spaced (or one-per-stratum) samples of nearly sorted keys never do -- they would report
+         * singleton runs for keys whose runs are 16 long. Positions drawn twice are counted too (table nl) and
+         * taken off by the caller: pairs[nl] of them. */
+        const size_t pos = (size_t) (mset_hash64(0x5EED5A3Bu + i) % (u64) n);
         const u64 key = rec_key_at(recs, pos, W, khi, flip);
-        for (u32 j = 0; j < a.nl; j++) {
-            const u64 hi = (a.lobits[j] >= 64 ? 0ULL : key >> a.lobits[j]) + 1ULL;      /* 0 = empty slot */
+        for (u32 j = 0; j <= a.nl; j++) {
             unsigned long long * tk = (unsigned long long *) table + (size_t) j * 2 * tsize;
-            unsigned long long * tc = tk + tsize;
-            u64 h = mset_hash64(hi) & mask;
-            for (u64 probe = 0; probe < tsize; probe++) {
-                const unsigned long long prev = atomicCAS(&tk[h], 0ULL, (unsigned long long) hi);
-                if (prev == 0ULL || prev == hi) { found[j] = atomicAdd(&tc[h], 1ULL); break; }
-                h = (h + 1) & mask;
-            }
+            const u64 value = j == a.nl ? (u64) pos : (a.lobits[j] >= 64 ? 0ULL : key >> a.lobits[j]);
+            found[j] = pred_insert(tk, tk + tsize, tsize, value);
         }
     }
 #pragma unroll
-    for (int j = 0; j < 2; j++) {
+    for (int j = 0; j < 3; j++) {
         u64 v = found[j];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);

@@ -21,9 +21,14 @@
  * HBM traffic: E read + E write per record (+ ~8/S for the samples).
  */
 #define MPSK_MERGE_MAX_RUNS 32
+#ifndef MPSK_MERGE_TILE
 #define MPSK_MERGE_TILE 4096
+#endif
 #ifndef MPSK_MERGE_THREADS
 #define MPSK_MERGE_THREADS 512
+#endif
+#ifndef MPSK_MERGE_MINBLOCKS
+#define MPSK_MERGE_MINBLOCKS 2
 #endif
 
 struct MergeRuns {
@@ -151,7 +156,7 @@ __device__ __forceinline__ void merge_prefetch_tile(const unsigned char * recv, 
 /* FAST8: one aligned 8-byte key word (no generic key packing code in the kernel);
  * LPR1: a record is exactly one V (no division in the output loop) */
 template <typename V, bool FAST8, bool LPR1>
-__global__ void __launch_bounds__(MPSK_MERGE_THREADS, 2)
+__global__ void __launch_bounds__(MPSK_MERGE_THREADS, MPSK_MERGE_MINBLOCKS)
 merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, MergeRuns m,
                   const u32 * __restrict__ cut, unsigned char * __restrict__ out, u32 * __restrict__ overflow,
                   u32 ntiles, u32 pf_dist)
@@ -166,31 +171,38 @@ merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, MergeRuns 
     __shared__ u32 srcbase[MPSK_MERGE_MAX_RUNS];
     __shared__ u32 s_outstart;
 
-    const u32 t = blockIdx.x, p = m.p, tid = threadIdx.x;
-    if (tid < 32) {
-        /* one lane per run (p <= 32): the 2p cut words are fetched in parallel, not by one
-         * thread in a dependent loop (that loop alone was ~4 us per tile at p = 8) */
+    const u32 t = blockIdx.x, p = m.p, tid = threadIdx.x, lane = tid & 31u;
+    /* EVERY warp fetches the 2p cut words (one lane per run, p <= 32; the same few words for all warps: L1
+     * hits) and scans them for itself: nobody waits at a barrier for warp 0's two dependent global loads before
+     * its own key loads can go out -- a fifth of all warp samples of the first version sat at that barrier
+     * (ncu, profiles/r01_ncu_full_merge_tile_p8.csv). Warp 0 also leaves the offsets in shared memory for the
+     * rounds; the barrier after the key staging publishes them. */
+    u32 my_seqoff, my_srcbase, cnt;
+    {
         u32 c0 = 0, c1 = 0;
-        if (tid < p) { c0 = cut[t * p + tid]; c1 = cut[(t + 1) * p + tid]; }
+        if (lane < p) { c0 = cut[t * p + lane]; c1 = cut[(t + 1) * p + lane]; }
         const u32 len = c1 - c0;
         u32 incl = len, sum0 = c0;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const u32 y = __shfl_up_sync(FULL_MASK, incl, o);
-            if (tid >= (u32) o) incl += y;
+            if (lane >= (u32) o) incl += y;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum0 += __shfl_xor_sync(FULL_MASK, sum0, o);
-        if (tid < p) { seqoff[tid] = incl - len; srcbase[tid] = m.rdispl[tid] + c0; }
-        if (tid == p - 1) seqoff[p] = incl;
-        if (tid == 0) s_outstart = sum0;
-    } else if (tid < 64) {
-        /* the p sub-ranges of tile t + pf_dist are asked into L2 (cp.async.bulk.prefetch.L2, one lane per
-         * run): this kernel waits for its scattered key loads more than for anything else */
-        merge_prefetch_tile(recv, d.elsize, m, cut, t + pf_dist, ntiles, tid - 32, pf_dist);
+        my_seqoff = incl - len;                       /* lanes >= p hold the total: the run after the last starts there */
+        my_srcbase = lane < p ? m.rdispl[lane] + c0 : 0u;
+        cnt = __shfl_sync(FULL_MASK, incl, 31);
+        if (tid < 32) {
+            if (tid < p) { seqoff[tid] = my_seqoff; srcbase[tid] = my_srcbase; }
+            if (tid == p - 1) seqoff[p] = incl;
+            if (tid == 0) s_outstart = sum0;
+        } else if (tid < 64) {
+            /* the p sub-ranges of tile t + pf_dist are asked into L2 (cp.async.bulk.prefetch.L2, one lane per
+             * run): this kernel waits for its scattered key loads more than for anything else */
+            merge_prefetch_tile(recv, d.elsize, m, cut, t + pf_dist, ntiles, tid - 32, pf_dist);
+        }
     }
-    __syncthreads();
-    const u32 cnt = seqoff[p];
     if (cnt > MPSK_MERGE_TILE) {            /* cannot happen (tile bound); never corrupt memory */
         if (tid == 0) atomicAdd(overflow, 1u);
         return;
@@ -199,15 +211,20 @@ merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, MergeRuns 
     {
         u32 src[VT];
         u64 key[VT];
-        u32 r = 0;                                  /* a thread's positions increase: the run index only moves up */
+        u32 run[VT];
+        /* the run of position i = the number of run starts at or below it (empty runs included), found with
+         * warp-uniform broadcasts of the starts: every lane executes every shuffle */
+#pragma unroll
+        for (int k = 0; k < VT; k++) run[k] = 0;
+        for (u32 q = 1; q < p; q++) {
+            const u32 start = __shfl_sync(FULL_MASK, my_seqoff, q);
+#pragma unroll
+            for (int k = 0; k < VT; k++) run[k] += (tid + k * MPSK_MERGE_THREADS >= start) ? 1u : 0u;
+        }
 #pragma unroll
         for (int k = 0; k < VT; k++) {
             const u32 i = tid + k * MPSK_MERGE_THREADS;
-            src[k] = 0;
-            if (i < cnt) {
-                while (i >= seqoff[r + 1]) r++;
-                src[k] = srcbase[r] + (i - seqoff[r]);
-            }
+            src[k] = __shfl_sync(FULL_MASK, my_srcbase, run[k]) + (i - __shfl_sync(FULL_MASK, my_seqoff, run[k]));
         }
 #pragma unroll
         for (int k = 0; k < VT; k++) {
@@ -454,15 +471,19 @@ extern "C" int mpsk_merge_rank_samples(const uint64_t * skeys, uint32_t p, const
     return 0;
 }
 
-/* MPSORT_PREFETCH_MERGE_TILES=d: tile + d is asked into L2 when a tile starts (two or three CTAs per SM) */
+/* MPSORT_PREFETCH_MERGE_TILES=d: tile + d is asked into L2 when a tile starts. Measured at 2^28 records
+ * (profiles/r02_call3_predictor_prefetch_distances.log): 16-byte records 5.09 -> 4.89 ms at 8 runs, 3.76 -> 3.48 at 4,
+ * 2.88 -> 2.78 at 2, with 74 .. 296; 48-byte records get SLOWER (4.29 -> 4.68 ms: eight 24 KB sub-ranges per tile
+ * evict what the tiles at work still need), so the default is 148 up to 16-byte records and none above. */
 #ifndef MPSK_MERGE_PREFETCH_TILES
-#define MPSK_MERGE_PREFETCH_TILES 0
+#define MPSK_MERGE_PREFETCH_TILES 148
 #endif
-static u32 merge_prefetch_tiles()
+static u32 merge_prefetch_tiles(size_t elsize)
 {
     static int v = -1;
-    if (v < 0) { const char * e = getenv("MPSORT_PREFETCH_MERGE_TILES"); v = e ? atoi(e) : MPSK_MERGE_PREFETCH_TILES; if (v < 0) v = 0; }
-    return (u32) v;
+    if (v < 0) { const char * e = getenv("MPSORT_PREFETCH_MERGE_TILES"); v = e ? atoi(e) : -2; }
+    if (v >= 0) return (u32) v;
+    return elsize <= 16 ? (u32) MPSK_MERGE_PREFETCH_TILES : 0u;
 }
 
 template <typename V>
@@ -476,7 +497,7 @@ static int launch_merge_tiles(const void * recv, KeyDesc d, bool fast8, const Me
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
         if (e != cudaSuccess) return (int) e; \
         kern<<<ntiles, MPSK_MERGE_THREADS, smem, stream>>>((const unsigned char *) recv, d, m, cut, \
-                                                           (unsigned char *) out, overflow, ntiles, merge_prefetch_tiles()); } while (0)
+                                                           (unsigned char *) out, overflow, ntiles, merge_prefetch_tiles(d.elsize)); } while (0)
     if (fast8 && lpr1) MERGE_LAUNCH(true, true);
     else if (fast8) MERGE_LAUNCH(true, false);
     else if (lpr1) MERGE_LAUNCH(false, true);
@@ -511,12 +532,12 @@ extern "C" int mpsk_merge_runs(const void * recv, void * out, size_t elsize, siz
             auto kern = merge_tile_rec16_kernel<true>;
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return (int) e;
-            kern<<<ntiles, MPSK_MERGE16_THREADS, smem, stream>>>((const uint4 *) recv, flip, m, cut, (uint4 *) out, overflow, ntiles, merge_prefetch_tiles());
+            kern<<<ntiles, MPSK_MERGE16_THREADS, smem, stream>>>((const uint4 *) recv, flip, m, cut, (uint4 *) out, overflow, ntiles, merge_prefetch_tiles(16));
         } else {
             auto kern = merge_tile_rec16_kernel<false>;
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return (int) e;
-            kern<<<ntiles, MPSK_MERGE16_THREADS, smem, stream>>>((const uint4 *) recv, flip, m, cut, (uint4 *) out, overflow, ntiles, merge_prefetch_tiles());
+            kern<<<ntiles, MPSK_MERGE16_THREADS, smem, stream>>>((const uint4 *) recv, flip, m, cut, (uint4 *) out, overflow, ntiles, merge_prefetch_tiles(16));
         }
         CUDA_LAUNCH_CHECK();
         return 0;

@@ -368,8 +368,10 @@ static int sweep_ticket_tiles()
 }
 
 /* index passes: MPSORT_PREFETCH_INDEX_TILES (tiles are 6144 pairs, two CTAs per SM: a wave is 296 tiles) */
+/* 1.59 ms per pass without, 1.50 with 74 or 148, 1.52 with 296, 1.65 with 592 (2^28 pairs,
+ * profiles/r02_call3_predictor_prefetch_distances.log) */
 #ifndef MPSK_SWEEP_PREFETCH_TILES
-#define MPSK_SWEEP_PREFETCH_TILES 0
+#define MPSK_SWEEP_PREFETCH_TILES 148
 #endif
 static u32 sweep_prefetch_index_tiles()
 {

@@ -344,6 +344,11 @@ void mpsort_comm_destroy(mpsort_comm_t c)
         for (s = 0; s < 9; s++) cudaEventDestroy(c->p2p.ce_ev[s]);
     }
     if (c->stream2) cudaStreamDestroy(c->stream2);
+    if (c->io_created) {
+        for (s = 0; s < MPS_MAX_CHUNKS; s++) cudaEventDestroy(c->in.ev[s]);
+        cudaEventDestroy(c->io_ev[0]); cudaEventDestroy(c->io_ev[1]);
+        cudaStreamDestroy(c->h2d_stream); cudaStreamDestroy(c->d2h_stream);
+    }
     if (c->phase_ev_created) { int i; for (i = 0; i <= MPS_MAX_RANKS; i++) cudaEventDestroy(c->phase_ev[i]); }
     if (c->kind == MPS_T_NCCL && c->nccl) ncclCommDestroy(c->nccl);
     if (c->kind == MPS_T_LOCAL && c->grp) {

@@ -150,6 +150,125 @@ void mpsort_comm_last_stats(mpsort_comm_t c, struct mpsort_last_stats * st, int6
 }
 
 /* ------------------------------------------------------------------------- */
+/* host buffers in chunks: see struct mpsort_comm                */
+
+/* host buffers of at least MPSORT_CHUNK_MIN_BYTES (64 MiB) move in chunks of MPSORT_CHUNK_BYTES (256 MiB);
+ * the tests lower both to run the chunked flow on small arrays */
+static size_t io_env_bytes(const char * name, size_t dflt)
+{
+    const char * e = getenv(name);
+    const long long v = e ? atoll(e) : 0;
+    return v > 0 ? (size_t) v : dflt;
+}
+#define MPS_CHUNK_MIN_BYTES io_env_bytes("MPSORT_CHUNK_MIN_BYTES", (size_t) 64 << 20)
+#define MPS_CHUNK_BYTES io_env_bytes("MPSORT_CHUNK_BYTES", (size_t) 256 << 20)
+
+static void io_create(struct mpsort_comm * c)
+{
+    int k;
+    if (c->io_created) return;
+    CUDA_OK(c, cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+    CUDA_OK(c, cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    for (k = 0; k < MPS_MAX_CHUNKS; k++) CUDA_OK(c, cudaEventCreateWithFlags(&c->in.ev[k], cudaEventDisableTiming));
+    for (k = 0; k < 2; k++) CUDA_OK(c, cudaEventCreateWithFlags(&c->io_ev[k], cudaEventDisableTiming));
+    c->io_created = 1;
+}
+
+static int io_chunking_enabled(void)
+{
+    static int v = -1;
+    if (v < 0) v = getenv("MPSORT_NO_HOST_CHUNKS") ? 0 : 1;
+    return v;
+}
+
+/* host -> device: one copy on c->stream, or (large inputs) chunks on the copy stream that the readers of
+ * `din` wait for range by range (mps_input_wait) */
+static void input_stage(struct mpsort_comm * c, void * din, const void * base, size_t nmemb, size_t elsize)
+{
+    const size_t bytes = nmemb * elsize;
+    c->in.dbase = NULL;
+    if (bytes < MPS_CHUNK_MIN_BYTES || !io_chunking_enabled()) {
+        if (bytes) CUDA_OK(c, cudaMemcpyAsync(din, base, bytes, cudaMemcpyHostToDevice, c->stream));
+        return;
+    }
+    io_create(c);
+    size_t nch = (bytes + MPS_CHUNK_BYTES - 1) / MPS_CHUNK_BYTES;
+    if (nch > MPS_MAX_CHUNKS) nch = MPS_MAX_CHUNKS;
+    /* whole fix-up / merge tiles per chunk is not needed on the way in: any record boundary will do,
+     * kept at a multiple of 4096 records so that vector loads of every kernel stay aligned */
+    size_t per = ((nmemb + nch - 1) / nch + 4095) & ~(size_t) 4095;
+    nch = (nmemb + per - 1) / per;
+    c->in.dbase = din; c->in.n = nmemb; c->in.elsize = elsize; c->in.chunk = per; c->in.nchunks = (int) nch; c->in.waited = 0;
+    /* the copy stream starts after whatever c->stream has queued on `din` (an earlier call's readers) */
+    CUDA_OK(c, cudaEventRecord(c->io_ev[0], c->stream));
+    CUDA_OK(c, cudaStreamWaitEvent(c->h2d_stream, c->io_ev[0], 0));
+    size_t k;
+    for (k = 0; k < nch; k++) {
+        const size_t a = k * per, b = (a + per < nmemb) ? a + per : nmemb;
+        CUDA_OK(c, cudaMemcpyAsync((char *) din + a * elsize, (const char *) base + a * elsize, (b - a) * elsize,
+                                   cudaMemcpyHostToDevice, c->h2d_stream));
+        CUDA_OK(c, cudaEventRecord(c->in.ev[k], c->h2d_stream));
+    }
+}
+
+void mps_input_wait(struct mpsort_comm * c, const void * dbase, size_t first, size_t count)
+{
+    if (!c->in.dbase || dbase != c->in.dbase || count == 0) return;
+    size_t last = (first + count - 1) / c->in.chunk;
+    if (last >= (size_t) c->in.nchunks) last = (size_t) c->in.nchunks - 1;
+    if ((int) last < c->in.waited) return;
+    /* the copy stream runs in order: waiting for chunk `last` is waiting for all before it */
+    CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->in.ev[last], 0));
+    c->in.waited = (int) last + 1;
+}
+
+int mps_input_ranges(struct mpsort_comm * c, const void * dbase, size_t n, size_t * a)
+{
+    int k;
+    a[0] = 0;
+    if (!c->in.dbase || dbase != c->in.dbase || n != c->in.n) { a[1] = n; return 1; }
+    for (k = 0; k < c->in.nchunks; k++) a[k + 1] = ((size_t) (k + 1) * c->in.chunk < n) ? (size_t) (k + 1) * c->in.chunk : n;
+    return c->in.nchunks;
+}
+
+static void output_begin(struct mpsort_comm * c, void * host, const void * dout, size_t outnmemb, size_t elsize)
+{
+    c->outp.host = NULL;
+    if (!host || outnmemb * elsize < MPS_CHUNK_MIN_BYTES || !io_chunking_enabled()) return;
+    io_create(c);
+    c->outp.host = host; c->outp.dout = dout; c->outp.elsize = elsize; c->outp.total = outnmemb; c->outp.done = 0;
+}
+
+void mps_output_ready(struct mpsort_comm * c, size_t upto)
+{
+    if (!c->outp.host) return;
+    if (upto > c->outp.total) upto = c->outp.total;
+    if (upto <= c->outp.done) return;
+    /* the copy stream waits for the producer (c->stream may be the merge stream right now) */
+    CUDA_OK(c, cudaEventRecord(c->io_ev[1], c->stream));
+    CUDA_OK(c, cudaStreamWaitEvent(c->d2h_stream, c->io_ev[1], 0));
+    CUDA_OK(c, cudaMemcpyAsync((char *) c->outp.host + c->outp.done * c->outp.elsize,
+                               (const char *) c->outp.dout + c->outp.done * c->outp.elsize,
+                               (upto - c->outp.done) * c->outp.elsize, cudaMemcpyDeviceToHost, c->d2h_stream));
+    c->outp.done = upto;
+}
+
+void mps_output_reset(struct mpsort_comm * c)
+{
+    if (c->outp.host) c->outp.done = 0;
+}
+
+/* everything not yet on its way leaves now; c->stream then waits for the copy stream */
+static void output_finish(struct mpsort_comm * c)
+{
+    if (!c->outp.host) return;
+    mps_output_ready(c, c->outp.total);
+    CUDA_OK(c, cudaEventRecord(c->io_ev[1], c->d2h_stream));
+    CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->io_ev[1], 0));
+    c->outp.host = NULL;
+}
+
+/* ------------------------------------------------------------------------- */
 /* local sort: replaces radix_sort (radixsort.c:35-44)                        */
 
 struct sorted_view {
@@ -209,9 +328,18 @@ static void local_sort(struct mpsort_comm * c, const void * dbase, size_t n, siz
         hmm[0] = ~0ULL; hmm[1] = 0;
         CUDA_OK(c, cudaMemcpyAsync(minmax, hmm, 2 * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
     }
-    for (g = 0; g < nw; g++) {
-        KERN_T(c, MPS_K_EXTRACT, mpsk_extract_keys(dbase, n, elsize, desc->offset, desc->width, desc->nwords,
-                                     desc->is_signed, g, 0, kw + (size_t) g * n, hist + (size_t) g * 8 * 256, (nw == 1 ? minmax : NULL), c->stream));
+    {
+        /* a host input that is still arriving is read chunk by chunk (histograms and min/max accumulate) */
+        size_t ra[MPS_MAX_CHUNKS + 1];
+        const int nr = mps_input_ranges(c, dbase, n, ra);
+        int i;
+        for (i = 0; i < nr; i++) {
+            mps_input_wait(c, dbase, ra[i], ra[i + 1] - ra[i]);
+            for (g = 0; g < nw; g++)
+                KERN_T(c, MPS_K_EXTRACT, mpsk_extract_keys((const char *) dbase + ra[i] * elsize, ra[i + 1] - ra[i], elsize, desc->offset,
+                                             desc->width, desc->nwords, desc->is_signed, g, 0, kw + (size_t) g * n + ra[i],
+                                             hist + (size_t) g * 8 * 256, (nw == 1 ? minmax : NULL), c->stream));
+        }
     }
     KERN_T(c, MPS_K_EXTRACT, mpsk_scan_histograms(hist, bins, (int) nhist, c->stream));
 
@@ -349,7 +477,7 @@ static void predictor_launch(struct mpsort_comm * c, const void * dbase, size_t 
         const struct mpsort_radix_desc * desc, struct predictor * pr)
 {
     const uint64_t flip = desc->is_signed ? (1ULL << 63) : 0ULL;
-    const size_t tbytes = (size_t) pr->nl * 2 * ((size_t) 1 << MPS_PRED_LOG2_TABLE) * sizeof(uint64_t);
+    const size_t tbytes = (size_t) (pr->nl + 1) * 2 * ((size_t) 1 << MPS_PRED_LOG2_TABLE) * sizeof(uint64_t);
     uint64_t * tab = (uint64_t *) mps_arena_get(c, MPS_S_PRED, tbytes + 64);
     pr->d_pairs = tab + tbytes / sizeof(uint64_t);
     CUDA_OK(c, cudaMemsetAsync(tab, 0, tbytes + 64, c->stream));
@@ -396,9 +524,14 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
     int have_low = 1;
     struct predictor pr;
     memset(&pr, 0, sizeof(pr));
+    size_t ra[MPS_MAX_CHUNKS + 1];
+    const int nr = mps_input_ranges(c, dbase, n, ra);
+    int ri;
     if (hybrid_ok && !getenv("MPSORT_NO_HIST4")) {
         uint64_t * hd = (uint64_t *) mps_host_stage(c, sizeof(uint64_t));
-        KERN_T(c, MPS_K_EXTRACT, mpsk_rec_sample_diff(dbase, n, E, khi, 4096, ddiff, c->stream));
+        /* (of a host input that is still arriving, the preview looks at the first chunk) */
+        mps_input_wait(c, dbase, 0, ra[1]);
+        KERN_T(c, MPS_K_EXTRACT, mpsk_rec_sample_diff(dbase, ra[1], E, khi, 4096, ddiff, c->stream));
         CUDA_OK(c, cudaMemcpyAsync(hd, ddiff, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
         CUDA_OK(c, cudaMemsetAsync(ddiff, 0, sizeof(uint64_t), c->stream));
         CUDA_OK(c, cudaStreamSynchronize(c->stream));
@@ -415,19 +548,30 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
             if (vary >= 7) pr.lobits[pr.nl++] = 8u * (uint32_t) pd[vary - 5];
         }
     }
-    if (have_low) KERN_T(c, MPS_K_EXTRACT, mpsk_rec_histograms(dbase, n, E, khi, flip, 0, 8, hist, ddiff, c->stream));
-    else KERN_T(c, MPS_K_EXTRACT, mpsk_rec_histograms(dbase, n, E, khi, flip, 4, 4, hist, ddiff, c->stream));
+    for (ri = 0; ri < nr; ri++) {
+        /* chunk by chunk behind the copy of a host input; one launch otherwise */
+        const char * part = (const char *) dbase + ra[ri] * E;
+        mps_input_wait(c, dbase, ra[ri], ra[ri + 1] - ra[ri]);
+        if (have_low) KERN_T(c, MPS_K_EXTRACT, mpsk_rec_histograms(part, ra[ri + 1] - ra[ri], E, khi, flip, 0, 8, hist, ddiff, dbase, c->stream));
+        else KERN_T(c, MPS_K_EXTRACT, mpsk_rec_histograms(part, ra[ri + 1] - ra[ri], E, khi, flip, 4, 4, hist, ddiff, dbase, c->stream));
+    }
     KERN_T(c, MPS_K_EXTRACT, mpsk_scan_histograms(hist, bins, 8, c->stream));
     if (pr.nl) predictor_launch(c, dbase, n, E, desc, &pr);
     const size_t hbytes = 8 * 256 * sizeof(uint32_t);
-    uint32_t * hhist = (uint32_t *) mps_host_stage(c, hbytes + 4 * sizeof(uint64_t));
-    uint64_t * htail = (uint64_t *) ((char *) hhist + hbytes);      /* [0] diff, [1..2] predictor pairs */
+    uint32_t * hhist = (uint32_t *) mps_host_stage(c, hbytes + 8 * sizeof(uint64_t));
+    uint64_t * htail = (uint64_t *) ((char *) hhist + hbytes);      /* [0] diff, [1..3] predictor pairs */
     CUDA_OK(c, cudaMemcpyAsync(hhist, hist, hbytes, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(c, cudaMemcpyAsync(htail, ddiff, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
-    if (pr.nl) CUDA_OK(c, cudaMemcpyAsync(htail + 1, pr.d_pairs, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    if (pr.nl) CUDA_OK(c, cudaMemcpyAsync(htail + 1, pr.d_pairs, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
     int digits[8], P = 0;
-    uint64_t pairs_of[2] = { htail[1], htail[2] };
+    /* (pairs of samples that drew the same record are in every count: off they go) */
+    uint64_t pairs_of[2] = { 0, 0 };
+    if (pr.nl) {
+        const uint64_t dup = htail[1 + pr.nl];
+        pairs_of[0] = htail[1] - dup;
+        if (pr.nl > 1) pairs_of[1] = htail[2] - dup;
+    }
     {
         const uint64_t diff = htail[0];
         for (d = 0; d < 8; d++) if ((diff >> (8 * d)) & 255u) digits[P++] = (int) d;
@@ -439,7 +583,7 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
     }
 /* counts of the four low digits, when the first histogram pass left them out */
 #define ENSURE_LOW_HISTOGRAMS() do { if (!have_low) { \
-        KERN_T(c, MPS_K_EXTRACT, mpsk_rec_histograms(dbase, n, E, khi, flip, 0, 4, hist, NULL, c->stream)); \
+        KERN_T(c, MPS_K_EXTRACT, mpsk_rec_histograms(dbase, n, E, khi, flip, 0, 4, hist, NULL, NULL, c->stream)); \
         KERN_T(c, MPS_K_EXTRACT, mpsk_scan_histograms(hist, bins, 8, c->stream)); \
         have_low = 1; } } while (0)
 
@@ -452,10 +596,11 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
         if (pr.nl < nwant || pr.lobits[0] != want[0] || (nwant == 2 && pr.lobits[1] != want[1])) {
             pr.nl = nwant; pr.lobits[0] = want[0]; pr.lobits[1] = want[1];
             predictor_launch(c, dbase, n, E, desc, &pr);
-            uint64_t * h = (uint64_t *) mps_host_stage(c, hbytes + 4 * sizeof(uint64_t)) + hbytes / sizeof(uint64_t);
-            CUDA_OK(c, cudaMemcpyAsync(h + 1, pr.d_pairs, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+            uint64_t * h = (uint64_t *) mps_host_stage(c, hbytes + 8 * sizeof(uint64_t)) + hbytes / sizeof(uint64_t);
+            CUDA_OK(c, cudaMemcpyAsync(h + 1, pr.d_pairs, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
             CUDA_OK(c, cudaStreamSynchronize(c->stream));
-            pairs_of[0] = h[1]; pairs_of[1] = h[2];
+            pairs_of[0] = h[1] - h[1 + pr.nl];
+            pairs_of[1] = pr.nl > 1 ? h[2] - h[1 + pr.nl] : 0;
         }
         const double run4 = predictor_mean_run(pairs_of[0], n);
         const double run5 = nwant == 2 ? predictor_mean_run(pairs_of[1], n) : 1e30;
@@ -473,7 +618,20 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
             uint32_t * wl = (uint32_t *) mps_arena_get(c, MPS_S_MERGE_CUT, (2 * MPS_HYBRID_MAX_LONG_RUNS + 64) * sizeof(uint32_t));
             uint32_t * nwork = wl + 2 * MPS_HYBRID_MAX_LONG_RUNS;
             CUDA_OK(c, cudaMemsetAsync(nwork, 0, sizeof(uint32_t), c->stream));
-            KERN_T(c, MPS_K_HYBRID, mpsk_fixup_rec(dest, n, E, desc->offset == 8, flip, lobits, wl, nwork, MPS_HYBRID_MAX_LONG_RUNS, c->stream));
+            if (c->outp.host && dest == c->outp.dout && n == c->outp.total) {
+                /* the sorted records are a host output: fix up a range of tiles, send it on, next range */
+                const size_t tile = mpsk_fixup_tile_items(), ntile = (n + tile - 1) / tile;
+                const size_t per = (MPS_CHUNK_BYTES / E + tile - 1) / tile;
+                size_t t0;
+                for (t0 = 0; t0 < ntile; t0 += per) {
+                    KERN_T(c, MPS_K_HYBRID, mpsk_fixup_rec(dest, n, E, desc->offset == 8, flip, lobits, wl, nwork, MPS_HYBRID_MAX_LONG_RUNS,
+                                                           t0, per, c->stream));
+                    if (t0 + per < ntile) mps_output_ready(c, (t0 + per) * tile);
+                }
+            } else {
+                KERN_T(c, MPS_K_HYBRID, mpsk_fixup_rec(dest, n, E, desc->offset == 8, flip, lobits, wl, nwork, MPS_HYBRID_MAX_LONG_RUNS,
+                                                       0, 0, c->stream));
+            }
             uint32_t * h = (uint32_t *) mps_host_stage(c, (2 * MPS_HYBRID_MAX_LONG_RUNS + 1) * sizeof(uint32_t));
             CUDA_OK(c, cudaMemcpyAsync(h, nwork, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
             CUDA_OK(c, cudaStreamSynchronize(c->stream));
@@ -481,13 +639,14 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
             out->npasses = (uint32_t) H;
             c->stats.hybrid = 1;
             c->stats.hybrid_long_runs = nlong;
+            if (nlong > 0) mps_output_reset(c);          /* long runs are sorted below: ranges already sent go again */
             if (nlong > MPS_HYBRID_MAX_LONG_RUNS) {
                 /* the predictor was wrong: finish with a full stable LSD of what we have
                  * (a permutation of the input in which equal keys kept their order) */
                 if (!have_low) {
                     /* (histograms are permutation invariant: counting dest is counting dbase,
                      * which an in-place sort has already overwritten) */
-                    KERN_T(c, MPS_K_EXTRACT, mpsk_rec_histograms(dest, n, E, khi, flip, 0, 4, hist, NULL, c->stream));
+                    KERN_T(c, MPS_K_EXTRACT, mpsk_rec_histograms(dest, n, E, khi, flip, 0, 4, hist, NULL, NULL, c->stream));
                     KERN_T(c, MPS_K_EXTRACT, mpsk_scan_histograms(hist, bins, 8, c->stream));
                     have_low = 1;
                 }
@@ -628,6 +787,7 @@ static void gather_sort(struct mpsort_comm * c, const void * dbase, void * dout,
         if (nmemb[j] > nmemb[leader]) leader = j;
     }
     int64_t * cut = (int64_t *) malloc(sizeof(int64_t) * (size_t) p * (p + 1));
+    mps_input_wait(c, dbase, 0, (size_t) nmemb[c->rank]);
     /* 1: everyone -> leader */
     for (j = 0; j < p; j++) for (k = 0; k <= p; k++) cut[(size_t) j * (p + 1) + k] = (k <= leader) ? 0 : nmemb[j];
     char * all = (char *) mps_arena_get(c, MPS_S_RECV, (size_t) (c->rank == leader ? total : 0) * elsize);
@@ -1005,6 +1165,8 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
                 KERN_T(c, MPS_K_GATHER_RECORDS, mpsk_gather_records(part_in, v2.idx, part_out, (size_t) cnt, elsize, c->stream));
                 c->stats.second_sort_passes = v2.npasses;
             }
+            /* a host output leaves part by part, beside the merge of the next part */
+            if (q + 1 < Q) mps_output_ready(c, (size_t) (base + cnt));
         }
         if (Q > 1) {
             CUDA_OK(c, cudaEventRecord(c->phase_ev[MPS_MAX_RANKS], c->stream));
@@ -1062,9 +1224,11 @@ void mpsort_mpi_newarray_desc_impl(void * base, size_t nmemb,
     const int out_dev = (outnmemb == 0) ? 1 : is_device_pointer(c, out);
     const void * dbase = base;
     void * dout = out;
+    c->in.dbase = NULL;
+    c->outp.host = NULL;
     if (!in_dev) {
         void * din = mps_arena_get(c, MPS_S_DIN, nmemb * elsize);
-        CUDA_OK(c, cudaMemcpyAsync(din, base, nmemb * elsize, cudaMemcpyHostToDevice, c->stream));
+        input_stage(c, din, base, nmemb, elsize);
         dbase = din;
     }
     if (!out_dev) {
@@ -1076,16 +1240,24 @@ void mpsort_mpi_newarray_desc_impl(void * base, size_t nmemb,
 
     uint64_t sum1 = 0;
     const int verify = mpsort_mpi_has_options(MPSORT_VERIFY_CHECKSUM);
-    if (verify) sum1 = device_checksum(c, dbase, nmemb * elsize);
+    if (verify) {
+        mps_input_wait(c, dbase, 0, nmemb);
+        sum1 = device_checksum(c, dbase, nmemb * elsize);
+    }
+    /* (with the checksum on, the output is only sent once it has been verified) */
+    if (!out_dev && !verify) output_begin(c, out, dout, outnmemb, elsize);
 
     histogram_sort(c, dbase, nmemb, dout, outnmemb, elsize, desc);
+    mps_input_wait(c, dbase, 0, nmemb);            /* (paths that never looked at the input: empty ranks) */
+    c->in.dbase = NULL;
 
     if (verify) {
         const uint64_t sum2 = device_checksum(c, dout, outnmemb * elsize);
         if (sum1 != sum2)
             mps_fatal(c, __FILE__, __LINE__, "Data changed after sorting; checksum mismatch");   /* :324-330 */
     }
-    if (!out_dev && outnmemb > 0)
+    if (c->outp.host) output_finish(c);
+    else if (!out_dev && outnmemb > 0)
         CUDA_OK(c, cudaMemcpyAsync(out, dout, outnmemb * elsize, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
     mps_merge_ovf_check(c);

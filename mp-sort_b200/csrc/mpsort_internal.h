@@ -104,6 +104,26 @@ struct mpsort_comm {
     uint32_t * d_merge_ovf;                    /* device u32: tiles that broke their bound */
     uint32_t * h_merge_ovf;                    /* pinned copy */
     int merge_ovf_pending;
+
+    /* Host buffers. A large host INPUT arrives in chunks on its own copy stream and the
+     * histogram / key-extraction pass of FirstSort runs chunk by chunk behind it; a host OUTPUT leaves range by
+     * range on a second copy stream as soon as a prefix of it is final (fix-up chunks, merged exchange parts),
+     * while the rest is still being produced. */
+#define MPS_MAX_CHUNKS 32
+    struct {
+        const void * dbase;                    /* the staged device copy the chunks land in (NULL: not chunked) */
+        size_t n, elsize, chunk;               /* records in all, bytes per record, records per chunk */
+        int nchunks, waited;                   /* chunks, and how many of them c->stream has waited for */
+        cudaEvent_t ev[MPS_MAX_CHUNKS];
+    } in;
+    struct {
+        void * host;                           /* NULL: the output is not a staged host buffer */
+        const void * dout;
+        size_t elsize, total, done;            /* records: in all / already on their way */
+    } outp;
+    cudaStream_t h2d_stream, d2h_stream;
+    cudaEvent_t io_ev[2];
+    int io_created;
     cudaEvent_t phase_ev[MPS_MAX_RANKS + 1];
     int phase_ev_created;
 
@@ -169,6 +189,18 @@ void mps_host_free(void * ptr, const char * file, int line);
 void mps_merge_ovf_begin(struct mpsort_comm * c);
 void mps_merge_ovf_fetch(struct mpsort_comm * c);     /* async copy to the pinned words on c->stream */
 void mps_merge_ovf_check(struct mpsort_comm * c);     /* after the stream was synchronised */
+
+/* ---- chunked host input / output (mpsort_host.c) ---- */
+/* c->stream goes on only after records [first, first + count) of the staged input dbase have arrived
+ * (no-op for any other pointer) */
+void mps_input_wait(struct mpsort_comm * c, const void * dbase, size_t first, size_t count);
+/* the ranges to process dbase in: a[0] = 0 < a[1] < ... < a[nr] = n; returns nr (1 unless dbase is chunked) */
+int mps_input_ranges(struct mpsort_comm * c, const void * dbase, size_t n, size_t * a);
+/* records [0, upto) of the staged output are final once what is queued on c->stream has run: send on what
+ * has not left yet (no-op unless the output is a staged host buffer) */
+void mps_output_ready(struct mpsort_comm * c, size_t upto);
+/* forget what was announced: everything is sent again at the end (a late change to records already sent) */
+void mps_output_reset(struct mpsort_comm * c);
 
 /* ---- arena ---- */
 void * mps_arena_get(struct mpsort_comm * c, int slot, size_t bytes);

@@ -36,10 +36,12 @@ int mpsk_extract_keys(const void * base, size_t n, size_t elsize,
 /* Record mode (elsize 8 or 16, key = one aligned u64 in the low or high half): counts of
  * the nh (4 or 8) digits d0 .. d0+nh-1 of (key ^ flip) are ADDED to hist[d][256], and the
  * OR of (key ^ key[0]) over all records is ORed into *diff (device u64, may be NULL):
- * byte b of *diff is zero exactly when digit b is the same in every key.
+ * byte b of *diff is zero exactly when digit b is the same in every key. `ref` is the record whose key
+ * stands for key[0] (NULL: recs itself): an array counted in several calls, chunk by chunk as it arrives
+ * from the host, passes the first record of the WHOLE array every time.
  * mpsk_rec_sample_diff does the OR over s evenly spaced records only (a preview). */
 int mpsk_rec_histograms(const void * recs, size_t n, size_t elsize, int key_in_high, uint64_t flip,
-        uint32_t d0, uint32_t nh, uint32_t * hist, uint64_t * diff, mpsk_stream_t stream);
+        uint32_t d0, uint32_t nh, uint32_t * hist, uint64_t * diff, const void * ref, mpsk_stream_t stream);
 int mpsk_rec_sample_diff(const void * recs, size_t n, size_t elsize, int key_in_high, uint32_t s,
         uint64_t * diff, mpsk_stream_t stream);
 
@@ -75,13 +77,18 @@ int mpsk_onesweep_pass_rec(const void * in, void * out, size_t n, size_t elsize,
  * (*nwork counts them, also beyond cap; both device memory, *nwork zeroed by the
  * caller). mpsk_fixup_extents turns starts into lengths. */
 int mpsk_fixup_rec(void * recs, size_t n, size_t elsize, int key_in_high, uint64_t flip, uint32_t lobits,
-        uint32_t * worklist, uint32_t * nwork, uint32_t cap, mpsk_stream_t stream);
+        uint32_t * worklist, uint32_t * nwork, uint32_t cap, size_t tile0, size_t ntiles, mpsk_stream_t stream);
+/* records per fix-up tile. mpsk_fixup_rec handles the runs whose first record lies in tiles
+ * [tile0, tile0 + ntiles) of the n records (ntiles = 0: all of them): once tiles 0 .. t-1 are done, records
+ * 0 .. t * tile_items - 1 are final, so the output can leave for the host range by range. */
+size_t mpsk_fixup_tile_items(void);
 int mpsk_fixup_extents(const void * recs, size_t n, size_t elsize, int key_in_high, uint64_t flip, uint32_t lobits,
         const uint32_t * worklist, uint32_t nwork, uint32_t * lengths, mpsk_stream_t stream);
 /* predictor of the hybrid sort: pairs[j] += the number of equal PAIRS (sum of k(k-1)/2 over values)
- * among the high parts (key ^ flip) >> lobits[j] of s evenly spaced records, for j < nl <= 2 at once.
- * table: device u64[nl][2 << log2_tsize], zeroed by the caller, 1 << log2_tsize >= 2 s; pairs: device
- * u64[2], zeroed by the caller. lobits is a host array. */
+ * among the high parts (key ^ flip) >> lobits[j] of s records at pseudo-random positions, for j < nl <= 2
+ * at once; pairs[nl] += the pairs of samples that drew the SAME position (they are in every pairs[j] too:
+ * the caller takes them off). table: device u64[nl + 1][2 << log2_tsize], zeroed by the caller,
+ * 1 << log2_tsize >= 2 s; pairs: device u64[3], zeroed by the caller. lobits is a host array. */
 int mpsk_prefix_pairs(const void * recs, size_t n, size_t elsize, uint32_t s, int key_in_high, uint64_t flip,
         const uint32_t * lobits, uint32_t nl, uint64_t * table, uint32_t log2_tsize, uint64_t * pairs, mpsk_stream_t stream);
 

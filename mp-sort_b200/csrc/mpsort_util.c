@@ -14,6 +14,12 @@ int mpsort_util_device_count(void)
     return n;
 }
 
+int mpsort_util_device_pci_bus_id(int device, char * buf, int len)
+{
+    if (cudaDeviceGetPCIBusId(buf, len, device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return 0;
+}
+
 void * mpsort_util_dev_malloc(int device, size_t nbytes)
 {
     void * p = NULL;

@@ -119,6 +119,7 @@ _proto("mpsort_key_range", c_int, c_int, ctypes.c_uint32, ctypes.POINTER(c_i64),
 
 # ---- include/mpsort_util.h --------------------------------------------------
 _proto("mpsort_util_device_count", c_int)
+_proto("mpsort_util_device_pci_bus_id", c_int, c_int, ctypes.c_char_p, c_int)
 _proto("mpsort_util_dev_malloc", c_void_p, c_int, c_size_t)
 _proto("mpsort_util_dev_free", None, c_int, c_void_p)
 _proto("mpsort_util_host_malloc_pinned", c_void_p, c_size_t)

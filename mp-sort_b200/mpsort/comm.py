@@ -26,6 +26,7 @@ class Comm(object):
         self.rank = lib.mpsort_comm_rank(self.handle)
         self.size = lib.mpsort_comm_size(self.handle)
         self.device = lib.mpsort_comm_device(self.handle)
+        self.numa = None
 
     # ---- construction --------------------------------------------------
     @classmethod
@@ -58,8 +59,11 @@ class Comm(object):
         rank = int(os.environ.get("RANK", "0"))
         size = int(os.environ.get("WORLD_SIZE", "1"))
         local = int(os.environ.get("LOCAL_RANK", str(rank)))
+        numa = bind_to_device_numa_node(local)
         if size <= 1:
-            return cls.self(local)
+            comm = cls.self(local)
+            comm.numa = numa
+            return comm
         uid = ctypes.create_string_buffer(C.MPSORT_UNIQUE_ID_BYTES)
         path = _rendezvous_path()
         if rank == 0:
@@ -78,6 +82,7 @@ class Comm(object):
             with open(path, "rb") as f:
                 uid.raw = f.read(C.MPSORT_UNIQUE_ID_BYTES)
         comm = cls(lib.mpsort_comm_init_rank(rank, size, uid, local))
+        comm.numa = numa
         comm.barrier()
         if rank == 0:
             try:
@@ -140,6 +145,50 @@ class Comm(object):
 
     def __repr__(self):
         return "<mpsort.Comm rank %d of %d on cuda:%d>" % (self.rank, self.size, self.device)
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.update(range(int(a), int(b) + 1))
+        else:
+            cpus.add(int(part))
+    return cpus
+
+
+def bind_to_device_numa_node(device):
+    """One process per GPU: run this process on the CPUs of the NUMA node its GPU hangs off, so that the
+    host buffers it allocates and pins afterwards (first touch) are local to that GPU's PCIe root. With eight
+    ranks staging 4 GiB each way, buffers that all land on one socket leave half of the GPUs copying across
+    the socket interconnect. MPSORT_NO_NUMA_BIND=1 leaves the affinity alone. Returns a short description
+    (None when nothing was done: single node, no sysfs entry, or an affinity the launcher already narrowed)."""
+    if os.environ.get("MPSORT_NO_NUMA_BIND"):
+        return None
+    try:
+        buf = ctypes.create_string_buffer(64)
+        if lib.mpsort_util_device_pci_bus_id(device, buf, 64) != 0:
+            return None
+        bus = buf.value.decode().lower()
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = _parse_cpulist(f.read())
+        have = os.sched_getaffinity(0)
+        if len(have) < (os.cpu_count() or 0):
+            return "affinity already set by the launcher (%d cpus); left alone" % len(have)
+        use = cpus & have
+        if not use or use == have:
+            return None
+        os.sched_setaffinity(0, use)
+        return "cuda:%d %s -> NUMA node %d (%d cpus)" % (device, bus, node, len(use))
+    except (OSError, ValueError, AttributeError):
+        return None
 
 
 _rdzv_seq = [0]

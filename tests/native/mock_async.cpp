@@ -58,12 +58,12 @@ ncclResult_t mocksync_ncclGroupStart(void);
 ncclResult_t mocksync_ncclGroupEnd(void);
 #define K(name) mocksync_##name
 int K(mpsk_extract_keys)(const void *, size_t, size_t, size_t, uint32_t, uint32_t, int, uint32_t, uint64_t, uint64_t *, uint32_t *, uint64_t *, mpsk_stream_t);
-int K(mpsk_rec_histograms)(const void *, size_t, size_t, int, uint64_t, uint32_t, uint32_t, uint32_t *, uint64_t *, mpsk_stream_t);
+int K(mpsk_rec_histograms)(const void *, size_t, size_t, int, uint64_t, uint32_t, uint32_t, uint32_t *, uint64_t *, const void *, mpsk_stream_t);
 int K(mpsk_rec_sample_diff)(const void *, size_t, size_t, int, uint32_t, uint64_t *, mpsk_stream_t);
 int K(mpsk_scan_histograms)(const uint32_t *, uint32_t *, int, mpsk_stream_t);
 int K(mpsk_onesweep_pass)(const uint64_t *, const uint32_t *, uint64_t *, uint32_t *, size_t, int, const uint32_t *, void *, mpsk_stream_t);
 int K(mpsk_onesweep_pass_rec)(const void *, void *, size_t, size_t, int, int, uint64_t, const uint32_t *, void *, mpsk_stream_t);
-int K(mpsk_fixup_rec)(void *, size_t, size_t, int, uint64_t, uint32_t, uint32_t *, uint32_t *, uint32_t, mpsk_stream_t);
+int K(mpsk_fixup_rec)(void *, size_t, size_t, int, uint64_t, uint32_t, uint32_t *, uint32_t *, uint32_t, size_t, size_t, mpsk_stream_t);
 int K(mpsk_fixup_extents)(const void *, size_t, size_t, int, uint64_t, uint32_t, const uint32_t *, uint32_t, uint32_t *, mpsk_stream_t);
 int K(mpsk_prefix_pairs)(const void *, size_t, size_t, uint32_t, int, uint64_t, const uint32_t *, uint32_t, uint64_t *, uint32_t, uint64_t *, mpsk_stream_t);
 int K(mpsk_gather_u64)(const uint64_t *, const uint32_t *, uint64_t *, size_t, mpsk_stream_t);
@@ -410,10 +410,10 @@ int mpsk_extract_keys(const void * base, size_t n, size_t elsize, size_t offset,
 { LAUNCH(stream, K(mpsk_extract_keys)(base, n, elsize, offset, width, nwords, is_signed, g, sub, kout, hist, minmax, stream)); }
 
 int mpsk_rec_histograms(const void * recs, size_t n, size_t elsize, int khi, uint64_t flip, uint32_t d0, uint32_t nh,
-        uint32_t * hist, uint64_t * diff, mpsk_stream_t stream)
+        uint32_t * hist, uint64_t * diff, const void * ref, mpsk_stream_t stream)
 {
     if (n && ((elsize != 8 && elsize != 16) || (nh != 4 && nh != 8) || d0 + nh > 8)) return (int) cudaErrorInvalidValue;
-    LAUNCH(stream, K(mpsk_rec_histograms)(recs, n, elsize, khi, flip, d0, nh, hist, diff, stream));
+    LAUNCH(stream, K(mpsk_rec_histograms)(recs, n, elsize, khi, flip, d0, nh, hist, diff, ref, stream));
 }
 
 int mpsk_rec_sample_diff(const void * recs, size_t n, size_t elsize, int khi, uint32_t s, uint64_t * diff, mpsk_stream_t stream)
@@ -437,8 +437,8 @@ int mpsk_onesweep_pass_rec(const void * in, void * out, size_t n, size_t elsize,
 }
 
 int mpsk_fixup_rec(void * recs, size_t n, size_t elsize, int khi, uint64_t flip, uint32_t lobits, uint32_t * worklist,
-        uint32_t * nwork, uint32_t cap, mpsk_stream_t stream)
-{ LAUNCH(stream, K(mpsk_fixup_rec)(recs, n, elsize, khi, flip, lobits, worklist, nwork, cap, stream)); }
+        uint32_t * nwork, uint32_t cap, size_t tile0, size_t ntiles, mpsk_stream_t stream)
+{ LAUNCH(stream, K(mpsk_fixup_rec)(recs, n, elsize, khi, flip, lobits, worklist, nwork, cap, tile0, ntiles, stream)); }
 
 int mpsk_fixup_extents(const void * recs, size_t n, size_t elsize, int khi, uint64_t flip, uint32_t lobits,
         const uint32_t * worklist, uint32_t nwork, uint32_t * lengths, mpsk_stream_t stream)

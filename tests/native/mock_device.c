@@ -104,6 +104,13 @@ cudaError_t cudaEventElapsedTime(float * ms, cudaEvent_t a, cudaEvent_t b)
 cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
 cudaError_t cudaSetDevice(int d) { (void) d; return cudaSuccess; }
 cudaError_t cudaGetDevice(int * d) { *d = 0; return cudaSuccess; }
+cudaError_t cudaDeviceGetPCIBusId(char * pciBusId, int len, int device)
+{
+    (void) device;
+    if (len > 0) pciBusId[0] = 0;
+    return cudaErrorInvalidDevice;      /* no PCI address: callers skip NUMA placement */
+}
+
 cudaError_t cudaGetDeviceCount(int * n) { *n = 1; return cudaSuccess; }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 const char * cudaGetErrorString(cudaError_t e) { (void) e; return "mock device error"; }
@@ -425,7 +432,7 @@ static uint64_t rec_key(const void * recs, size_t i, size_t elsize, int khi, uin
 }
 
 int mpsk_rec_histograms(const void * recs, size_t n, size_t elsize, int khi, uint64_t flip, uint32_t d0, uint32_t nh,
-        uint32_t * hist, uint64_t * diff, mpsk_stream_t stream)
+        uint32_t * hist, uint64_t * diff, const void * ref, mpsk_stream_t stream)
 {
     size_t i;
     uint32_t q;
@@ -433,7 +440,7 @@ int mpsk_rec_histograms(const void * recs, size_t n, size_t elsize, int khi, uin
     if (n == 0) return 0;
     if ((elsize != 8 && elsize != 16) || (nh != 4 && nh != 8) || d0 + nh > 8) return (int) cudaErrorInvalidValue;
     LAUNCHED();
-    const uint64_t k0 = rec_key(recs, 0, elsize, khi, flip);
+    const uint64_t k0 = rec_key(ref ? ref : recs, 0, elsize, khi, flip);
     uint64_t acc = 0;
     for (i = 0; i < n; i++) {
         const uint64_t k = rec_key(recs, i, elsize, khi, flip);
@@ -509,16 +516,28 @@ int mpsk_onesweep_pass_rec(const void * in, void * out, size_t n, size_t elsize,
     return 0;
 }
 
+size_t mpsk_fixup_tile_items(void) { return 2048; }
+
 int mpsk_fixup_rec(void * recs, size_t n, size_t elsize, int khi, uint64_t flip, uint32_t lobits,
-        uint32_t * worklist, uint32_t * nwork, uint32_t cap, mpsk_stream_t stream)
+        uint32_t * worklist, uint32_t * nwork, uint32_t cap, size_t tile0, size_t ntiles, mpsk_stream_t stream)
 {
     size_t i = 0;
     (void) stream;
-    if (n == 0) return 0;
+    if (n == 0 || tile0 * 2048 >= n) return 0;
     LAUNCHED();
+    /* runs whose first record lies in tiles [tile0, tile0 + ntiles) */
+    const size_t first = tile0 * 2048, last = ntiles ? (tile0 + ntiles) * 2048 : n;
+    /* back up to the head of the run that `first` sits in: that run belongs to an earlier tile */
+    i = first;
+    while (i > 0 && i < n && (lobits >= 64 ? 0 : rec_key(recs, i - 1, elsize, khi, flip) >> lobits)
+                             == (lobits >= 64 ? 0 : rec_key(recs, i, elsize, khi, flip) >> lobits)) i--;
+    if (i < first) {                       /* skip it */
+        const uint64_t hi0 = lobits >= 64 ? 0 : rec_key(recs, i, elsize, khi, flip) >> lobits;
+        while (i < n && (lobits >= 64 ? 0 : rec_key(recs, i, elsize, khi, flip) >> lobits) == hi0) i++;
+    }
     const uint64_t lomask = lobits >= 64 ? ~0ULL : ((1ULL << lobits) - 1ULL);
     char * tmp = (char *) malloc(256 * elsize);
-    while (i < n) {
+    while (i < n && i < last) {
         size_t j = i + 1, a, b;
         const uint64_t hi = lobits >= 64 ? 0 : rec_key(recs, i, elsize, khi, flip) >> lobits;
         while (j < n && (lobits >= 64 ? 0 : rec_key(recs, j, elsize, khi, flip) >> lobits) == hi) j++;
@@ -569,6 +588,14 @@ int mpsk_fixup_extents(const void * recs, size_t n, size_t elsize, int khi, uint
     return 0;
 }
 
+static uint64_t mock_mix64(uint64_t x)
+{
+    uint64_t z = x + 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
 static int cmp_u64(const void * a, const void * b)
 {
     const uint64_t x = *(const uint64_t *) a, y = *(const uint64_t *) b;
@@ -585,13 +612,13 @@ int mpsk_prefix_pairs(const void * recs, size_t n, size_t elsize, uint32_t s, in
     if (nl > 2) return 1;
     LAUNCHED();
     uint64_t * v = (uint64_t *) malloc(sizeof(uint64_t) * s);
-    for (j = 0; j < nl; j++) {
+    for (j = 0; j <= nl; j++) {
         for (i = 0; i < s; i++) {
-            const size_t pos = (size_t) (((unsigned __int128) i * n) / s);
+            const size_t pos = (size_t) (mock_mix64(0x5EED5A3Bu + i) % (uint64_t) n);
             uint64_t k;
             memcpy(&k, (const unsigned char *) recs + pos * elsize + ((khi && elsize == 16) ? 8 : 0), 8);
             k ^= flip;
-            v[i] = lobits[j] >= 64 ? 0 : k >> lobits[j];
+            v[i] = j == nl ? (uint64_t) pos : (lobits[j] >= 64 ? 0 : k >> lobits[j]);      /* [nl]: positions drawn twice */
         }
         qsort(v, s, sizeof(uint64_t), cmp_u64);
         uint64_t c = 0;
@@ -880,14 +907,6 @@ int mpsk_checksum(const void * base, size_t nbytes, uint64_t * sum, mpsk_stream_
     for (i = 0; i < nbytes; i++) s += (uint64_t) (int64_t) ((const signed char *) base)[i];
     *sum += s;
     return 0;
-}
-
-static uint64_t mock_mix64(uint64_t x)
-{
-    uint64_t z = x + 0x9E3779B97F4A7C15ULL;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-    return z ^ (z >> 31);
 }
 
 int mpsk_multiset_hash(const void * base, size_t n, size_t elsize, uint64_t * out, mpsk_stream_t stream)

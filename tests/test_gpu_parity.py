@@ -436,6 +436,27 @@ def test_verify_checksum_option():
     assert same(out, O.numpy_sort([a[:9000], a[9000:]], O.Desc(0, 8, 1, 0, 0), [10000, 10000]))
 
 
+def test_randomised_cases_against_the_oracle():
+    """tests/support/hostflow_fuzz.py (the generator of the CPU host-flow tests) against the REAL library: 150 random
+    cases on rank threads of one GPU -- ranks, sizes with zeros, output layouts, record and key shapes, key
+    distributions, options, 1-4 exchange parts on tiny inputs, every shipped host-side switch -- byte for byte
+    against the oracle's contract"""
+    env = dict(os.environ, FUZZ_SWITCHES="shipped")
+    rc = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "support", "hostflow_fuzz.py"), "20261019", "150"],
+                        env=env, timeout=1200, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert rc.returncode == 0 and b"FUZZ OK" in rc.stdout, rc.stdout.decode()[-4000:]
+
+
+def test_host_buffers_in_chunks():
+    """SURVEY 8 f4 on the GPU: host input in chunks behind which the histogram pass runs, host output leaving range by
+    range beside the fix-up / the merges (tests/support/chunk_worker.py, tiny chunks), byte for byte against the oracle"""
+    env = dict(os.environ, MPSORT_CHUNK_MIN_BYTES="4096", MPSORT_CHUNK_BYTES="1000000", MPSORT_EXCHANGE_PHASES="2",
+               MPSORT_PHASES_MIN_RECORDS="1000")
+    rc = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "support", "chunk_worker.py")], env=env, timeout=600,
+                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert rc.returncode == 0 and b"CHUNK OK" in rc.stdout, rc.stdout.decode()[-4000:]
+
+
 # ------------------------------------------------------------------ full size, by properties
 def test_multiset_hash_matches_oracle_and_sees_what_a_byte_sum_cannot():
     """the whole-record multiset hash of the property checks: equal to the numpy restatement,

@@ -92,6 +92,19 @@ def test_exchange_in_parts_at_2_22_records_per_rank(mock_env, E, kind, extra):
     assert rc.returncode == 0 and b"CANDIDATE OK" in rc.stdout, rc.stdout.decode()[-4000:]
 
 
+@pytest.mark.parametrize("seed", ["", "3", "11"], ids=["immediate", "deferred-3", "deferred-11"])
+def test_host_buffers_in_chunks(mock_env, seed):
+    """a host input that arrives in chunks behind which the histogram pass runs, a host output that leaves
+    range by range beside the fix-up / the merge of the next exchange part -- with tiny chunks, every stream operation
+    run at once and deferred + randomly interleaved (a reader that does not wait for its chunk shows here)"""
+    extra = {"MPSORT_CHUNK_MIN_BYTES": "4096", "MPSORT_CHUNK_BYTES": "1000000", "MPSORT_EXCHANGE_PHASES": "2",
+             "MPSORT_PHASES_MIN_RECORDS": "1000"}
+    if seed:
+        extra["MOCK_ASYNC"] = seed
+    rc = run_py(mock_env, [os.path.join(ROOT, "tests", "support", "chunk_worker.py")], **extra)
+    assert rc.returncode == 0 and b"CHUNK OK" in rc.stdout, rc.stdout.decode()[-4000:]
+
+
 def test_bench_gpu_arm_runs_end_to_end_on_the_mock(mock_env):
     """bench.py itself (not a stand-in for it): device-resident leg, e2e leg through mpsort.sort, verification,
     roofline bookkeeping, one JSON line. Numbers are meaningless here; the control flow is what is checked."""

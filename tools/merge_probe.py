@@ -48,9 +48,9 @@ kt = C.kernel_times(comm)
 bad = lib.mpsort_util_check_sorted(comm, out, n, E, ctypes.byref(desc), 1, 8, None)
 h_out = C.multiset_hash(comm, out, n, E)
 st = C.last_stats(comm, 1)
-print("%-24s merge p=%d n=2^%d E=%d kind=%d: %.3f ms per merge (wall, incl. sample sort + host syncs) = %.0f GB/s (2E per record)  "
+print("%-36s merge p=%d n=2^%d E=%d kind=%d: %.3f ms per merge (wall, incl. sample sort + host syncs) = %.0f GB/s (2E per record)  "
       "bad=%d multiset_ok=%s | %s" % (
-          os.path.basename(os.environ.get("MPSORT_LIB", "default")),
+          os.path.basename(os.environ.get("MPSORT_LIB", "default")) + " " + " ".join("%s=%s" % (k[7:], v) for k, v in sorted(os.environ.items()) if k.startswith("MPSORT_") and k != "MPSORT_LIB"),
           p, log2n, E, kind, ms, 2.0 * E * n / ms / 1e6, bad, h_in == h_out,
           "  ".join("%s %.3f/%d" % (k, v[0] / reps, v[1] // reps) for k, v in kt.items() if v[1])))
 if bad or h_in != h_out:
