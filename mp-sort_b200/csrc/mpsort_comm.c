@@ -265,9 +265,6 @@ mpsort_comm_t mpsort_comm_init_rank(int rank, int size, const void * unique_id, 
     c->p2p.copy_engine = getenv("MPSORT_P2P_CE") ? atoi(getenv("MPSORT_P2P_CE")) : 1;
     if (c->p2p.copy_engine < 0) c->p2p.copy_engine = 0;
     if (c->p2p.copy_engine > 7) c->p2p.copy_engine = 7;
-    c->p2p.split = getenv("MPSORT_P2P_SPLIT") ? atoi(getenv("MPSORT_P2P_SPLIT")) : 1;
-    if (c->p2p.split < 1) c->p2p.split = 1;
-    if (c->p2p.split > 7) c->p2p.split = 7;
     return c;
 }
 
@@ -706,41 +703,17 @@ static void exchange_p2p(struct mpsort_comm * c, const void * sendbuf, const int
              * Every copy stream that gets a copy first waits for the send buffer (the main stream
              * up to here) and the main stream then waits for every one of them -- stream 7 included,
              * whatever p is (it used to be left out for p < 8: found by the CPU stream model,
-             * tests/native/mock_async.cpp). */
-            /* A large remote slice may be cut into `split` pieces that move at the same time on
-             * different copy streams (MPSORT_P2P_SPLIT; with two GPUs one copy per direction does not
-             * fill the 18 links). Piece i of the slice dealt to lane l goes to stream l * split + i;
-             * lanes * split <= 7 keeps stream 7 for the own slice. */
-            const int lanes = c->p2p.copy_engine;
-            int split = c->p2p.split;
-            while (split > 1 && lanes * split > 7) split--;
+             * tests/native/mock_async.cpp). (Cutting a slice into two or four copies that move at the same time
+             * was measured at two GPUs, where one copy per direction is all there is: no gain,
+             * profiles/r02_call_n2_nccl_parity_parts_candidates.log -- a single copy already runs at 770 GB/s.) */
             unsigned used = 0;
-            for (k = 0; k < p; k++) {
-                if (!rbytes[k]) continue;
-                if (!rrem[k]) { used |= 1u << 7; continue; }
-                const int pieces = (rbytes[k] >= ((uint64_t) 8 << 20)) ? split : 1;
-                int i;
-                for (i = 0; i < pieces; i++) used |= 1u << ((k % lanes) * split + i);
-            }
+            for (k = 0; k < p; k++) if (rbytes[k]) used |= 1u << (rrem[k] ? k % c->p2p.copy_engine : 7);
             CUDA_OK(c, cudaEventRecord(c->p2p.ce_ev[8], c->stream));
             for (k = 0; k < 8; k++) if ((used >> k) & 1u) CUDA_OK(c, cudaStreamWaitEvent(c->p2p.ce_stream[k], c->p2p.ce_ev[8], 0));
-            for (k = 0; k < p; k++) {
-                if (!rbytes[k]) continue;
-                if (!rrem[k]) {
-                    CUDA_OK(c, cudaMemcpyAsync(rdst[k], rsrc[k], (size_t) rbytes[k], cudaMemcpyDeviceToDevice, c->p2p.ce_stream[7]));
-                    continue;
-                }
-                const int pieces = (rbytes[k] >= ((uint64_t) 8 << 20)) ? split : 1;
-                /* pieces are whole records: cut at multiples of elsize */
-                const uint64_t nrec = rbytes[k] / elsize, per = (nrec + (uint64_t) pieces - 1) / (uint64_t) pieces;
-                int i;
-                for (i = 0; i < pieces; i++) {
-                    const uint64_t r0 = per * (uint64_t) i, r1 = (r0 + per < nrec) ? r0 + per : nrec;
-                    if (r0 >= r1) break;
-                    CUDA_OK(c, cudaMemcpyAsync((char *) rdst[k] + r0 * elsize, (const char *) rsrc[k] + r0 * elsize, (size_t) ((r1 - r0) * elsize),
-                                               cudaMemcpyDeviceToDevice, c->p2p.ce_stream[(k % lanes) * split + i]));
-                }
-            }
+            for (k = 0; k < p; k++)
+                if (rbytes[k])
+                    CUDA_OK(c, cudaMemcpyAsync(rdst[k], rsrc[k], (size_t) rbytes[k], cudaMemcpyDeviceToDevice,
+                                               c->p2p.ce_stream[rrem[k] ? k % c->p2p.copy_engine : 7]));
             for (k = 0; k < 8; k++) {
                 if (!((used >> k) & 1u)) continue;
                 CUDA_OK(c, cudaEventRecord(c->p2p.ce_ev[k], c->p2p.ce_stream[k]));
@@ -752,8 +725,10 @@ static void exchange_p2p(struct mpsort_comm * c, const void * sendbuf, const int
     }
     /* push: all stores into my buffer are complete when everyone's kernel is; pull: nobody
      * may reuse its send buffer before everyone has read it. A one-word all-reduce on the
-     * stream is the barrier (stream ordered, no host involvement). */
-    NCCL_OK(c, ncclAllReduce(c->p2p.d_flag, c->p2p.d_flag, 1, ncclInt32, ncclSum, c->nccl, c->stream));
+     * stream is the barrier (stream ordered, no host involvement). A caller that moves several
+     * parts in one step (a sparse exchange) asks for it after the last part only. */
+    if (!c->p2p.skip_barrier)
+        NCCL_OK(c, ncclAllReduce(c->p2p.d_flag, c->p2p.d_flag, 1, ncclInt32, ncclSum, c->nccl, c->stream));
     if (bytes_remote) *bytes_remote += remote;
 }
 
@@ -783,7 +758,8 @@ void mps_comm_exchange_gather(struct mpsort_comm * c, const void * base, const u
         if (q != me) remote += (uint64_t) sendcnt[q] * elsize;
     }
     KERN_OK(c, mpsk_p2p_gather_alltoallv(base, sidx, dst, nrec, elsize, p, c->stream));
-    NCCL_OK(c, ncclAllReduce(c->p2p.d_flag, c->p2p.d_flag, 1, ncclInt32, ncclSum, c->nccl, c->stream));
+    if (!c->p2p.skip_barrier)
+        NCCL_OK(c, ncclAllReduce(c->p2p.d_flag, c->p2p.d_flag, 1, ncclInt32, ncclSum, c->nccl, c->stream));
     if (bytes_remote) *bytes_remote += remote;
 }
 

@@ -431,6 +431,14 @@ static void local_sort(struct mpsort_comm * c, const void * dbase, size_t n, siz
  * extraction, no index array, no payload gather. `dest` receives the sorted records;
  * it may equal dbase (in place). dbase is only read when dest != dbase.
  */
+/* (the shape alone: aligned buffers decide the rest) */
+static int rec16_shape(size_t elsize, const struct mpsort_radix_desc * d)
+{
+    if (getenv("MPSORT_NO_REC16")) return 0;
+    if (d->nwords != 1 || d->width != 8) return 0;
+    return (elsize == 16 && (d->offset == 0 || d->offset == 8)) || (elsize == 8 && d->offset == 0);
+}
+
 static int rec16_applicable(size_t elsize, const struct mpsort_radix_desc * d, const void * dbase, const void * dest)
 {
     if (getenv("MPSORT_NO_REC16")) return 0;
@@ -683,13 +691,19 @@ static void local_sort_rec16(struct mpsort_comm * c, const void * dbase, size_t 
  * stable p-way merge that prefers the lower run on ties gives the same bytes with
  * E read + E write per record instead of a full radix sort.
  * Returns 0 if the merge ran, 1 if the caller must use the radix path. */
+/* will these runs be merged (1) or re-sorted by the radix path (0)? */
+static int merge_applicable(int p, size_t outn, const struct mpsort_radix_desc * desc)
+{
+    if (key_words(desc) != 1 || p > 32 || p < 2 || outn < 4 * mpsk_merge_tile_items() || outn > 0xfffffff0u) return 0;
+    return getenv("MPSORT_NO_MERGE") == NULL;
+}
+
 static int merge_received_runs(struct mpsort_comm * c, int p, const void * recvbuf, const int64_t * rdispl,
         void * dout, size_t outn, size_t elsize, const struct mpsort_radix_desc * desc)
 {
     const size_t T = mpsk_merge_tile_items_for(recvbuf, dout, elsize, desc->offset, desc->width, desc->nwords, (uint32_t) p);
     int r;
-    if (key_words(desc) != 1 || p > 32 || p < 2 || outn < 4 * mpsk_merge_tile_items() || outn > 0xfffffff0u) return 1;
-    if (getenv("MPSORT_NO_MERGE")) return 1;
+    if (!merge_applicable(p, outn, desc)) return 1;
     /* (k + p) * S <= T with k = 3p: S = T / (4p) rounded down to a power of two */
     uint32_t S = 1;
     while ((size_t) S * 2 * 4 * (size_t) p <= T) S *= 2;
@@ -896,8 +910,11 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
         free(info);
         return;
     }
-    if (p > 1) sendbuf = mps_arena_get(c, MPS_S_SEND, n * elsize);
-    if (p > 1 && rec16_applicable(elsize, desc, dbase, sendbuf)) {
+    /* record mode sorts straight into the send buffer; index mode only needs one when it packs (no fused
+     * pack) or when peers pull from it, so it is made then */
+    if (p > 1 && (rec16_shape(elsize, desc) || c->p2p.pull || c->kind != MPS_T_NCCL || c->p2p.disabled))
+        sendbuf = mps_arena_get(c, MPS_S_SEND, n * elsize);
+    if (p > 1 && sendbuf && rec16_applicable(elsize, desc, dbase, sendbuf)) {
         local_sort_rec16(c, dbase, n, elsize, desc, sendbuf, &v1);
         c->stats.record_mode = 1;
     } else {
@@ -956,11 +973,15 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
      * decided from global facts so that every rank takes the same branch. */
     int Q = 1;
     {
-        /* default: two parts when the slices move by DMA (the merge of part 0 then overlaps the
-         * transfer of part 1: 21.0 -> 19.2 ms per sort at 8 GPUs), one when SMs do the moving
-         * (transfer and merge then slow each other down, profiles/r01_pipelined_exchange.log) */
+        /* default: several parts when the slices move by DMA or by the fused pack kernel (the merge of a part
+         * overlaps the transfer of the next, and only the last part's merge is exposed), one when grouped
+         * send/recv does the moving (transfer and merge then slow each other down, profiles/r01_pipelined_exchange.log).
+         * Measured with 2^28 16-byte records per GPU (profiles/r02_call_n2_*.log, r02_call_n8_*.log), ms per sort for
+         * 1 / 2 / 3 / 4 / 8 parts: 8 GPUs 19.6 / 17.4 / 16.7 / 16.4 / 16.3; 2 GPUs 15.2 / 14.2 / - / 13.8 / 13.9.
+         * 48-byte records at 8 GPUs: 43.5 with 2 parts, 40.2 with 4. */
         const char * e = getenv("MPSORT_EXCHANGE_PHASES");
-        const int want = e ? atoi(e) : ((c->kind == MPS_T_NCCL && !c->p2p.disabled && c->p2p.copy_engine > 0 && !c->p2p.pull) ? 2 : 1);
+        const int dma = c->kind == MPS_T_NCCL && !c->p2p.disabled && c->p2p.copy_engine > 0 && !c->p2p.pull;
+        const int want = e ? atoi(e) : (dma ? ((p >= 8 && (elsize == 16 || elsize == 8)) ? 8 : 4) : 1);
         /* parts only pay for themselves on large inputs; MPSORT_PHASES_MIN_RECORDS (records per rank,
          * default 2^22) moves the threshold -- the CPU host-flow tests use it to cut tiny inputs */
         const char * m = getenv("MPSORT_PHASES_MIN_RECORDS");
@@ -999,11 +1020,14 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
         CUDA_OK(c, cudaMemcpyAsync(d_prefix, h, ((size_t) ns * nw + ns) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
     }
     int level, round = 0;
-    /* CANDIDATE, off by default (MPSORT_PEER_SPLITTER=1; not yet run on a GPU): every level in one
-     * kernel per GPU, the sums taken over mapped peer memory (mpsk_splitter_descent_peer). The
-     * switch must be set on all ranks or on none; mapping failures fall back together. */
-    const int peer_desc = ns > 0 && ns <= 63 && level0 < nlevels && getenv("MPSORT_PEER_SPLITTER") != NULL
-                          && mps_comm_peer_boxes_prepare(c);
+    /* One process per GPU (NCCL transport): every level in ONE kernel per GPU, the per-level sums taken over
+     * mapped peer memory (mpsk_splitter_descent_peer) instead of count kernel + ncclAllReduce + select kernel
+     * per level: 17.42 -> 17.16 ms per sort at 8 GPUs, 14.15 -> 13.92 at 2 (profiles/r02_call_n8_*.log,
+     * r02_call_n2_*.log). MPSORT_NO_PEER_SPLITTER=1 keeps the all-reduce per level, which is also what rank
+     * threads of one process use (MPSORT_PEER_SPLITTER=1 turns the kernel on for them too) and the fallback
+     * when a mailbox cannot be mapped -- a collective verdict. The switches must agree on all ranks. */
+    const int peer_wanted = c->kind == MPS_T_NCCL ? getenv("MPSORT_NO_PEER_SPLITTER") == NULL : getenv("MPSORT_PEER_SPLITTER") != NULL;
+    const int peer_desc = ns > 0 && ns <= 63 && level0 < nlevels && peer_wanted && mps_comm_peer_boxes_prepare(c);
     if (peer_desc) {
         KERN_T(c, MPS_K_SPLITTER, mps_comm_peer_descent(c, v1.kv, n, nw, d_prefix, d_target, ns, level0, nlevels));
         mps_comm_peer_descent_check(c);
@@ -1077,17 +1101,17 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
     /* ---- Exchange: pack (payload gather into destination-contiguous order; the
      * destinations are contiguous slices of the sorted order, SendDispl[i] == myC[i]
      * :483-501) then, part by part, grouped send/recv or peer stores */
-    /* CANDIDATE, off by default (MPSORT_PACK_PIPELINE=1; not yet run on a GPU): with Q > 1 parts the
-     * slices of part q+1 are packed on the second stream while part q is in flight, instead of packing
-     * everything first (48-byte particles at 8 GPUs: pack 8.7 ms, then 21.5 ms of exchange). */
-    /* CANDIDATE, off by default (MPSORT_FUSED_PACK=1; not yet run on a GPU): index mode over mapped
-     * peer buffers skips the pack: one kernel gathers by sorted index and stores into the peers'
-     * receive buffers (mps_comm_exchange_gather). use_p2p is a collective verdict, so is this. */
-    const int fused_pack = use_p2p && !c->p2p.pull && v1.sorted_recs != sendbuf && n <= 0xffffffffu
-                           && getenv("MPSORT_FUSED_PACK") != NULL;
-    const int pack_pipe = !fused_pack && Q > 1 && v1.sorted_recs != sendbuf && getenv("MPSORT_PACK_PIPELINE") != NULL;
-    if (v1.sorted_recs != sendbuf && !pack_pipe && !fused_pack)
+    /* Index mode over mapped peer buffers skips the pack: ONE kernel gathers by sorted index and stores into
+     * the peers' receive buffers over NVLink (mps_comm_exchange_gather) -- no send buffer, no separate 2E+4
+     * bytes-per-record pack pass. 48-byte particles at 8 GPUs, 4 parts: 40.2 ms with pack + DMA copies, 36.2 with
+     * the pack of part q+1 beside the copy of part q, 35.7 fused (profiles/r02_call_n8_*.log); at 2 GPUs 29.7 /
+     * 27.5 / 26.3. MPSORT_NO_FUSED_PACK=1 packs first. use_p2p is a collective verdict, so is this. */
+    const int index_mode = v1.sorted_recs == NULL;
+    const int fused_pack = index_mode && use_p2p && !c->p2p.pull && n <= 0xffffffffu && getenv("MPSORT_NO_FUSED_PACK") == NULL;
+    if (index_mode && !fused_pack) {
+        if (!sendbuf) sendbuf = mps_arena_get(c, MPS_S_SEND, n * elsize);
         KERN_T(c, MPS_K_GATHER_RECORDS, mpsk_gather_records(dbase, v1.idx, sendbuf, n, elsize, c->stream));
+    }
     timer_mark(c, "Pack");
     mps_merge_ovf_begin(c);
     const int dense = mpsort_mpi_has_options(MPSORT_DISABLE_SPARSE_ALLTOALLV)
@@ -1103,6 +1127,19 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
     const int me = c->rank;
     int64_t (*recvcnt_q)[MPS_MAX_RANKS] = (int64_t (*)[MPS_MAX_RANKS]) malloc(sizeof(int64_t) * MPS_MAX_RANKS * (size_t) Q);
     int q;
+    /* A SPARSE exchange (mostly sorted input: 21 MB leave a GPU of the 4 GiB it holds) is all latency: part after
+     * part, each with its own completion barrier, took 1.4 ms at 8 GPUs with two parts. When no rank sends more than
+     * 128 MiB away, all parts move in ONE step -- every copy queued at once, one barrier -- and the merges follow.
+     * Every rank holds the whole cut matrix, so all take the same branch. */
+    int one_step = 0;
+    if (Q > 1 && use_p2p) {
+        int64_t worst = 0;
+        for (j = 0; j < p; j++) {
+            const int64_t away = nmemb[j] - (CUTV(j, (j + 1) * Q) - CUTV(j, j * Q));
+            if (away > worst) worst = away;
+        }
+        one_step = (uint64_t) worst * elsize <= ((uint64_t) 128 << 20) && !getenv("MPSORT_NO_ONE_STEP");
+    }
     for (q = 0; q < Q; q++) {
         int64_t sendoff[MPS_MAX_RANKS], sendcnt[MPS_MAX_RANKS], peer_recvoff[MPS_MAX_RANKS], peer_sendoff[MPS_MAX_RANKS];
         int k;
@@ -1115,23 +1152,7 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
             recvcnt_q[q][k] = CUTV(k, me * Q + q + 1) - CUTV(k, me * Q + q);
             peer_sendoff[k] = CUTV(k, me * Q + q);
         }
-        if (pack_pipe) {
-            /* part 0 on the main stream; part q > 0 on the second stream, after the pack of part q-1
-             * and beside the transfer of part q-1; the exchange of part q waits for it */
-            cudaStream_t main_stream = c->stream;
-            cudaEvent_t * pev = c->phase_ev + MPS_MAX_RANKS / 2;
-            if (q > 0) {
-                c->stream = c->stream2;
-                CUDA_OK(c, cudaStreamWaitEvent(c->stream, pev[q - 1], 0));
-            }
-            for (k = 0; k < p; k++)
-                if (sendcnt[k] > 0)
-                    KERN_T(c, MPS_K_GATHER_RECORDS, mpsk_gather_records(dbase, v1.idx + sendoff[k],
-                           (char *) sendbuf + (size_t) sendoff[k] * elsize, (size_t) sendcnt[k], elsize, c->stream));
-            CUDA_OK(c, cudaEventRecord(pev[q], c->stream));
-            c->stream = main_stream;
-            if (q > 0) CUDA_OK(c, cudaStreamWaitEvent(c->stream, pev[q], 0));
-        }
+        c->p2p.skip_barrier = one_step && q + 1 < Q;
         mps_kt_begin(c, MPS_K_EXCHANGE);
         if (fused_pack)
             mps_comm_exchange_gather(c, dbase, v1.idx, sendoff, sendcnt, recvbuf, peer_recvoff, elsize, &c->stats.bytes_sent_remote);
@@ -1139,8 +1160,11 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
             mps_comm_exchange(c, sendbuf, sendoff, sendcnt, recvbuf, PARTBASE(me, q), recvcnt_q[q], peer_recvoff, peer_sendoff,
                               elsize, dense, use_p2p, &c->stats.bytes_sent_remote);
         mps_kt_end(c);
-        CUDA_OK(c, cudaEventRecord(c->phase_ev[q], c->stream));
+        c->p2p.skip_barrier = 0;
+        /* (one step: no part is complete before the barrier that follows the last) */
+        if (!one_step) CUDA_OK(c, cudaEventRecord(c->phase_ev[q], c->stream));
     }
+    if (one_step) for (q = 0; q < Q; q++) CUDA_OK(c, cudaEventRecord(c->phase_ev[q], c->stream));
     timer_mark(c, "Exchange");
 
     /* ---- SecondSort: every received part is p sorted runs in source-rank order; a stable
@@ -1154,9 +1178,11 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
             int64_t rdispl[MPS_MAX_RANKS + 1];
             rdispl[0] = 0;
             for (j = 0; j < p; j++) rdispl[j + 1] = rdispl[j] + recvcnt_q[q][j];
-            /* (the fused pack candidate reads the input and the sorted permutation until its last
-             * part is out, and the merge's sample sort reuses those arena slots: no merge before that) */
-            if (Q > 1) CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->phase_ev[fused_pack ? Q - 1 : q], 0));
+            /* (the fused pack reads the input and the sorted permutation until its last part is out: an
+             * in-place sort, whose merges write that very input, and a part that is re-sorted by the radix
+             * path, which reuses the arena slots the permutation lives in, must not start before that) */
+            const int late = fused_pack && (dout == dbase || !merge_applicable(p, (size_t) cnt, desc));
+            if (Q > 1) CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->phase_ev[late ? Q - 1 : q], 0));
             char * part_in = (char *) recvbuf + (size_t) base * elsize;
             char * part_out = (char *) dout + (size_t) base * elsize;
             if (merge_received_runs(c, p, part_in, rdispl, part_out, (size_t) cnt, elsize, desc) != 0) {

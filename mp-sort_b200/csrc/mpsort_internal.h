@@ -147,8 +147,8 @@ struct mpsort_comm {
         uint64_t generation;                   /* bumped every time my exchange buffer is replaced */
         uint64_t peer_gen[MPS_MAX_RANKS];      /* generation of rank j's buffer my mapping belongs to */
         int * d_flag;                          /* device word for the completion all-reduce */
+        int skip_barrier;                      /* 1: the caller asks for the completion barrier itself (after its last part) */
         int copy_engine;                       /* >= 1: slices move by cudaMemcpyAsync (DMA engines, no SMs), that many at a time */
-        int split;                             /* pieces a large slice is cut into, moved concurrently (MPSORT_P2P_SPLIT) */
         cudaStream_t ce_stream[8];             /* copy-engine mode: peer copies fan out over these */
         cudaEvent_t ce_ev[9];
         int ce_created;

@@ -65,7 +65,7 @@ def _candidates():
     return T
 
 
-@pytest.mark.parametrize("extra", [{}, {"MPSORT_EXCHANGE_PHASES": "2"}, {"MPSORT_EXCHANGE_PHASES": "3", "MPSORT_PACK_PIPELINE": "1"},
+@pytest.mark.parametrize("extra", [{}, {"MPSORT_EXCHANGE_PHASES": "2"}, {"MPSORT_EXCHANGE_PHASES": "3"},
                                    {"MPSORT_NO_MERGE": "1"}, {"MPSORT_NO_REC16": "1", "MPSORT_NO_REBASE": "1"}, {"MPSORT_PEER_SPLITTER": "1"},
                                    {"MPSORT_NO_HYBRID": "1", "MPSORT_NO_HIST4": "1"}],
                          ids=lambda e: "+".join(sorted(e)) or "default")
@@ -80,11 +80,11 @@ def test_switches_leave_the_result_bit_exact(mock_env, extra):
     assert rc.returncode == 0 and b"CANDIDATE OK" in rc.stdout, rc.stdout.decode()[-4000:]
 
 
-@pytest.mark.parametrize("E,kind,extra", [(16, 0, {}), (48, 2, {}), (48, 2, {"MPSORT_PACK_PIPELINE": "1"}),
-                                          (24, 3, {"MPSORT_PACK_PIPELINE": "1", "MPSORT_EXCHANGE_PHASES": "4"})])
+@pytest.mark.parametrize("E,kind,extra", [(16, 0, {}), (48, 2, {}), (48, 2, {"MPSORT_EXCHANGE_PHASES": "3"}),
+                                          (24, 3, {"MPSORT_EXCHANGE_PHASES": "4"})])
 def test_exchange_in_parts_at_2_22_records_per_rank(mock_env, E, kind, extra):
     """4 rank threads x 2^22 records (the smallest size at which the exchange is cut into parts): order, tie order,
-    checksum of checksums, and that the parts were really taken; with and without the pipelined pack"""
+    checksum of checksums, and that the parts were really taken"""
     code = _candidates().WORKER_PROPS % {"root": ROOT, "E": E, "kind": kind, "log2n": 22, "passes": 0}
     if extra.get("MPSORT_EXCHANGE_PHASES", "2") != "2":
         code = code.replace('x[5]["exchange_phases"] == 2', 'x[5]["exchange_phases"] == %s' % extra["MPSORT_EXCHANGE_PHASES"])
@@ -131,7 +131,7 @@ NCCL_WORKER = os.path.join(ROOT, "tests", "support", "nccl_threads_worker.py")
 
 @pytest.mark.parametrize("p,extra,p2p", [(4, {}, 1), (2, {}, 1), (7, {"MOCK_NO_IPC": "1"}, 0), (4, {"MPSORT_NO_P2P": "1"}, 0),
                                          (3, {"MPSORT_P2P_PULL": "1"}, 1), (4, {"MPSORT_P2P_CE": "0"}, 1), (5, {"MPSORT_P2P_CE": "7"}, 1),
-                                         (6, {"MPSORT_PEER_SPLITTER": "1"}, 1), (3, {"MPSORT_PEER_SPLITTER": "1", "MOCK_NO_IPC": "1"}, 0)],
+                                         (6, {"MPSORT_NO_PEER_SPLITTER": "1"}, 1), (3, {"MPSORT_NO_FUSED_PACK": "1"}, 1), (3, {"MOCK_NO_IPC": "1", "MPSORT_NO_PEER_SPLITTER": "1"}, 0)],
                          ids=lambda v: "+".join("%s=%s" % kv for kv in sorted(v.items())) or "default" if isinstance(v, dict) else str(v))
 def test_nccl_transport_small_cases(mock_env, p, extra, p2p):
     """the cases of tests/nccl_worker.py (which needs >= 2 GPUs) over every exchange transport of mpsort_comm.c:
@@ -144,13 +144,14 @@ def test_nccl_transport_small_cases(mock_env, p, extra, p2p):
 SMALLER = {"BIG_LOG2N": "18", "MPSORT_PHASES_MIN_RECORDS": "1000"}      # the candidates: same flow at 2^18 records per rank
 
 
-@pytest.mark.parametrize("extra,phases", [({}, 2), (dict(SMALLER, MPSORT_PACK_PIPELINE="1", MPSORT_EXCHANGE_PHASES="3"), 3),
-                                          (dict(SMALLER, MPSORT_FUSED_PACK="1", MPSORT_EXCHANGE_PHASES="2"), 2)],
+@pytest.mark.parametrize("extra,phases", [({}, 4), (dict(SMALLER, MPSORT_NO_FUSED_PACK="1", MPSORT_EXCHANGE_PHASES="3"), 3),
+                                          (dict(SMALLER, MPSORT_NO_PEER_SPLITTER="1", MPSORT_EXCHANGE_PHASES="2"), 2)],
                          ids=lambda v: "+".join("%s=%s" % kv for kv in sorted(v.items())) or "default" if isinstance(v, dict) else str(v))
 def test_nccl_transport_exchange_in_parts(mock_env, extra, phases):
     """3 ranks x 2^22 records (16-byte uniform keys, 48-byte records with duplicates): the default of one process per
-    GPU -- two exchange parts over mapped peer buffers with the merge of part 0 beside the transfer of part 1, taken
-    from 2^22 records per rank on -- and the candidates that change the host flow of that path"""
+    GPU -- four exchange parts over mapped peer buffers with the merge of a part beside the transfer of the next, the
+    fused pack for 48-byte records, the peer-memory splitter kernel, taken from 2^22 records per rank on -- and the
+    switches that turn each of them off"""
     rc = run_py(mock_env, [NCCL_WORKER, "3", "big"], EXPECT_PHASES=str(phases), **extra)
     assert rc.returncode == 0 and b"NCCL THREADS OK" in rc.stdout, rc.stdout.decode()[-4000:]
 
@@ -251,16 +252,16 @@ def test_gpu_suite_host_flow_with_deferred_stream_operations(mock_env):
 MUTANTS = [
     # the bug this model found in round 1: the copy stream of the own slice was only synchronised when p == 8
     ("mpsort_comm.c", "for (k = 0; k < 8; k++) if ((used >> k) & 1u) CUDA_OK(c, cudaStreamWaitEvent(c->p2p.ce_stream[k], c->p2p.ce_ev[8], 0));",
-     "for (k = 0; k < 8 && k < p; k++) if ((used >> k) & 1u) CUDA_OK(c, cudaStreamWaitEvent(c->p2p.ce_stream[k], c->p2p.ce_ev[8], 0));"),
+     "for (k = 0; k < 8 && k < p; k++) if ((used >> k) & 1u) CUDA_OK(c, cudaStreamWaitEvent(c->p2p.ce_stream[k], c->p2p.ce_ev[8], 0));", ("3", "200", "1")),
     # the merge of a part does not wait for its transfer
-    ("mpsort_host.c", "if (Q > 1) CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->phase_ev[fused_pack ? Q - 1 : q], 0));", "/* mutant */"),
+    ("mpsort_host.c", "if (Q > 1) CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->phase_ev[late ? Q - 1 : q], 0));", "/* mutant */", ("3", "200", "1")),
     # the caller's stream does not wait for the merges on the second stream
-    ("mpsort_host.c", "CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->phase_ev[MPS_MAX_RANKS], 0));", "/* mutant */"),
+    ("mpsort_host.c", "CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->phase_ev[MPS_MAX_RANKS], 0));", "/* mutant */", ("3", "200", "1")),
 ]
 
 
-@pytest.mark.parametrize("fname,old,new", MUTANTS, ids=["own-slice-stream", "merge-before-transfer", "return-before-merge"])
-def test_stream_model_catches_seeded_synchronisation_bugs(tmp_path, mock_env, fname, old, new):
+@pytest.mark.parametrize("fname,old,new,fuzz", MUTANTS, ids=["own-slice-stream", "merge-before-transfer", "return-before-merge"])
+def test_stream_model_catches_seeded_synchronisation_bugs(tmp_path, mock_env, fname, old, new, fuzz):
     """mutation check of the checker: a copy of the host sources with ONE synchronisation removed must fail the
     randomised cases under MOCK_ASYNC (and these three do, with every seed tried)"""
     import shutil
@@ -278,7 +279,7 @@ def test_stream_model_catches_seeded_synchronisation_bugs(tmp_path, mock_env, fn
     finally:
         hostmock.CSRC = saved[0]
         hostmock.INCLUDES[:] = saved[1]
-    rc = run_py(dict(mock_env, MPSORT_LIB=so), [os.path.join(ROOT, "tests", "support", "hostflow_fuzz.py"), "3", "200", "nccl"], MOCK_ASYNC="1")
+    rc = run_py(dict(mock_env, MPSORT_LIB=so), [os.path.join(ROOT, "tests", "support", "hostflow_fuzz.py"), fuzz[0], fuzz[1], "nccl"], MOCK_ASYNC=fuzz[2])
     assert rc.returncode != 0 and b"FUZZ OK" not in rc.stdout, "the mutant went unnoticed"
 
 

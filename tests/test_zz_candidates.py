@@ -2,7 +2,6 @@
 at hand (end of round 1). They run only with MPSORT_TEST_CANDIDATES=1, so that the default suite
 states what the shipped paths do; tools/candidates_ab.sh runs them and times each candidate.
 
-  MPSORT_PACK_PIPELINE=1  index mode: pack of exchange part q+1 beside the transfer of part q
   MPSORT_FUSED_PACK=1     index mode: gather by sorted index + peer stores in one kernel (needs >= 2 GPUs)
   MPSORT_PEER_SPLITTER=1  all levels of the splitter descent in one kernel, sums over mapped peer memory
 """
@@ -98,9 +97,7 @@ sys.exit(0 if ok else 1)
 """
 
 
-@pytest.mark.parametrize("E,kind,extra", [(48, 2, {"MPSORT_PACK_PIPELINE": "1"}),
-                                          (24, 3, {"MPSORT_PACK_PIPELINE": "1"}),
-                                          (16, 0, {"MPSORT_PEER_SPLITTER": "1"})])
+@pytest.mark.parametrize("E,kind,extra", [(16, 0, {"MPSORT_PEER_SPLITTER": "1"})])
 def test_candidates_at_2_22_records_per_rank_by_properties(E, kind, extra):
     """4 rank threads x 2^22 records, exchange in two parts: global order, tie order (tags), checksum
     of checksums -- with the pipelined pack (index mode) or the peer splitter kernel switched on"""
