@@ -706,14 +706,17 @@ static void exchange_p2p(struct mpsort_comm * c, const void * sendbuf, const int
              * tests/native/mock_async.cpp). (Cutting a slice into two or four copies that move at the same time
              * was measured at two GPUs, where one copy per direction is all there is: no gain,
              * profiles/r02_call_n2_nccl_parity_parts_candidates.log -- a single copy already runs at 770 GB/s.) */
+            /* (a sparse exchange moves small slices: one at a time would be all launch latency, so they go out
+             * on seven streams at once) */
+            const int lanes = c->p2p.burst ? 7 : c->p2p.copy_engine;
             unsigned used = 0;
-            for (k = 0; k < p; k++) if (rbytes[k]) used |= 1u << (rrem[k] ? k % c->p2p.copy_engine : 7);
+            for (k = 0; k < p; k++) if (rbytes[k]) used |= 1u << (rrem[k] ? k % lanes : 7);
             CUDA_OK(c, cudaEventRecord(c->p2p.ce_ev[8], c->stream));
             for (k = 0; k < 8; k++) if ((used >> k) & 1u) CUDA_OK(c, cudaStreamWaitEvent(c->p2p.ce_stream[k], c->p2p.ce_ev[8], 0));
             for (k = 0; k < p; k++)
                 if (rbytes[k])
                     CUDA_OK(c, cudaMemcpyAsync(rdst[k], rsrc[k], (size_t) rbytes[k], cudaMemcpyDeviceToDevice,
-                                               c->p2p.ce_stream[rrem[k] ? k % c->p2p.copy_engine : 7]));
+                                               c->p2p.ce_stream[rrem[k] ? k % lanes : 7]));
             for (k = 0; k < 8; k++) {
                 if (!((used >> k) & 1u)) continue;
                 CUDA_OK(c, cudaEventRecord(c->p2p.ce_ev[k], c->p2p.ce_stream[k]));

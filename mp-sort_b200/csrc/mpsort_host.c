@@ -785,6 +785,7 @@ static uint64_t device_checksum(struct mpsort_comm * c, const void * d, size_t n
 struct rank_info {
     int64_t nmemb, outnmemb;
     uint64_t kmin[MPS_MAX_KEY_WORDS], kmax[MPS_MAX_KEY_WORDS];
+    uint64_t q01, q99;          /* single-word keys: the keys 1 % from either end of the sorted array */
 };
 
 /* gather everything on one leader, sort there, scatter by outnmemb
@@ -943,18 +944,23 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
 
     /* ---- PmaxPmin (mpsort-mpi.c:606-661): ends of the locally sorted keys */
     if (n > 0) {
-        uint64_t * h = (uint64_t *) mps_host_stage(c, 2 * MPS_MAX_KEY_WORDS * sizeof(uint64_t));
         const char * kb = (const char *) v1.kv.base;
+        uint64_t * h = (uint64_t *) mps_host_stage(c, (2 * MPS_MAX_KEY_WORDS + 2) * sizeof(uint64_t));
         for (w = 0; w < (int) nw; w++) {
             CUDA_OK(c, cudaMemcpyAsync(h + w, kb + (size_t) w * v1.kv.word_stride, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
             CUDA_OK(c, cudaMemcpyAsync(h + MPS_MAX_KEY_WORDS + w, kb + (n - 1) * v1.kv.item_stride + (size_t) w * v1.kv.word_stride,
                                        sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
         }
+        /* (two more keys for the sparse-exchange hint below) */
+        CUDA_OK(c, cudaMemcpyAsync(h + 2 * MPS_MAX_KEY_WORDS, kb + (n / 100) * v1.kv.item_stride, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(c, cudaMemcpyAsync(h + 2 * MPS_MAX_KEY_WORDS + 1, kb + (n - 1 - n / 100) * v1.kv.item_stride, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
         CUDA_OK(c, cudaStreamSynchronize(c->stream));
         for (w = 0; w < (int) nw; w++) {
             mine.kmin[w] = (h[w] ^ v1.kv.flip) + (w == 0 ? v1.kv.add : 0);
             mine.kmax[w] = (h[MPS_MAX_KEY_WORDS + w] ^ v1.kv.flip) + (w == 0 ? v1.kv.add : 0);
         }
+        mine.q01 = (h[2 * MPS_MAX_KEY_WORDS] ^ v1.kv.flip) + v1.kv.add;
+        mine.q99 = (h[2 * MPS_MAX_KEY_WORDS + 1] ^ v1.kv.flip) + v1.kv.add;
     }
     mpsort_comm_allgather_host(c, &mine, info, sizeof(mine));
     uint64_t kmin[MPS_MAX_RANKS * MPS_MAX_KEY_WORDS], kmax[MPS_MAX_RANKS * MPS_MAX_KEY_WORDS];
@@ -981,7 +987,22 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
          * 48-byte records at 8 GPUs: 43.5 with 2 parts, 40.2 with 4. */
         const char * e = getenv("MPSORT_EXCHANGE_PHASES");
         const int dma = c->kind == MPS_T_NCCL && !c->p2p.disabled && c->p2p.copy_engine > 0 && !c->p2p.pull;
-        const int want = e ? atoi(e) : (dma ? ((p >= 8 && (elsize == 16 || elsize == 8)) ? 8 : 4) : 1);
+        /* A hint that the exchange will be SPARSE (mostly sorted input): every rank keeps its record count and the
+         * ranks' key ranges, 1 % trimmed at either end, do not overlap and follow rank order. Then almost nothing
+         * moves, there is no transfer for the merges to hide behind, and parts only cost launches: two are taken
+         * (16.5 ms with 8 parts, 16.1 with 2 or 1 for config 4 at 8 GPUs, profiles/r02_call_n8_*.log). The hint only
+         * picks the number of parts; a wrong one costs time, never the result. */
+        int sparse_hint = nw == 1;
+        {
+            int prev = -1;
+            for (j = 0; j < p && sparse_hint; j++) {
+                if (nmemb[j] != outnmemb[j]) sparse_hint = 0;
+                if (nmemb[j] == 0) continue;
+                if (prev >= 0 && info[prev].q99 > info[j].q01) sparse_hint = 0;
+                prev = j;
+            }
+        }
+        const int want = e ? atoi(e) : (dma ? (sparse_hint ? 2 : ((p >= 8 && (elsize == 16 || elsize == 8)) ? 8 : 4)) : 1);
         /* parts only pay for themselves on large inputs; MPSORT_PHASES_MIN_RECORDS (records per rank,
          * default 2^22) moves the threshold -- the CPU host-flow tests use it to cut tiny inputs */
         const char * m = getenv("MPSORT_PHASES_MIN_RECORDS");
@@ -1153,6 +1174,7 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
             peer_sendoff[k] = CUTV(k, me * Q + q);
         }
         c->p2p.skip_barrier = one_step && q + 1 < Q;
+        c->p2p.burst = one_step;            /* many small copies: on all copy streams at once */
         mps_kt_begin(c, MPS_K_EXCHANGE);
         if (fused_pack)
             mps_comm_exchange_gather(c, dbase, v1.idx, sendoff, sendcnt, recvbuf, peer_recvoff, elsize, &c->stats.bytes_sent_remote);
@@ -1161,6 +1183,7 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
                               elsize, dense, use_p2p, &c->stats.bytes_sent_remote);
         mps_kt_end(c);
         c->p2p.skip_barrier = 0;
+        c->p2p.burst = 0;
         /* (one step: no part is complete before the barrier that follows the last) */
         if (!one_step) CUDA_OK(c, cudaEventRecord(c->phase_ev[q], c->stream));
     }
