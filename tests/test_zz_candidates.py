@@ -1,9 +1,12 @@
-"""Opt-in GPU checks of CANDIDATE kernels that are off by default and were written without a GPU
-at hand (end of round 1). They run only with MPSORT_TEST_CANDIDATES=1, so that the default suite
-states what the shipped paths do; tools/candidates_ab.sh runs them and times each candidate.
+"""Opt-in GPU checks of NON-DEFAULT switches (MPSORT_TEST_CANDIDATES=1), so that the default suite states what the
+shipped paths do. Round 1 wrote candidates here without a GPU at hand; round 2 measured them all
+(profiles/r02_call1..., r02_call_n2..., r02_call_n8...): the bucket merge, the persistent record pass, the pipelined pack and the
+split copies were slower or no faster and are gone; the peer-memory splitter kernel, the fused pack + exchange kernel and the
+five-pass hybrid depth became defaults (one process per GPU). What is left here:
 
-  MPSORT_FUSED_PACK=1     index mode: gather by sorted index + peer stores in one kernel (needs >= 2 GPUs)
-  MPSORT_PEER_SPLITTER=1  all levels of the splitter descent in one kernel, sums over mapped peer memory
+  MPSORT_PEER_SPLITTER=1     the splitter kernel also for rank THREADS of one process (default there: all-reduce per level)
+  MPSORT_NO_FUSED_PACK=1 / MPSORT_NO_PEER_SPLITTER=1 over NCCL processes (needs >= 2 GPUs): the fallbacks of the defaults
+  randomised cases as NCCL ranks (needs >= 2 GPUs)
 """
 import os
 import subprocess
@@ -107,10 +110,10 @@ def test_candidates_at_2_22_records_per_rank_by_properties(E, kind, extra):
     assert rc.returncode == 0 and b"CANDIDATE OK" in rc.stdout, rc.stdout.decode()[-4000:]
 
 
-@pytest.mark.parametrize("switch", ["MPSORT_FUSED_PACK", "MPSORT_PEER_SPLITTER"])
+@pytest.mark.parametrize("switch", ["MPSORT_NO_FUSED_PACK", "MPSORT_NO_PEER_SPLITTER"])
 def test_candidates_over_nccl_processes(switch):
     """one process per GPU (mapped peer memory): the NCCL worker of the default suite (48-byte and
-    16-byte records, uneven sizes, all tunings) with the candidate on"""
+    16-byte records, uneven sizes, all tunings) with one of the defaults switched off"""
     sys.path.insert(0, os.path.join(ROOT, "mp-sort_b200"))
     from mpsort import _capi as C
     ngpu = min(C.lib.mpsort_util_device_count(), 8)
