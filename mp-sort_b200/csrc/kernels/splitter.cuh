@@ -1,4 +1,4 @@
-/* kernels/splitter.cuh -- K4: splitter count / select / final; peer-memory descent candidate; u64 sum.
+/* kernels/splitter.cuh -- K4: splitter count / select / final; the peer-memory descent kernel; u64 sum.
  * Part of the single translation unit mpsort_kernels.cu (included there, in order). */
 /* ========================================================================= */
 /* K4: splitter kernels                                                      */
@@ -118,41 +118,47 @@ extern "C" int mpsk_splitter_final(struct mpsk_keyview view, size_t n, uint32_t 
 }
 
 /*
- * CANDIDATE, off by default (MPSORT_PEER_SPLITTER=1) and not yet run on a GPU: the whole byte-wise
- * descent in ONE kernel per GPU, the per-level all-reduce done over peer memory instead of one
- * ncclAllReduce + two launches per level (8 x ~60 us at 8 GPUs).
+ * The whole byte-wise descent in ONE kernel per GPU, the per-level sums taken over peer memory instead of
+ * count kernel + ncclAllReduce + select kernel per level (the default of one process per GPU).
  *
- * Every rank owns a mailbox in device memory that all peers have mapped (CUDA IPC; plain pointers
- * for rank threads of one process): counts[2][PEER_MAXS][256] u64 and one flag word per splitter.
- * Block b works on splitter b on every rank. Per level: count the 256 candidates locally
- * (splitter_count_kernel's arithmetic), store them in the own mailbox (parity = level & 1), fence,
- * release-store flag[b] = seq + level + 1; poll the same flag of every peer (acquire), then add the
- * peers' 256 counts read over NVLink and pick the digit (splitter_select_kernel's rule). All ranks
- * compute the same sums, so nothing is broadcast. Two parities suffice: a rank reaches level L+2 only
- * after every peer published level L+1, which a peer does after it has read level L.
- * Block b only ever waits for block b of the peers' kernels; <= 63 blocks are always co-resident. A
- * wait that exceeds `timeout` clock cycles sets *err and leaves (the host aborts the job) instead of
- * hanging the GPU.
+ * Every rank owns a mailbox in device memory that all peers have mapped (CUDA IPC; plain pointers for rank
+ * threads of one process): words[2 parities][source rank][splitter][256 digits]. Block b works on splitter b on
+ * every rank. Per level thread d counts the local keys <= candidate d (a binary search, from the second level on
+ * inside the range the previous level left: the searches shrink 256-fold per level), PUSHES the count into the
+ * mailbox of every peer as ONE 64-bit word {tag = seq + level + 1 : count} and then polls ITS OWN mailbox (local
+ * memory) for the words of the peers with that tag. Data and flag are one word, so no fence and no separate flag
+ * round trip is needed, and nothing is read over NVLink: a level costs one remote-store latency. All ranks compute
+ * the same sums, so nothing is broadcast. Two parities suffice: a rank reaches level L+2 only after every peer
+ * published level L+1, which a peer does after it has read level L.
+ * The first version (pull: counts in the own mailbox, a release flag per splitter, two system fences per level,
+ * peers' counts read over NVLink) took 0.33 ms for eight levels at 8 GPUs (profiles/r02_call_n8_final.log).
+ * Block b only ever waits for block b of the peers' kernels; <= 63 blocks are always co-resident. A wait that
+ * exceeds `timeout` clock cycles sets *err and leaves (the host aborts the job) instead of hanging the GPU.
  */
 #define MPSK_PEER_MAXS 63
+#define MPSK_PEER_MAXR 64
 struct PeerBoxes { unsigned long long * box[64]; };
-__host__ __device__ constexpr size_t peer_box_count_words() { return (size_t) 2 * MPSK_PEER_MAXS * 256; }
+__host__ __device__ constexpr size_t peer_box_count_words() { return (size_t) 2 * MPSK_PEER_MAXR * MPSK_PEER_MAXS * 256; }
 
-__device__ __forceinline__ u32 ld_acquire_sys_u32(const u32 * p)
-{
-    u32 v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys_u32(u32 * p, u32 v)
-{
-    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ u64 ld_relaxed_sys_u64(const u64 * p)
 {
     u64 v;
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(u64 * p, u64 v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+/* number of keys <= cand, known to lie in [lo, hi] */
+__device__ __forceinline__ u64 bound_key_in(const mpsk_keyview & v, size_t lo, size_t hi, const u64 * cand, u32 nw)
+{
+    while (lo < hi) {
+        const size_t mid = lo + ((hi - lo) >> 1);
+        if (cmp_key(v, mid, cand, nw) <= 0) lo = mid + 1; else hi = mid;
+    }
+    return (u64) lo;
 }
 
 __global__ void __launch_bounds__(256)
@@ -161,14 +167,15 @@ splitter_descent_peer_kernel(mpsk_keyview v, size_t n, u32 nw, u64 * __restrict_
                              long long timeout, u32 * __restrict__ err)
 {
     __shared__ u64 s_prefix[MPSK_MAX_KEY_WORDS];
+    __shared__ u64 s_cnt[257];                 /* [d + 1] = local keys <= candidate d; [0] = below the whole range */
     __shared__ u32 s_min, s_abort;
     const u32 b = blockIdx.x, d = threadIdx.x;
     if (d < nw) s_prefix[d] = prefix[(size_t) b * nw + d];
     if (d == 0) s_abort = 0;
     __syncthreads();
     const u64 tgt = target[b];
-    u64 * mycounts = boxes.box[me];
-    u32 * myflags = (u32 *) (boxes.box[me] + peer_box_count_words());
+    u64 * mybox = boxes.box[me];
+    size_t lo = 0, hi = n;                     /* where the local keys with the prefix decided so far sit */
     for (int level = level0; level < nlevels; level++) {
         const u32 par = (u32) level & 1u;
         const u32 byteidx = 8 * nw - 1 - (u32) level;   /* from the least significant byte */
@@ -181,47 +188,52 @@ splitter_descent_peer_kernel(mpsk_keyview v, size_t n, u32 nw, u64 * __restrict_
             else if (w == wi) x |= ((u64) d << sh) | ((sh == 0) ? 0ULL : ((1ULL << sh) - 1ULL));
             cand[w] = x;
         }
-        const u64 c = bound_key<true>(v, n, cand, nw);
-        const size_t slot = ((size_t) par * MPSK_PEER_MAXS + b) * 256 + d;
-        mycounts[slot] = c;
-        __threadfence_system();
-        if (d == 0) s_min = 255u;
-        __syncthreads();
+        const u64 c = bound_key_in(v, lo, hi, cand, nw);
+        s_cnt[d + 1] = c;
+        if (d == 0) { s_cnt[0] = (u64) lo; s_min = 255u; }
+        /* push {tag : count} to every peer, then gather the peers' words from my own mailbox */
         const u32 want = seq + (u32) level + 1u;
-        if (d == 0) st_release_sys_u32(&myflags[b], want);
-        if (d < p && d != me) {
-            const u32 * pf = (const u32 *) (boxes.box[d] + peer_box_count_words()) + b;
-            const long long t0 = clock64();
-            while ((int) (ld_acquire_sys_u32(pf) - want) < 0) {
+        const u64 word = ((u64) want << 32) | (u64) (u32) c;
+        const size_t myslot = (((size_t) par * MPSK_PEER_MAXR + me) * MPSK_PEER_MAXS + b) * 256 + d;
+        for (u32 r = 0; r < p; r++)
+            if (r != me) st_relaxed_sys_u64(boxes.box[r] + myslot, word);
+        u64 sum = c;
+        const long long t0 = clock64();
+        for (u32 r = 0; r < p; r++) {
+            if (r == me) continue;
+            const u64 * src = mybox + (((size_t) par * MPSK_PEER_MAXR + r) * MPSK_PEER_MAXS + b) * 256 + d;
+            u64 w = ld_relaxed_sys_u64(src);
+            while ((u32) (w >> 32) != want) {
                 if (clock64() - t0 > timeout) { s_abort = 1; break; }
-                __nanosleep(100);
+                __nanosleep(40);
+                w = ld_relaxed_sys_u64(src);
             }
+            sum += (u64) (u32) w;
         }
         __syncthreads();
         if (s_abort) {
             if (d == 0) atomicExch(err, 1u);
             return;
         }
-        __threadfence_system();
-        u64 sum = c;
-        for (u32 r = 0; r < p; r++)
-            if (r != me) sum += ld_relaxed_sys_u64(boxes.box[r] + slot);
         if (sum >= tgt) atomicMin(&s_min, d);
         __syncthreads();
-        if (d == 0) s_prefix[wi] |= ((u64) s_min) << sh;
+        const u32 pick = s_min;
+        lo = pick == 0 ? (size_t) s_cnt[0] : (size_t) s_cnt[pick];        /* local keys <= candidate pick - 1 */
+        hi = (size_t) s_cnt[pick + 1];
+        if (d == 0) s_prefix[wi] |= ((u64) pick) << sh;
         __syncthreads();
     }
     if (d < nw) prefix[(size_t) b * nw + d] = s_prefix[d];
 }
 
-extern "C" size_t mpsk_peer_box_bytes(void) { return peer_box_count_words() * sizeof(u64) + 256 * sizeof(u32); }
+extern "C" size_t mpsk_peer_box_bytes(void) { return peer_box_count_words() * sizeof(u64); }
 
 extern "C" int mpsk_splitter_descent_peer(struct mpsk_keyview view, size_t n, uint32_t nw,
         uint64_t * prefix, const uint64_t * target, int nsplit, int level0, int nlevels,
         uint32_t me, uint32_t p, void * const * boxes, uint32_t seq, uint32_t * err, mpsk_stream_t stream)
 {
     if (nsplit <= 0 || level0 >= nlevels) return 0;
-    if (nw > MPSK_MAX_KEY_WORDS || nsplit > MPSK_PEER_MAXS || p > 64 || me >= p) return (int) cudaErrorInvalidValue;
+    if (nw > MPSK_MAX_KEY_WORDS || nsplit > MPSK_PEER_MAXS || p > MPSK_PEER_MAXR || me >= p || n > 0xffffffffu) return (int) cudaErrorInvalidValue;
     PeerBoxes pb;
     for (u32 r = 0; r < 64; r++) pb.box[r] = r < p ? (unsigned long long *) boxes[r] : NULL;
     /* ~10 s at 2 GHz: a peer may still be in its local sort; a dead peer must not hang the box */

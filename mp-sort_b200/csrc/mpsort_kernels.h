@@ -130,10 +130,11 @@ int mpsk_splitter_select(const uint64_t * counts, const uint64_t * target,
 int mpsk_splitter_final(struct mpsk_keyview view, size_t n, uint32_t nw,
         const uint64_t * prefix, int nsplit, uint64_t * out, mpsk_stream_t stream);
 
-/* CANDIDATE (MPSORT_PEER_SPLITTER=1): all levels of the descent in one kernel, the per-level sums
- * over peer memory. boxes[r] = rank r's mailbox of mpsk_peer_box_bytes() bytes as mapped here
- * (zeroed once at allocation); seq = 256 * (number of earlier calls on this communicator);
- * *err != 0 afterwards means a peer never answered. prefix is updated in place. */
+/* All levels of the descent in one kernel, the per-level sums over peer memory (the default of one
+ * process per GPU). boxes[r] = rank r's mailbox of mpsk_peer_box_bytes() bytes as mapped here (zeroed once
+ * at allocation; every rank pushes its counts into every peer's mailbox and polls its own);
+ * seq = 256 * (number of earlier calls on this communicator); *err != 0 afterwards means a peer never
+ * answered. prefix is updated in place. */
 size_t mpsk_peer_box_bytes(void);
 int mpsk_splitter_descent_peer(struct mpsk_keyview view, size_t n, uint32_t nw,
         uint64_t * prefix, const uint64_t * target, int nsplit, int level0, int nlevels,
