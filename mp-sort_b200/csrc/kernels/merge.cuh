@@ -168,7 +168,6 @@ merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, MergeRuns 
     u32 * sA = (u32 *) (kB + MPSK_MERGE_PADDED);
     u32 * sB = sA + MPSK_MERGE_PADDED;
     __shared__ u32 seqoff[MPSK_MERGE_MAX_RUNS + 1];
-    __shared__ u32 srcbase[MPSK_MERGE_MAX_RUNS];
     __shared__ u32 s_outstart;
 
     const u32 t = blockIdx.x, p = m.p, tid = threadIdx.x, lane = tid & 31u;
@@ -177,7 +176,7 @@ merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, MergeRuns 
      * its own key loads can go out -- a fifth of all warp samples of the first version sat at that barrier
      * (ncu, profiles/r01_ncu_full_merge_tile_p8.csv). Warp 0 also leaves the offsets in shared memory for the
      * rounds; the barrier after the key staging publishes them. */
-    u32 my_seqoff, my_srcbase, cnt;
+    u32 my_seqoff, my_srcbase, cnt, pe;
     {
         u32 c0 = 0, c1 = 0;
         if (lane < p) { c0 = cut[t * p + lane]; c1 = cut[(t + 1) * p + lane]; }
@@ -193,10 +192,18 @@ merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, MergeRuns 
         my_seqoff = incl - len;                       /* lanes >= p hold the total: the run after the last starts there */
         my_srcbase = lane < p ? m.rdispl[lane] + c0 : 0u;
         cnt = __shfl_sync(FULL_MASK, incl, 31);
+        /* the rounds below merge only the runs that HAVE records in this tile (in run order: still stable):
+         * ceil(log2) of their number instead of ceil(log2 p) rounds. Mostly sorted input sends a rank records
+         * from itself and one neighbour -- one round where p = 8 would take three. */
+        const u32 nonempty = __ballot_sync(FULL_MASK, lane < p && len > 0);
+        pe = max((u32) __popc(nonempty), 1u);
         if (tid < 32) {
-            if (tid < p) { seqoff[tid] = my_seqoff; srcbase[tid] = my_srcbase; }
-            if (tid == p - 1) seqoff[p] = incl;
-            if (tid == 0) s_outstart = sum0;
+            if (lane < p && len > 0) seqoff[__popc(nonempty & ((1u << lane) - 1u))] = my_seqoff;
+            if (tid == 0) {
+                if (nonempty == 0) seqoff[0] = 0;
+                seqoff[pe] = cnt;
+                s_outstart = sum0;
+            }
         } else if (tid < 64) {
             /* the p sub-ranges of tile t + pf_dist are asked into L2 (cp.async.bulk.prefetch.L2, one lane per
              * run): this kernel waits for its scattered key loads more than for anything else */
@@ -242,15 +249,15 @@ merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, MergeRuns 
      * consecutive outputs, starting from its merge-path intersection (one binary
      * search per thread and pair instead of one per item). Ties take from A, the
      * lower runs: stable. */
-    for (u32 w = 1; w < p; w <<= 1) {
+    for (u32 w = 1; w < pe; w <<= 1) {
         u32 o = tid * VT;
         const u32 end = min(o + (u32) VT, cnt);
         u32 g = 0;                                  /* pair index: groups 2g and 2g+1 */
         while (o < end) {
-            while (seqoff[min((2 * g + 2) * w, p)] <= o) g++;
-            const u32 a0 = seqoff[min(2 * g * w, p)];
-            const u32 a1 = seqoff[min((2 * g + 1) * w, p)];
-            const u32 b1 = seqoff[min((2 * g + 2) * w, p)];
+            while (seqoff[min((2 * g + 2) * w, pe)] <= o) g++;
+            const u32 a0 = seqoff[min(2 * g * w, pe)];
+            const u32 a1 = seqoff[min((2 * g + 1) * w, pe)];
+            const u32 b1 = seqoff[min((2 * g + 2) * w, pe)];
             const u32 lenA = a1 - a0, lenB = b1 - a1;
             const u32 seg_end = min(end, b1);
             const u32 diag = o - a0;

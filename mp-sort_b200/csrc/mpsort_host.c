@@ -1175,6 +1175,7 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
         }
         c->p2p.skip_barrier = one_step && q + 1 < Q;
         c->p2p.burst = one_step;            /* many small copies: on all copy streams at once */
+        c->p2p.chained = q > 0 && !getenv("MPSORT_NO_CHAINED_PARTS");
         mps_kt_begin(c, MPS_K_EXCHANGE);
         if (fused_pack)
             mps_comm_exchange_gather(c, dbase, v1.idx, sendoff, sendcnt, recvbuf, peer_recvoff, elsize, &c->stats.bytes_sent_remote);
@@ -1184,6 +1185,7 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
         mps_kt_end(c);
         c->p2p.skip_barrier = 0;
         c->p2p.burst = 0;
+        c->p2p.chained = 0;
         /* (one step: no part is complete before the barrier that follows the last) */
         if (!one_step) CUDA_OK(c, cudaEventRecord(c->phase_ev[q], c->stream));
     }

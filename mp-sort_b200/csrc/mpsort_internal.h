@@ -149,6 +149,7 @@ struct mpsort_comm {
         int * d_flag;                          /* device word for the completion all-reduce */
         int skip_barrier;                      /* 1: the caller asks for the completion barrier itself (after its last part) */
         int burst;                             /* 1: a sparse exchange -- small slices, all copy streams at once */
+        int chained;                           /* 1: a later part of ONE exchange -- its copies queue up behind the previous part's on the copy streams, not behind the main stream */
         int copy_engine;                       /* >= 1: slices move by cudaMemcpyAsync (DMA engines, no SMs), that many at a time */
         cudaStream_t ce_stream[8];             /* copy-engine mode: peer copies fan out over these */
         cudaEvent_t ce_ev[9];

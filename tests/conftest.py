@@ -20,6 +20,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_exception_interact(node, call, report):
+    """MPSORT_TEST_INSTAFAIL=1: the failure is written out at once, not in the summary at the end of the session --
+    a run under compute-sanitizer that is killed by its time limit after a failure would lose it (tools/sanitize.sh)"""
+    if os.environ.get("MPSORT_TEST_INSTAFAIL"):
+        sys.stderr.write("\n==== FAILED %s\n%s\n" % (node.nodeid, str(report.longrepr)[-8000:]))
+        sys.stderr.flush()
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _built():
     """build the product library and the oracle once per session if missing"""

@@ -23,7 +23,7 @@ NDEV = max(1, lib.mpsort_util_device_count())
 REAL_GPU = not hasattr(lib, "mpsk_launch_count") or not hasattr(lib, "mocksync_cudaFree")    # real NCCL wants one device per rank
 SEEN = {}
 SWITCHES = ["MPSORT_NO_FUSED_PACK", "MPSORT_NO_MERGE", "MPSORT_NO_REC16", "MPSORT_NO_REBASE", "MPSORT_NO_P2P",
-            "MPSORT_P2P_PULL", "MOCK_NO_IPC", "MPSORT_PEER_SPLITTER", "MPSORT_NO_PEER_SPLITTER", "MPSORT_NO_HYBRID5"]
+            "MPSORT_P2P_PULL", "MOCK_NO_IPC", "MPSORT_PEER_SPLITTER", "MPSORT_NO_PEER_SPLITTER", "MPSORT_NO_HYBRID5", "MPSORT_NO_CHAINED_PARTS"]
 if os.environ.get("FUZZ_SWITCHES") == "shipped":       # on a real GPU: leave the unmeasured candidates out
     SWITCHES = ["MPSORT_NO_MERGE", "MPSORT_NO_REC16", "MPSORT_NO_REBASE", "MPSORT_NO_HYBRID", "MPSORT_NO_FUSED_PACK", "MPSORT_NO_PEER_SPLITTER"]
 

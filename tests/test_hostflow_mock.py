@@ -255,15 +255,17 @@ MUTANTS = [
      "for (k = 0; k < 8 && k < p; k++) if ((used >> k) & 1u) CUDA_OK(c, cudaStreamWaitEvent(c->p2p.ce_stream[k], c->p2p.ce_ev[8], 0));", ("3", "200", "1")),
     # the merge of a part does not wait for its transfer
     ("mpsort_host.c", "if (Q > 1) CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->phase_ev[late ? Q - 1 : q], 0));", "/* mutant */", ("3", "200", "1")),
+    # the copies of an exchange do not wait for the send buffer (the event of the first part is never recorded)
+    ("mpsort_comm.c", "if (!c->p2p.chained) CUDA_OK(c, cudaEventRecord(c->p2p.ce_ev[8], c->stream));", "/* mutant */", ("3", "200", "1")),
     # the caller's stream does not wait for the merges on the second stream
     ("mpsort_host.c", "CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->phase_ev[MPS_MAX_RANKS], 0));", "/* mutant */", ("3", "200", "1")),
 ]
 
 
-@pytest.mark.parametrize("fname,old,new,fuzz", MUTANTS, ids=["own-slice-stream", "merge-before-transfer", "return-before-merge"])
+@pytest.mark.parametrize("fname,old,new,fuzz", MUTANTS, ids=["own-slice-stream", "merge-before-transfer", "copies-before-send-buffer", "return-before-merge"])
 def test_stream_model_catches_seeded_synchronisation_bugs(tmp_path, mock_env, fname, old, new, fuzz):
     """mutation check of the checker: a copy of the host sources with ONE synchronisation removed must fail the
-    randomised cases under MOCK_ASYNC (and these three do, with every seed tried)"""
+    randomised cases under MOCK_ASYNC (and these four do, with every seed tried)"""
     import shutil
     csrc = str(tmp_path / "csrc")
     shutil.copytree(hostmock.CSRC, csrc, ignore=shutil.ignore_patterns("kernels"))

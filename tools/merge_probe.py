@@ -27,10 +27,20 @@ desc = C.RadixDesc(0, 8, 1, 1 if kind == 2 else 0, 0)
 runs = lib.mpsort_util_dev_malloc(0, n * E)
 out = lib.mpsort_util_dev_malloc(0, n * E)
 rd = (ctypes.c_int64 * (p + 1))()
+# PROBE_SHAPE=two: what a rank of a sort of MOSTLY SORTED input receives -- 99% from itself, 1% from one
+# neighbour, nothing from the rest (the tile kernel then runs one merge round, not log2 p)
+shape = os.environ.get("PROBE_SHAPE", "even")
+sizes = [per] * (p - 1) + [n - per * (p - 1)]
+if shape == "two" and p >= 2:
+    sizes = [0] * p
+    sizes[p // 2] = n - n // 100
+    sizes[p // 2 - 1] = n // 100
 for r in range(p):
-    rd[r + 1] = rd[r] + (per if r < p - 1 else n - per * (p - 1))
+    rd[r + 1] = rd[r] + sizes[r]
     ptr = ctypes.c_void_p(runs + rd[r] * E)
     cnt = rd[r + 1] - rd[r]
+    if cnt == 0:
+        continue
     # tags (rank << 40) + i: ties across runs must come out in run order
     lib.mpsort_util_generate_as(comm, ptr, cnt, E, kind, 0x5EED0001, r, p)
     lib.mpsort_mpi_desc_impl(ptr, cnt, E, ctypes.byref(desc), comm, 0, b"merge_probe")
@@ -48,10 +58,10 @@ kt = C.kernel_times(comm)
 bad = lib.mpsort_util_check_sorted(comm, out, n, E, ctypes.byref(desc), 1, 8, None)
 h_out = C.multiset_hash(comm, out, n, E)
 st = C.last_stats(comm, 1)
-print("%-36s merge p=%d n=2^%d E=%d kind=%d: %.3f ms per merge (wall, incl. sample sort + host syncs) = %.0f GB/s (2E per record)  "
+print("%-36s merge[%s] p=%d n=2^%d E=%d kind=%d: %.3f ms per merge (wall, incl. sample sort + host syncs) = %.0f GB/s (2E per record)  "
       "bad=%d multiset_ok=%s | %s" % (
           os.path.basename(os.environ.get("MPSORT_LIB", "default")) + " " + " ".join("%s=%s" % (k[7:], v) for k, v in sorted(os.environ.items()) if k.startswith("MPSORT_") and k != "MPSORT_LIB"),
-          p, log2n, E, kind, ms, 2.0 * E * n / ms / 1e6, bad, h_in == h_out,
+          shape, p, log2n, E, kind, ms, 2.0 * E * n / ms / 1e6, bad, h_in == h_out,
           "  ".join("%s %.3f/%d" % (k, v[0] / reps, v[1] // reps) for k, v in kt.items() if v[1])))
 if bad or h_in != h_out:
     sys.exit(1)

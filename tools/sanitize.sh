@@ -16,8 +16,9 @@ for TOOL in ${TOOLS:-memcheck racecheck synccheck initcheck}; do
   EXTRA=""
   [ "$TOOL" = memcheck ] && EXTRA="--leak-check full"
   [ "$TOOL" = initcheck ] && EXTRA="--track-unused-memory no"
-  timeout ${SANITIZE_TIMEOUT:-1500} $CS --tool $TOOL $EXTRA --target-processes all --error-exitcode 66 --log-file $LOG \
+  MPSORT_TEST_INSTAFAIL=1 timeout ${SANITIZE_TIMEOUT:-1500} $CS --tool $TOOL $EXTRA --target-processes all --error-exitcode 66 --log-file $LOG \
       python -m pytest tests/test_gpu_parity.py -q -x -m gpu -k "$SEL" > gpurun_out/sanitize_$TOOL.pytest.log 2>&1
   echo "== $TOOL: exit $? ; $(grep -c 'ERROR SUMMARY' $LOG 2>/dev/null) summaries ; $(grep 'ERROR SUMMARY' $LOG 2>/dev/null | sort | uniq -c | tr '\n' ';')"
+  grep -A60 '==== FAILED' gpurun_out/sanitize_$TOOL.pytest.log | cut -c1-240 | head -120
   tail -2 gpurun_out/sanitize_$TOOL.pytest.log
 done | tee gpurun_out/sanitize_summary.log
