@@ -235,6 +235,7 @@ struct mpsort_last_stats {
     uint32_t rebased;            /* 1: keys were sorted relative to their minimum (fewer passes) */
     uint32_t p2p_exchange;       /* 1: records moved by peer stores (CUDA IPC), 0: ncclSend/ncclRecv or copies */
     uint32_t exchange_phases;    /* parts the exchange + merge were pipelined in (1 = not pipelined) */
+    uint32_t own_slices_in_place;/* parts whose own slice was merged from the send buffer, never copied */
 };
 void mpsort_comm_last_stats(mpsort_comm_t comm, struct mpsort_last_stats * st,
                             int64_t * sendcounts, int max);

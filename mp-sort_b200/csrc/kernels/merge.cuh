@@ -37,7 +37,21 @@ struct MergeRuns {
     u32 k;            /* samples per tile */
     u32 rdispl[MPSK_MERGE_MAX_RUNS + 1];   /* run starts in records */
     u32 sstart[MPSK_MERGE_MAX_RUNS + 1];   /* first sample id of every run */
+    /* ONE run may live elsewhere: the rank's own slice, read where the local sort left it (in the send
+     * buffer) instead of being copied beside the received ones -- mostly sorted input keeps 99 % of its
+     * records, and that copy was 1.3 ms of its 14.7 ms. Record i of run self_run is at
+     * self_recv + (rdispl[self_run] + i) * elsize: the same indexing from another base. In the tile kernels
+     * bit 31 of a source index says "from self_recv" (the host only asks for this below 2^31 records). */
+    u32 self_run;                          /* MPSK_MERGE_NO_SELF: none */
+    const unsigned char * self_recv;
 };
+#define MPSK_MERGE_NO_SELF 0xffffffffu
+#define MPSK_MERGE_SELF_BIT 0x80000000u
+
+__device__ __forceinline__ const unsigned char * merge_run_base(const unsigned char * recv, const MergeRuns & m, u32 r)
+{
+    return r == m.self_run ? m.self_recv : recv;
+}
 
 __device__ __forceinline__ u64 load_key_any(const unsigned char * rec, const KeyDesc & d, bool fast8)
 {
@@ -55,7 +69,7 @@ merge_sample_kernel(const unsigned char * __restrict__ recv, KeyDesc d, bool fas
         while (s >= m.sstart[r + 1]) r++;
         const u32 j = s - m.sstart[r];
         const size_t pos = (size_t) m.rdispl[r] + (size_t) (j + 1) * m.S - 1;
-        skeys[s] = load_key_any(recv + pos * d.elsize, d, fast8);
+        skeys[s] = load_key_any(merge_run_base(recv, m, r) + pos * d.elsize, d, fast8);
     }
 }
 
@@ -115,7 +129,7 @@ merge_bounds_kernel(const unsigned char * __restrict__ recv, KeyDesc d, bool fas
             if (r == rb) {
                 c = (sid - m.sstart[rb] + 1) * m.S;
             } else {
-                const unsigned char * base = recv + (size_t) m.rdispl[r] * d.elsize;
+                const unsigned char * base = merge_run_base(recv, m, r) + (size_t) m.rdispl[r] * d.elsize;
                 u32 lo = 0, hi = len;
                 const bool upper = r < rb;
                 while (lo < hi) {
@@ -139,8 +153,9 @@ __device__ __forceinline__ void merge_prefetch_tile(const unsigned char * recv, 
     if (pf_dist == 0 || tt >= ntiles || r >= m.p) return;
     const u32 c0 = cut[tt * m.p + r], c1 = cut[(tt + 1) * m.p + r];
     if (c1 <= c0) return;
-    uintptr_t a0 = (uintptr_t) (recv + ((size_t) m.rdispl[r] + c0) * elsize);
-    uintptr_t a1 = (uintptr_t) (recv + ((size_t) m.rdispl[r] + c1) * elsize);
+    const unsigned char * base = merge_run_base(recv, m, r);
+    uintptr_t a0 = (uintptr_t) (base + ((size_t) m.rdispl[r] + c0) * elsize);
+    uintptr_t a1 = (uintptr_t) (base + ((size_t) m.rdispl[r] + c1) * elsize);
     a0 = (a0 + 15) & ~(uintptr_t) 15;
     a1 &= ~(uintptr_t) 15;
     if (a1 <= a0) return;
@@ -190,7 +205,7 @@ merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, MergeRuns 
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum0 += __shfl_xor_sync(FULL_MASK, sum0, o);
         my_seqoff = incl - len;                       /* lanes >= p hold the total: the run after the last starts there */
-        my_srcbase = lane < p ? m.rdispl[lane] + c0 : 0u;
+        my_srcbase = lane < p ? ((m.rdispl[lane] + c0) | (lane == m.self_run ? MPSK_MERGE_SELF_BIT : 0u)) : 0u;
         cnt = __shfl_sync(FULL_MASK, incl, 31);
         /* the rounds below merge only the runs that HAVE records in this tile (in run order: still stable):
          * ceil(log2) of their number instead of ceil(log2 p) rounds. Mostly sorted input sends a rank records
@@ -236,7 +251,9 @@ merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, MergeRuns 
 #pragma unroll
         for (int k = 0; k < VT; k++) {
             const u32 i = tid + k * MPSK_MERGE_THREADS;
-            if (i < cnt) key[k] = load_key_any(recv + (size_t) src[k] * d.elsize, d, FAST8);
+            if (i < cnt)
+                key[k] = load_key_any(((src[k] & MPSK_MERGE_SELF_BIT) ? m.self_recv : recv)
+                                      + (size_t) (src[k] & ~MPSK_MERGE_SELF_BIT) * d.elsize, d, FAST8);
         }
 #pragma unroll
         for (int k = 0; k < VT; k++) {
@@ -291,6 +308,7 @@ merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, MergeRuns 
     /* ---- write the records in merged order (lanes of one record move consecutive pieces) */
     const u32 lpr = LPR1 ? 1u : (u32) (d.elsize / sizeof(V));
     const V * in = (const V *) recv;
+    const V * in_self = (const V *) m.self_recv;
     V * o = (V *) out + (size_t) s_outstart * lpr;
     const u32 totalv = cnt * lpr;
     for (u32 x0 = 0; x0 < totalv; x0 += VT * MPSK_MERGE_THREADS) {
@@ -300,10 +318,12 @@ merge_tile_kernel(const unsigned char * __restrict__ recv, KeyDesc d, MergeRuns 
             const u32 x = x0 + tid + k * MPSK_MERGE_THREADS;
             if (x < totalv) {
                 if (LPR1) {
-                    v[k] = in[sA[MPD(x)]];
+                    const u32 s = sA[MPD(x)];
+                    v[k] = ((s & MPSK_MERGE_SELF_BIT) ? in_self : in)[s & ~MPSK_MERGE_SELF_BIT];
                 } else {
                     const u32 i = x / lpr, part = x - i * lpr;
-                    v[k] = in[(size_t) sA[MPD(i)] * lpr + part];
+                    const u32 s = sA[MPD(i)];
+                    v[k] = ((s & MPSK_MERGE_SELF_BIT) ? in_self : in)[(size_t) (s & ~MPSK_MERGE_SELF_BIT) * lpr + part];
                 }
             }
         }
@@ -371,7 +391,7 @@ merge_tile_rec16_kernel(const uint4 * __restrict__ recv, u64 flip, MergeRuns m,
             if (i < cnt) {
                 u32 r = 0;
                 while (i >= seqoff[r + 1]) r++;
-                rec[k] = recv[srcbase[r] + (i - seqoff[r])];
+                rec[k] = (r == m.self_run ? (const uint4 *) m.self_recv : recv)[srcbase[r] + (i - seqoff[r])];
             }
         }
 #pragma unroll
@@ -447,15 +467,18 @@ extern "C" size_t mpsk_merge_tile_items(void) { return MPSK_MERGE_TILE; }
 
 extern "C" int mpsk_merge_samples(const void * recv, size_t elsize, size_t offset, uint32_t width,
         uint32_t nwords, int is_signed, uint32_t p, uint32_t S, uint32_t k,
-        const uint32_t * rdispl, const uint32_t * sstart, uint64_t * skeys, mpsk_stream_t stream)
+        const uint32_t * rdispl, const uint32_t * sstart, uint32_t self_run, const void * self_recv,
+        uint64_t * skeys, mpsk_stream_t stream)
 {
     if (p > MPSK_MERGE_MAX_RUNS) return (int) cudaErrorInvalidValue;
     MergeRuns m; m.p = p; m.S = S; m.k = k;
+    m.self_run = self_recv ? self_run : MPSK_MERGE_NO_SELF; m.self_recv = (const unsigned char *) self_recv;
     for (u32 r = 0; r <= p; r++) { m.rdispl[r] = rdispl[r]; m.sstart[r] = sstart[r]; }
     const u32 ns = sstart[p];
     if (ns == 0) return 0;
     KeyDesc d; d.elsize = elsize; d.offset = offset; d.width = width; d.nwords = nwords; d.is_signed = is_signed; d.g = 0; d.sub = 0;
-    const bool fast8 = (width == 8) && (nwords == 1) && (elsize % 8 == 0) && (offset % 8 == 0) && ((((uintptr_t) recv) & 7) == 0);
+    const bool fast8 = (width == 8) && (nwords == 1) && (elsize % 8 == 0) && (offset % 8 == 0)
+                       && (((((uintptr_t) recv) | ((uintptr_t) self_recv)) & 7) == 0);
     u32 blocks = (ns + 255) / 256;
     if (blocks > (u32) num_sms() * 8) blocks = (u32) num_sms() * 8;
     merge_sample_kernel<<<blocks, 256, 0, (cudaStream_t) stream>>>((const unsigned char *) recv, d, fast8, m, (u64 *) skeys);
@@ -467,7 +490,7 @@ extern "C" int mpsk_merge_rank_samples(const uint64_t * skeys, uint32_t p, const
         uint64_t * sorted_skeys, uint32_t * sorted_sid, mpsk_stream_t stream)
 {
     if (p > MPSK_MERGE_MAX_RUNS) return (int) cudaErrorInvalidValue;
-    MergeRuns m; m.p = p; m.S = 0; m.k = 0;
+    MergeRuns m; m.p = p; m.S = 0; m.k = 0; m.self_run = MPSK_MERGE_NO_SELF; m.self_recv = NULL;
     for (u32 r = 0; r <= p; r++) { m.rdispl[r] = 0; m.sstart[r] = sstart[r]; }
     const u32 ns = sstart[p];
     if (ns == 0) return 0;
@@ -516,22 +539,26 @@ static int launch_merge_tiles(const void * recv, KeyDesc d, bool fast8, const Me
 
 extern "C" int mpsk_merge_runs(const void * recv, void * out, size_t elsize, size_t offset, uint32_t width,
         uint32_t nwords, int is_signed, uint32_t p, uint32_t S, uint32_t k,
-        const uint32_t * rdispl, const uint32_t * sstart,
+        const uint32_t * rdispl, const uint32_t * sstart, uint32_t self_run, const void * self_recv,
         const uint64_t * sorted_skeys, const uint32_t * sorted_sid, uint32_t ntiles,
         uint32_t * cut, uint32_t * overflow, mpsk_stream_t stream_)
 {
     if (p > MPSK_MERGE_MAX_RUNS) return (int) cudaErrorInvalidValue;
+    if (self_recv && (self_run >= p || rdispl[p] >= MPSK_MERGE_SELF_BIT)) return (int) cudaErrorInvalidValue;
     cudaStream_t stream = (cudaStream_t) stream_;
     MergeRuns m; m.p = p; m.S = S; m.k = k;
+    m.self_run = self_recv ? self_run : MPSK_MERGE_NO_SELF; m.self_recv = (const unsigned char *) self_recv;
     for (u32 r = 0; r <= p; r++) { m.rdispl[r] = rdispl[r]; m.sstart[r] = sstart[r]; }
     KeyDesc d; d.elsize = elsize; d.offset = offset; d.width = width; d.nwords = nwords; d.is_signed = is_signed; d.g = 0; d.sub = 0;
-    const bool fast8 = (width == 8) && (nwords == 1) && (elsize % 8 == 0) && (offset % 8 == 0) && ((((uintptr_t) recv) & 7) == 0);
+    /* (every alignment question is asked of both bases) */
+    const void * recv_probe = (const void *) (((uintptr_t) recv) | ((uintptr_t) self_recv));
+    const bool fast8 = (width == 8) && (nwords == 1) && (elsize % 8 == 0) && (offset % 8 == 0) && ((((uintptr_t) recv_probe) & 7) == 0);
     const u32 total = (ntiles + 1) * p;
     u32 blocks = (total + 255) / 256;
     merge_bounds_kernel<<<blocks, 256, 0, stream>>>((const unsigned char *) recv, d, fast8, m,
                                                     (const u64 *) sorted_skeys, sorted_sid, ntiles, cut);
     CUDA_LAUNCH_CHECK();
-    if (p == 2 && merge_rec16_ok(recv, out, elsize, offset, width, nwords)) {
+    if (p == 2 && merge_rec16_ok(recv_probe, out, elsize, offset, width, nwords)) {
         const int smem = MPSK_MERGE16_PADDED * 16 * 2;
         const u64 flip = is_signed ? (1ULL << 63) : 0ULL;
         cudaError_t e;
@@ -549,7 +576,7 @@ extern "C" int mpsk_merge_runs(const void * recv, void * out, size_t elsize, siz
         CUDA_LAUNCH_CHECK();
         return 0;
     }
-    const uintptr_t a = ((uintptr_t) recv) | ((uintptr_t) out) | (uintptr_t) elsize;
+    const uintptr_t a = ((uintptr_t) recv_probe) | ((uintptr_t) out) | (uintptr_t) elsize;
     if ((a & 15) == 0) return launch_merge_tiles<uint4>(recv, d, fast8, m, cut, out, overflow, ntiles, stream);
     if ((a & 7) == 0) return launch_merge_tiles<u64>(recv, d, fast8, m, cut, out, overflow, ntiles, stream);
     if ((a & 3) == 0) return launch_merge_tiles<u32>(recv, d, fast8, m, cut, out, overflow, ntiles, stream);

@@ -338,7 +338,7 @@ void mpsort_comm_destroy(mpsort_comm_t c)
     if (c->p2p.d_flag) cudaFree(c->p2p.d_flag);
     if (c->p2p.ce_created) {
         for (s = 0; s < 8; s++) cudaStreamDestroy(c->p2p.ce_stream[s]);
-        for (s = 0; s < 9; s++) cudaEventDestroy(c->p2p.ce_ev[s]);
+        for (s = 0; s < 10; s++) cudaEventDestroy(c->p2p.ce_ev[s]);
     }
     if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->io_created) {
@@ -533,7 +533,7 @@ void mps_comm_exchange(struct mpsort_comm * c, const void * sendbuf, const int64
             }
         }
         NCCL_OK(c, ncclGroupEnd());
-        if (sendcnt[me] > 0)
+        if (sendcnt[me] > 0 && !c->p2p.skip_self)
             CUDA_OK(c, cudaMemcpyAsync((char *) recvbuf + (size_t) rdispl[me] * elsize,
                                        (const char *) sendbuf + (size_t) sendoff[me] * elsize,
                                        (size_t) sendcnt[me] * elsize, cudaMemcpyDeviceToDevice, c->stream));
@@ -545,7 +545,7 @@ void mps_comm_exchange(struct mpsort_comm * c, const void * sendbuf, const int64
     c->grp->slot2[me] = sendbuf;
     local_barrier(c);
     for (j = 0; j < p; j++) {
-        if (recvcnt[j] <= 0) continue;
+        if (recvcnt[j] <= 0 || (j == me && c->p2p.skip_self)) continue;
         const char * src = (const char *) c->grp->slot2[j] + (size_t) peer_sendoff[j] * elsize;
         CUDA_OK(c, cudaMemcpyAsync((char *) recvbuf + (size_t) rdispl[j] * elsize, src,
                                    (size_t) recvcnt[j] * elsize, cudaMemcpyDefault, c->stream));
@@ -680,6 +680,7 @@ static void exchange_p2p(struct mpsort_comm * c, const void * sendbuf, const int
             if (k != me) remote += bytes[k];
         }
     }
+    if (c->p2p.skip_self) bytes[me] = 0;     /* the merge reads my own slice where it is */
     {
         /* segments in shifted order: me+1, me+2, ..., me (self last) */
         const void * rsrc[MPS_MAX_RANKS];
@@ -695,7 +696,7 @@ static void exchange_p2p(struct mpsort_comm * c, const void * sendbuf, const int
              * earlier part (MPSORT_EXCHANGE_PHASES) can have the whole GPU meanwhile */
             if (!c->p2p.ce_created) {
                 for (k = 0; k < 8; k++) CUDA_OK(c, cudaStreamCreateWithFlags(&c->p2p.ce_stream[k], cudaStreamNonBlocking));
-                for (k = 0; k < 9; k++) CUDA_OK(c, cudaEventCreateWithFlags(&c->p2p.ce_ev[k], cudaEventDisableTiming));
+                for (k = 0; k < 10; k++) CUDA_OK(c, cudaEventCreateWithFlags(&c->p2p.ce_ev[k], cudaEventDisableTiming));
                 c->p2p.ce_created = 1;
             }
             /* remote slices in shifted order (me+1, me+2, ...: at every step the pairs form a
@@ -711,14 +712,26 @@ static void exchange_p2p(struct mpsort_comm * c, const void * sendbuf, const int
             const int lanes = c->p2p.burst ? 7 : c->p2p.copy_engine;
             unsigned used = 0;
             for (k = 0; k < p; k++) if (rbytes[k]) used |= 1u << (rrem[k] ? k % lanes : 7);
-            /* The send buffer was complete, and every rank past its local sort, before the FIRST part of an
-             * exchange: the copies of the later parts (chained) queue up behind the earlier ones on the copy
-             * streams and do NOT wait for the main stream, where the completion barrier of the part before sits.
-             * With that wait the links idled for a barrier (an all-reduce, its launch, two event hand-overs:
-             * ~0.1 ms) after every part -- 0.8 ms of an 8-part exchange at 8 GPUs. The parts land in disjoint
-             * slices of the receive buffers, so a copy of part q+1 never touches what a merge of part q reads. */
-            if (!c->p2p.chained) CUDA_OK(c, cudaEventRecord(c->p2p.ce_ev[8], c->stream));
-            for (k = 0; k < 8; k++) if ((used >> k) & 1u) CUDA_OK(c, cudaStreamWaitEvent(c->p2p.ce_stream[k], c->p2p.ce_ev[8], 0));
+            /* What the copies of this part wait for (the gate). The send buffer was complete, and every rank
+             * past its local sort, before the FIRST part of an exchange, and the parts land in disjoint slices
+             * of the receive buffers, so nothing but the first part's gate is NEEDED; what the gate decides is
+             * how far the ranks may drift apart:
+             *   chained 0  the main stream as it is now, i.e. behind the completion barrier of the part before:
+             *              every part starts in lock step, and the shifted order keeps the pairs a permutation;
+             *              the links idle for that barrier (~0.1 ms) after every part;
+             *   chained 1  the gate of the first part: the copies of all parts queue up back to back. Two GPUs
+             *              (one peer, nothing to collide with): 13.49 -> 13.13 ms. Eight GPUs: the ranks drift,
+             *              several senders meet at one receiver and the exchange takes 6.9 ms instead of 5.95
+             *              (profiles/r02_call_n2c_*.log, r02_call_n8_c_*.log);
+             *   chained 2  the main stream as it was when the part BEFORE started (behind the barrier of the part
+             *              before that): the links stay busy during a barrier, the drift is bounded by one part. */
+            cudaEvent_t gate = c->p2p.ce_ev[8];
+            if (c->p2p.chained != 1) {
+                cudaEvent_t now = c->p2p.ce_ev[8 + (c->p2p.part & 1)];
+                CUDA_OK(c, cudaEventRecord(now, c->stream));
+                gate = (c->p2p.chained == 2 && c->p2p.part > 0) ? c->p2p.ce_ev[8 + ((c->p2p.part - 1) & 1)] : now;
+            }
+            for (k = 0; k < 8; k++) if ((used >> k) & 1u) CUDA_OK(c, cudaStreamWaitEvent(c->p2p.ce_stream[k], gate, 0));
             for (k = 0; k < p; k++)
                 if (rbytes[k])
                     CUDA_OK(c, cudaMemcpyAsync(rdst[k], rsrc[k], (size_t) rbytes[k], cudaMemcpyDeviceToDevice,

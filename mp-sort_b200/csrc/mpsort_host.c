@@ -698,10 +698,17 @@ static int merge_applicable(int p, size_t outn, const struct mpsort_radix_desc *
     return getenv("MPSORT_NO_MERGE") == NULL;
 }
 
+/* self_run >= 0: run self_run is not in recvbuf -- its first record is at self_ptr (the rank's own slice,
+ * still in the send buffer where the local sort left it; no transport copied it, mps_comm_exchange with
+ * p2p.skip_self). The kernels index that run from the base that puts record rdispl[self_run] at self_ptr. */
 static int merge_received_runs(struct mpsort_comm * c, int p, const void * recvbuf, const int64_t * rdispl,
-        void * dout, size_t outn, size_t elsize, const struct mpsort_radix_desc * desc)
+        void * dout, size_t outn, size_t elsize, const struct mpsort_radix_desc * desc, int self_run, const void * self_ptr)
 {
-    const size_t T = mpsk_merge_tile_items_for(recvbuf, dout, elsize, desc->offset, desc->width, desc->nwords, (uint32_t) p);
+    const void * self_recv = NULL;
+    if (self_run >= 0 && self_ptr)
+        self_recv = (const void *) ((uintptr_t) self_ptr - (uintptr_t) ((uint64_t) rdispl[self_run] * elsize));
+    const size_t T = mpsk_merge_tile_items_for((const void *) ((uintptr_t) recvbuf | (uintptr_t) self_recv), dout, elsize,
+                                               desc->offset, desc->width, desc->nwords, (uint32_t) p);
     int r;
     if (!merge_applicable(p, outn, desc)) return 1;
     /* (k + p) * S <= T with k = 3p: S = T / (4p) rounded down to a power of two */
@@ -727,10 +734,11 @@ static int merge_received_runs(struct mpsort_comm * c, int p, const void * recvb
      * searches in the other runs' lists) -> tile bounds + tiles. Tiles that break their bound (never
      * happens) are counted in c->d_merge_ovf and looked at once, after the sort's final synchronisation. */
     KERN_T(c, MPS_K_MERGE, mpsk_merge_samples(recvbuf, elsize, desc->offset, desc->width, desc->nwords, desc->is_signed,
-                                              (uint32_t) p, S, k, rd, ss, skeys, c->stream));
+                                              (uint32_t) p, S, k, rd, ss, (uint32_t) self_run, self_recv, skeys, c->stream));
     KERN_T(c, MPS_K_MERGE, mpsk_merge_rank_samples(skeys, (uint32_t) p, ss, sorted_skeys, sorted_sid, c->stream));
     KERN_T(c, MPS_K_MERGE, mpsk_merge_runs(recvbuf, dout, elsize, desc->offset, desc->width, desc->nwords, desc->is_signed,
-                                           (uint32_t) p, S, k, rd, ss, sorted_skeys, sorted_sid, ntiles, cut, c->d_merge_ovf, c->stream));
+                                           (uint32_t) p, S, k, rd, ss, (uint32_t) self_run, self_recv, sorted_skeys, sorted_sid, ntiles, cut,
+                                           c->d_merge_ovf, c->stream));
     c->stats.second_sort_merge_tiles += ntiles;
     return 0;
 }
@@ -744,7 +752,7 @@ int mpsort_util_merge_runs(mpsort_comm_t c, int p, const void * runs, const int6
 {
     CUDA_OK(c, cudaSetDevice(c->device));
     mps_merge_ovf_begin(c);
-    const int rc = merge_received_runs(c, p, runs, rdispl, out, (size_t) (rdispl[p] - rdispl[0]), elsize, desc);
+    const int rc = merge_received_runs(c, p, runs, rdispl, out, (size_t) (rdispl[p] - rdispl[0]), elsize, desc, -1, NULL);
     mps_merge_ovf_fetch(c);
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
     mps_merge_ovf_check(c);
@@ -1147,11 +1155,17 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
     if (Q > 1 && !c->stream2) CUDA_OK(c, cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     const int me = c->rank;
     int64_t (*recvcnt_q)[MPS_MAX_RANKS] = (int64_t (*)[MPS_MAX_RANKS]) malloc(sizeof(int64_t) * MPS_MAX_RANKS * (size_t) Q);
+    int self_direct[MPS_MAX_RANKS];
+    const char * self_ptr[MPS_MAX_RANKS];
     int q;
     /* A SPARSE exchange (mostly sorted input: 21 MB leave a GPU of the 4 GiB it holds) is all latency: part after
      * part, each with its own completion barrier, took 1.4 ms at 8 GPUs with two parts. When no rank sends more than
      * 128 MiB away, all parts move in ONE step -- every copy queued at once, one barrier -- and the merges follow.
      * Every rank holds the whole cut matrix, so all take the same branch. */
+    /* how the copies of part q+1 follow those of part q (exchange_p2p): back to back with one peer, in lock
+     * step behind every part's barrier with more (measured); MPSORT_CHAINED_PARTS=0/1/2 overrides */
+    const char * chain_env = getenv("MPSORT_CHAINED_PARTS");
+    const int chain_mode = getenv("MPSORT_NO_CHAINED_PARTS") ? 0 : (chain_env ? atoi(chain_env) : (p == 2 ? 1 : 0));
     int one_step = 0;
     if (Q > 1 && use_p2p) {
         int64_t worst = 0;
@@ -1173,9 +1187,22 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
             recvcnt_q[q][k] = CUTV(k, me * Q + q + 1) - CUTV(k, me * Q + q);
             peer_sendoff[k] = CUTV(k, me * Q + q);
         }
+        /* My own slice of a part that will be MERGED stays where it is: the merge reads run `me` from the send
+         * buffer (sorted records, or the packed ones), no transport copies it. Mostly sorted input keeps 99 % of
+         * its records: that copy alone was 1.3 ms of 14.7 (profiles/r02_call_n8_c_*.log). A part that takes the
+         * radix fallback needs its runs side by side and gets the copy. */
+        {
+            const int64_t cnt_q = PARTBASE(me, q + 1) - PARTBASE(me, q);
+            self_direct[q] = sendbuf != NULL && !fused_pack && recvcnt_q[q][me] > 0 && cnt_q < ((int64_t) 1 << 31)
+                             && merge_applicable(p, (size_t) cnt_q, desc) && !getenv("MPSORT_NO_SELF_IN_PLACE");
+            self_ptr[q] = self_direct[q] ? (const char *) sendbuf + (size_t) sendoff[me] * elsize : NULL;
+            c->stats.own_slices_in_place += (uint32_t) self_direct[q];
+        }
+        c->p2p.skip_self = self_direct[q];
         c->p2p.skip_barrier = one_step && q + 1 < Q;
         c->p2p.burst = one_step;            /* many small copies: on all copy streams at once */
-        c->p2p.chained = q > 0 && !getenv("MPSORT_NO_CHAINED_PARTS");
+        c->p2p.part = q;
+        c->p2p.chained = q > 0 ? chain_mode : 0;
         mps_kt_begin(c, MPS_K_EXCHANGE);
         if (fused_pack)
             mps_comm_exchange_gather(c, dbase, v1.idx, sendoff, sendcnt, recvbuf, peer_recvoff, elsize, &c->stats.bytes_sent_remote);
@@ -1186,6 +1213,8 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
         c->p2p.skip_barrier = 0;
         c->p2p.burst = 0;
         c->p2p.chained = 0;
+        c->p2p.part = 0;
+        c->p2p.skip_self = 0;
         /* (one step: no part is complete before the barrier that follows the last) */
         if (!one_step) CUDA_OK(c, cudaEventRecord(c->phase_ev[q], c->stream));
     }
@@ -1210,8 +1239,12 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
             if (Q > 1) CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->phase_ev[late ? Q - 1 : q], 0));
             char * part_in = (char *) recvbuf + (size_t) base * elsize;
             char * part_out = (char *) dout + (size_t) base * elsize;
-            if (merge_received_runs(c, p, part_in, rdispl, part_out, (size_t) cnt, elsize, desc) != 0) {
+            if (merge_received_runs(c, p, part_in, rdispl, part_out, (size_t) cnt, elsize, desc,
+                                    self_direct[q] ? me : -1, self_ptr[q]) != 0) {
                 struct sorted_view v2;
+                if (self_direct[q])          /* (cannot happen: the same test chose both; never leave a hole) */
+                    CUDA_OK(c, cudaMemcpyAsync(part_in + (size_t) rdispl[me] * elsize, self_ptr[q], (size_t) recvcnt_q[q][me] * elsize,
+                                               cudaMemcpyDeviceToDevice, c->stream));
                 local_sort(c, part_in, (size_t) cnt, elsize, desc, 0, 1, &v2);
                 KERN_T(c, MPS_K_GATHER_RECORDS, mpsk_gather_records(part_in, v2.idx, part_out, (size_t) cnt, elsize, c->stream));
                 c->stats.second_sort_passes = v2.npasses;

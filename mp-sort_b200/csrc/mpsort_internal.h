@@ -149,10 +149,12 @@ struct mpsort_comm {
         int * d_flag;                          /* device word for the completion all-reduce */
         int skip_barrier;                      /* 1: the caller asks for the completion barrier itself (after its last part) */
         int burst;                             /* 1: a sparse exchange -- small slices, all copy streams at once */
-        int chained;                           /* 1: a later part of ONE exchange -- its copies queue up behind the previous part's on the copy streams, not behind the main stream */
+        int skip_self;                         /* 1: the caller merges its own slice from the send buffer -- no transport copies it (any transport) */
+        int chained;                           /* a later part of ONE exchange: what its copies wait for (exchange_p2p: 0 the barrier before, 1 nothing, 2 the barrier before that) */
+        int part;                              /* index of the part within its exchange */
         int copy_engine;                       /* >= 1: slices move by cudaMemcpyAsync (DMA engines, no SMs), that many at a time */
         cudaStream_t ce_stream[8];             /* copy-engine mode: peer copies fan out over these */
-        cudaEvent_t ce_ev[9];
+        cudaEvent_t ce_ev[10];                 /* [0..7] end of a copy stream's part; [8], [9] gates (exchange_p2p) */
         int ce_created;
     } p2p;
 };

@@ -153,21 +153,26 @@ int mpsk_sum_u64(uint64_t * dst, const uint64_t * const * srcs, int nsrc, size_t
  *   mpsk_merge_rank_samples orders them stably by key (sorted_skeys, sorted_sid = permutation);
  *   mpsk_merge_runs     computes cut[(ntiles+1)*p] and merges tile by tile into out.
  * *overflow (device, zeroed by the caller) counts tiles that exceeded the bound
- * (never happens; such a tile is left unwritten instead of corrupting memory). */
+ * (never happens; such a tile is left unwritten instead of corrupting memory).
+ * self_recv != NULL: run self_run is NOT in recv -- its record i is at self_recv + (rdispl[self_run] + i) *
+ * elsize (the same indexing from another base): a rank's own slice is merged from where the local sort left
+ * it and never copied. Needs rdispl[p] < 2^31. For mpsk_merge_tile_items_for pass recv | self_recv (only the
+ * alignment of the pointer is looked at). */
 size_t mpsk_merge_tile_items(void);
 /* tile size the merge will use for these buffers (16-byte records get their own kernel) */
 size_t mpsk_merge_tile_items_for(const void * recv, const void * out, size_t elsize, size_t offset,
         uint32_t width, uint32_t nwords, uint32_t p);
 int mpsk_merge_samples(const void * recv, size_t elsize, size_t offset, uint32_t width,
         uint32_t nwords, int is_signed, uint32_t p, uint32_t S, uint32_t k,
-        const uint32_t * rdispl, const uint32_t * sstart, uint64_t * skeys, mpsk_stream_t stream);
+        const uint32_t * rdispl, const uint32_t * sstart, uint32_t self_run, const void * self_recv,
+        uint64_t * skeys, mpsk_stream_t stream);
 /* sorted_skeys / sorted_sid = the samples in (key, run, position) order and their sample ids;
  * each run's samples are sorted already, so every sample ranks itself by p - 1 binary searches */
 int mpsk_merge_rank_samples(const uint64_t * skeys, uint32_t p, const uint32_t * sstart,
         uint64_t * sorted_skeys, uint32_t * sorted_sid, mpsk_stream_t stream);
 int mpsk_merge_runs(const void * recv, void * out, size_t elsize, size_t offset, uint32_t width,
         uint32_t nwords, int is_signed, uint32_t p, uint32_t S, uint32_t k,
-        const uint32_t * rdispl, const uint32_t * sstart,
+        const uint32_t * rdispl, const uint32_t * sstart, uint32_t self_run, const void * self_recv,
         const uint64_t * sorted_skeys, const uint32_t * sorted_sid, uint32_t ntiles,
         uint32_t * cut, uint32_t * overflow, mpsk_stream_t stream);
 

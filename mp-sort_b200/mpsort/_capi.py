@@ -60,7 +60,8 @@ class LastStats(ctypes.Structure):
                 ("bytes_sent_remote", c_u64), ("second_sort_merge_tiles", ctypes.c_uint32),
                 ("record_mode", ctypes.c_uint32), ("hybrid", ctypes.c_uint32),
                 ("hybrid_long_runs", ctypes.c_uint32), ("rebased", ctypes.c_uint32),
-                ("p2p_exchange", ctypes.c_uint32), ("exchange_phases", ctypes.c_uint32)]
+                ("p2p_exchange", ctypes.c_uint32), ("exchange_phases", ctypes.c_uint32),
+                ("own_slices_in_place", ctypes.c_uint32)]
 
 
 def _proto(name, restype, *argtypes):

@@ -73,9 +73,9 @@ int K(mpsk_splitter_select)(const uint64_t *, const uint64_t *, uint64_t *, uint
 int K(mpsk_splitter_final)(struct mpsk_keyview, size_t, uint32_t, const uint64_t *, int, uint64_t *, mpsk_stream_t);
 int K(mpsk_splitter_descent_peer)(struct mpsk_keyview, size_t, uint32_t, uint64_t *, const uint64_t *, int, int, int, uint32_t, uint32_t, void * const *, uint32_t, uint32_t *, mpsk_stream_t);
 int K(mpsk_sum_u64)(uint64_t *, const uint64_t * const *, int, size_t, mpsk_stream_t);
-int K(mpsk_merge_samples)(const void *, size_t, size_t, uint32_t, uint32_t, int, uint32_t, uint32_t, uint32_t, const uint32_t *, const uint32_t *, uint64_t *, mpsk_stream_t);
+int K(mpsk_merge_samples)(const void *, size_t, size_t, uint32_t, uint32_t, int, uint32_t, uint32_t, uint32_t, const uint32_t *, const uint32_t *, uint32_t, const void *, uint64_t *, mpsk_stream_t);
 int K(mpsk_merge_rank_samples)(const uint64_t *, uint32_t, const uint32_t *, uint64_t *, uint32_t *, mpsk_stream_t);
-int K(mpsk_merge_runs)(const void *, void *, size_t, size_t, uint32_t, uint32_t, int, uint32_t, uint32_t, uint32_t, const uint32_t *, const uint32_t *, const uint64_t *, const uint32_t *, uint32_t, uint32_t *, uint32_t *, mpsk_stream_t);
+int K(mpsk_merge_runs)(const void *, void *, size_t, size_t, uint32_t, uint32_t, int, uint32_t, uint32_t, uint32_t, const uint32_t *, const uint32_t *, uint32_t, const void *, const uint64_t *, const uint32_t *, uint32_t, uint32_t *, uint32_t *, mpsk_stream_t);
 int K(mpsk_p2p_alltoallv)(const void * const *, void * const *, const uint64_t *, const unsigned char *, int, mpsk_stream_t);
 int K(mpsk_p2p_gather_alltoallv)(const void *, const uint32_t * const *, void * const *, const uint64_t *, size_t, int, mpsk_stream_t);
 int K(mpsk_checksum)(const void *, size_t, uint64_t *, mpsk_stream_t);
@@ -490,10 +490,11 @@ int mpsk_sum_u64(uint64_t * dst, const uint64_t * const * srcs, int nsrc, size_t
 }
 
 int mpsk_merge_samples(const void * recv, size_t elsize, size_t offset, uint32_t width, uint32_t nwords, int is_signed,
-        uint32_t p, uint32_t S, uint32_t k, const uint32_t * rdispl, const uint32_t * sstart, uint64_t * skeys, mpsk_stream_t stream)
+        uint32_t p, uint32_t S, uint32_t k, const uint32_t * rdispl, const uint32_t * sstart, uint32_t self_run, const void * self_recv,
+        uint64_t * skeys, mpsk_stream_t stream)
 {
     auto rd = snap(rdispl, (size_t) p + 1), ss = snap(sstart, (size_t) p + 1);
-    LAUNCH(stream, K(mpsk_merge_samples)(recv, elsize, offset, width, nwords, is_signed, p, S, k, rd->data(), ss->data(), skeys, stream));
+    LAUNCH(stream, K(mpsk_merge_samples)(recv, elsize, offset, width, nwords, is_signed, p, S, k, rd->data(), ss->data(), self_run, self_recv, skeys, stream));
 }
 
 int mpsk_merge_rank_samples(const uint64_t * skeys, uint32_t p, const uint32_t * sstart, uint64_t * sorted_skeys,
@@ -505,13 +506,13 @@ int mpsk_merge_rank_samples(const uint64_t * skeys, uint32_t p, const uint32_t *
 }
 
 int mpsk_merge_runs(const void * recv, void * out, size_t elsize, size_t offset, uint32_t width, uint32_t nwords, int is_signed,
-        uint32_t p, uint32_t S, uint32_t k, const uint32_t * rdispl, const uint32_t * sstart,
+        uint32_t p, uint32_t S, uint32_t k, const uint32_t * rdispl, const uint32_t * sstart, uint32_t self_run, const void * self_recv,
         const uint64_t * sorted_skeys, const uint32_t * sorted_sid, uint32_t ntiles, uint32_t * cut, uint32_t * overflow,
         mpsk_stream_t stream)
 {
     if (p > 32) return (int) cudaErrorInvalidValue;
     auto rd = snap(rdispl, (size_t) p + 1), ss = snap(sstart, (size_t) p + 1);
-    LAUNCH(stream, K(mpsk_merge_runs)(recv, out, elsize, offset, width, nwords, is_signed, p, S, k, rd->data(), ss->data(),
+    LAUNCH(stream, K(mpsk_merge_runs)(recv, out, elsize, offset, width, nwords, is_signed, p, S, k, rd->data(), ss->data(), self_run, self_recv,
                                       sorted_skeys, sorted_sid, ntiles, cut, overflow, stream));
 }
 

@@ -812,8 +812,17 @@ size_t mpsk_merge_tile_items_for(const void * recv, const void * out, size_t els
     return 4096;
 }
 
+/* record i (an index into the receive buffer's layout) of run r: the one run that was not copied is read from
+ * its own base with the same index (mpsort_kernels.h) */
+static const unsigned char * merge_rec(const void * recv, uint32_t r, uint32_t self_run, const void * self_recv, size_t i, size_t elsize)
+{
+    const uintptr_t base = (self_recv && r == self_run) ? (uintptr_t) self_recv : (uintptr_t) recv;
+    return (const unsigned char *) (base + i * elsize);
+}
+
 int mpsk_merge_samples(const void * recv, size_t elsize, size_t offset, uint32_t width, uint32_t nwords, int is_signed,
-        uint32_t p, uint32_t S, uint32_t k, const uint32_t * rdispl, const uint32_t * sstart, uint64_t * skeys, mpsk_stream_t stream)
+        uint32_t p, uint32_t S, uint32_t k, const uint32_t * rdispl, const uint32_t * sstart, uint32_t self_run, const void * self_recv,
+        uint64_t * skeys, mpsk_stream_t stream)
 {
     uint32_t r, j;
     (void) k; (void) stream;
@@ -822,7 +831,7 @@ int mpsk_merge_samples(const void * recv, size_t elsize, size_t offset, uint32_t
     for (r = 0; r < p; r++)
         for (j = 0; j < sstart[r + 1] - sstart[r]; j++) {
             const size_t pos = (size_t) rdispl[r] + (size_t) (j + 1) * S - 1;
-            skeys[sstart[r] + j] = pack_word((const unsigned char *) recv + pos * elsize, offset, width, nwords, is_signed, 0);
+            skeys[sstart[r] + j] = pack_word(merge_rec(recv, r, self_run, self_recv, pos, elsize), offset, width, nwords, is_signed, 0);
         }
     return 0;
 }
@@ -849,14 +858,14 @@ int mpsk_merge_rank_samples(const uint64_t * skeys, uint32_t p, const uint32_t *
 }
 
 int mpsk_merge_runs(const void * recv, void * out, size_t elsize, size_t offset, uint32_t width, uint32_t nwords, int is_signed,
-        uint32_t p, uint32_t S, uint32_t k, const uint32_t * rdispl, const uint32_t * sstart,
+        uint32_t p, uint32_t S, uint32_t k, const uint32_t * rdispl, const uint32_t * sstart, uint32_t self_run, const void * self_recv,
         const uint64_t * sorted_skeys, const uint32_t * sorted_sid, uint32_t ntiles, uint32_t * cut, uint32_t * overflow,
         mpsk_stream_t stream)
 {
     uint32_t head[64], r;
     size_t o = 0;
     (void) S; (void) k; (void) sstart; (void) sorted_skeys; (void) sorted_sid; (void) ntiles; (void) cut; (void) overflow; (void) stream;
-    if (p > 32) return (int) cudaErrorInvalidValue;
+    if (p > 32 || (self_recv && (self_run >= p || rdispl[p] >= 0x80000000u))) return (int) cudaErrorInvalidValue;
     LAUNCHED();
     for (r = 0; r < p; r++) head[r] = rdispl[r];
     for (;;) {
@@ -864,11 +873,11 @@ int mpsk_merge_runs(const void * recv, void * out, size_t elsize, size_t offset,
         uint64_t kb = 0;
         for (r = 0; r < p; r++) {
             if (head[r] >= rdispl[r + 1]) continue;
-            const uint64_t kr = pack_word((const unsigned char *) recv + (size_t) head[r] * elsize, offset, width, nwords, is_signed, 0);
+            const uint64_t kr = pack_word(merge_rec(recv, r, self_run, self_recv, head[r], elsize), offset, width, nwords, is_signed, 0);
             if (best < 0 || kr < kb) { best = (int) r; kb = kr; }      /* ties: the lower run */
         }
         if (best < 0) break;
-        memcpy((char *) out + o * elsize, (const char *) recv + (size_t) head[best] * elsize, elsize);
+        memcpy((char *) out + o * elsize, merge_rec(recv, (uint32_t) best, self_run, self_recv, head[best], elsize), elsize);
         head[best]++;
         o++;
     }

@@ -23,7 +23,7 @@ NDEV = max(1, lib.mpsort_util_device_count())
 REAL_GPU = not hasattr(lib, "mpsk_launch_count") or not hasattr(lib, "mocksync_cudaFree")    # real NCCL wants one device per rank
 SEEN = {}
 SWITCHES = ["MPSORT_NO_FUSED_PACK", "MPSORT_NO_MERGE", "MPSORT_NO_REC16", "MPSORT_NO_REBASE", "MPSORT_NO_P2P",
-            "MPSORT_P2P_PULL", "MOCK_NO_IPC", "MPSORT_PEER_SPLITTER", "MPSORT_NO_PEER_SPLITTER", "MPSORT_NO_HYBRID5", "MPSORT_NO_CHAINED_PARTS"]
+            "MPSORT_P2P_PULL", "MOCK_NO_IPC", "MPSORT_PEER_SPLITTER", "MPSORT_NO_PEER_SPLITTER", "MPSORT_NO_HYBRID5", "MPSORT_NO_CHAINED_PARTS", "MPSORT_NO_SELF_IN_PLACE"]
 if os.environ.get("FUZZ_SWITCHES") == "shipped":       # on a real GPU: leave the unmeasured candidates out
     SWITCHES = ["MPSORT_NO_MERGE", "MPSORT_NO_REC16", "MPSORT_NO_REBASE", "MPSORT_NO_HYBRID", "MPSORT_NO_FUSED_PACK", "MPSORT_NO_PEER_SPLITTER"]
 
@@ -149,6 +149,11 @@ def main():
         for k in par["switches"]:
             os.environ[k] = "1"
         os.environ["MPSORT_P2P_CE"] = str(int(rng.choice([1, 1, 0, 3])))
+        # what the copies of a later exchange part wait for (exchange_p2p): the default of p, or one of the three gates
+        os.environ.pop("MPSORT_CHAINED_PARTS", None)
+        if i % 4:
+            os.environ["MPSORT_CHAINED_PARTS"] = str(i % 4 - 1)
+        par["chained"] = os.environ.get("MPSORT_CHAINED_PARTS", "default")
         more = []
         if rng.integers(0, 3) == 0:
             # the same communicator sorts two more inputs of other sizes (same record and key shape)

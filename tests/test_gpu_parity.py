@@ -371,6 +371,14 @@ def test_second_sort_merge_path(p, elsize, desc, distinct):
     out, stats = sort_group(recs, outsizes, desc, C.MPSORT_DISABLE_GATHER_SORT)
     assert same(out, exp)
     assert all(st["second_sort_merge_tiles"] > 0 for st in stats), "the merge path did not run"
+    # every rank that keeps records merged them from its send buffer (no self copy); with the copy: the same bytes
+    assert [st["own_slices_in_place"] for st in stats] == [int(st["sendcounts"][r] > 0) for r, st in enumerate(stats)]
+    os.environ["MPSORT_NO_SELF_IN_PLACE"] = "1"
+    try:
+        out1, stats1 = sort_group(recs, outsizes, desc, C.MPSORT_DISABLE_GATHER_SORT)
+    finally:
+        del os.environ["MPSORT_NO_SELF_IN_PLACE"]
+    assert same(out1, exp) and all(st["own_slices_in_place"] == 0 and st["second_sort_merge_tiles"] > 0 for st in stats1)
     # and the radix SecondSort gives the same bytes
     os.environ["MPSORT_NO_MERGE"] = "1"
     try:

@@ -251,12 +251,12 @@ def test_gpu_suite_host_flow_with_deferred_stream_operations(mock_env):
 
 MUTANTS = [
     # the bug this model found in round 1: the copy stream of the own slice was only synchronised when p == 8
-    ("mpsort_comm.c", "for (k = 0; k < 8; k++) if ((used >> k) & 1u) CUDA_OK(c, cudaStreamWaitEvent(c->p2p.ce_stream[k], c->p2p.ce_ev[8], 0));",
-     "for (k = 0; k < 8 && k < p; k++) if ((used >> k) & 1u) CUDA_OK(c, cudaStreamWaitEvent(c->p2p.ce_stream[k], c->p2p.ce_ev[8], 0));", ("3", "200", "1")),
+    ("mpsort_comm.c", "for (k = 0; k < 8; k++) if ((used >> k) & 1u) CUDA_OK(c, cudaStreamWaitEvent(c->p2p.ce_stream[k], gate, 0));",
+     "for (k = 0; k < 8 && k < p; k++) if ((used >> k) & 1u) CUDA_OK(c, cudaStreamWaitEvent(c->p2p.ce_stream[k], gate, 0));", ("3", "200", "1")),
     # the merge of a part does not wait for its transfer
     ("mpsort_host.c", "if (Q > 1) CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->phase_ev[late ? Q - 1 : q], 0));", "/* mutant */", ("3", "200", "1")),
     # the copies of an exchange do not wait for the send buffer (the event of the first part is never recorded)
-    ("mpsort_comm.c", "if (!c->p2p.chained) CUDA_OK(c, cudaEventRecord(c->p2p.ce_ev[8], c->stream));", "/* mutant */", ("3", "200", "1")),
+    ("mpsort_comm.c", "CUDA_OK(c, cudaEventRecord(now, c->stream));", "/* mutant */", ("3", "200", "1")),
     # the caller's stream does not wait for the merges on the second stream
     ("mpsort_host.c", "CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->phase_ev[MPS_MAX_RANKS], 0));", "/* mutant */", ("3", "200", "1")),
 ]
