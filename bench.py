@@ -242,7 +242,8 @@ def parity_preflight(comm, lib, C, mpsort, np, log2n=22):
                     "generator_equals_oracle": gen_ok, "device_resident_equals_oracle": dev_ok,
                     "host_api_equals_oracle": api_ok,
                     "exchange_parts": st["exchange_phases"], "p2p_exchange": st["p2p_exchange"],
-                    "merge_tiles": st["second_sort_merge_tiles"], "hybrid": st["hybrid"], "record_mode": st["record_mode"]}
+                    "merge_tiles": st["second_sort_merge_tiles"], "hybrid": st["hybrid"], "record_mode": st["record_mode"],
+                    "own_slices_merged_in_place": st.get("own_slices_in_place", 0)}
             oks = comm.allgather((gen_ok, dev_ok, api_ok, st["second_sort_merge_tiles"]))
             case["all_ranks_ok"] = all(a and b and c for a, b, c, _ in oks)
             case["merge_tiles_all_ranks"] = [o[3] for o in oks]
@@ -397,7 +398,8 @@ def measure(comm, lib, C, workload, log2n, K, W, clocks=None):
         "exchange": {"bytes_sent_remote_rank0": stats["bytes_sent_remote"], "ms": ex_ms,
                      "gb_per_s_per_gpu": (stats["bytes_sent_remote"] / (ex_ms * 1e-3) / 1e9) if ex_ms and stats["bytes_sent_remote"] else None,
                      "frac_of_nvlink_900": (stats["bytes_sent_remote"] / (ex_ms * 1e-3) / 1e9 / 900.0) if ex_ms and stats["bytes_sent_remote"] else None,
-                     "splitter_rounds": stats["splitter_rounds"]},
+                     "splitter_rounds": stats["splitter_rounds"],
+                     "own_slices_merged_in_place": stats.get("own_slices_in_place", 0)},
         "verified": "order + tie order + rank boundaries + 64-bit multiset hash (sum and xor of mix64-folded records) "
                     "of every rank's input and output",
     }
