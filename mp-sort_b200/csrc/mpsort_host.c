@@ -991,7 +991,8 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
          * overlaps the transfer of the next, and only the last part's merge is exposed), one when grouped
          * send/recv does the moving (transfer and merge then slow each other down, profiles/r01_pipelined_exchange.log).
          * Measured with 2^28 16-byte records per GPU (profiles/r02_call_n2_*.log, r02_call_n8_*.log), ms per sort for
-         * 1 / 2 / 3 / 4 / 8 parts: 8 GPUs 19.6 / 17.4 / 16.7 / 16.4 / 16.3; 2 GPUs 15.2 / 14.2 / - / 13.8 / 13.9.
+         * 1 / 2 / 3 / 4 / 8 parts: 8 GPUs 19.6 / 17.4 / 16.7 / 16.4 / 16.3; 2 GPUs 15.2 / 14.2 / - / 13.8 / 13.9;
+         * 4 GPUs (final kernels, profiles/r02_call_n4_parts.log) 4 / 6 / 8 parts: 14.52 / 14.36 / 14.34.
          * 48-byte records at 8 GPUs: 43.5 with 2 parts, 40.2 with 4. */
         const char * e = getenv("MPSORT_EXCHANGE_PHASES");
         const int dma = c->kind == MPS_T_NCCL && !c->p2p.disabled && c->p2p.copy_engine > 0 && !c->p2p.pull;
@@ -1010,7 +1011,7 @@ static void histogram_sort(struct mpsort_comm * c, const void * dbase, size_t n,
                 prev = j;
             }
         }
-        const int want = e ? atoi(e) : (dma ? (sparse_hint ? 2 : ((p >= 8 && (elsize == 16 || elsize == 8)) ? 8 : 4)) : 1);
+        const int want = e ? atoi(e) : (dma ? (sparse_hint ? 2 : ((p >= 4 && (elsize == 16 || elsize == 8)) ? 8 : 4)) : 1);
         /* parts only pay for themselves on large inputs; MPSORT_PHASES_MIN_RECORDS (records per rank,
          * default 2^22) moves the threshold -- the CPU host-flow tests use it to cut tiny inputs */
         const char * m = getenv("MPSORT_PHASES_MIN_RECORDS");
