@@ -6,8 +6,8 @@ run on one machine; NCCL process-per-GPU cases need >= 2 GPUs.
 
 Full-size cases (BASELINE.json: 2^28 16-byte records) are checked through
 size-independent properties -- sortedness, tie order by tag, an order-independent multiset
-hash of whole records -- and, for config B, byte for byte against the unmodified reference
-run on the host cores (oracle/_ref)."""
+hash of whole records -- and, for configs B, 4 and 5 on one GPU, byte for byte against the unmodified
+reference run on the host cores (oracle/_ref)."""
 import ctypes
 import os
 import subprocess
@@ -529,13 +529,10 @@ def test_full_size_config_b_by_properties():
     comm.destroy()
 
 
-@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref (the compiled reference) is not in this tree")
-def test_full_size_config_b_bytes_equal_the_reference(tmp_path):
-    """BASELINE.json configs[1] at FULL size, byte for byte: the unmodified reference
-    (oracle/_ref/bench16 -> mpsort_mpi_newarray, one MPI-shim rank per host core) and one B200
-    sort the same 2^28 16-byte records. The reference's R ranks generate R chunks; the GPU holds
-    their rank-order concatenation, whose stable sort is the reference's output contract."""
-    log2n, E = 28, 16
+def _full_size_against_the_reference(tmp_path, log2n, E, kind):
+    """the unmodified reference (oracle/_ref/bench16 -> mpsort_mpi_newarray, one MPI-shim rank per host core) and
+    one B200 sort the same 2^log2n records. The reference's R ranks generate R chunks; the GPU holds their
+    rank-order concatenation, whose stable sort is the reference's output contract. Returns the GPU sort's statistics."""
     cores = os.cpu_count() or 1
     R = 1
     while R * 2 <= min(cores, 32):
@@ -544,10 +541,10 @@ def test_full_size_config_b_bytes_equal_the_reference(tmp_path):
     comm = mpsort.Comm.self(0)
     buf = lib.mpsort_util_dev_malloc(0, n * E)
     for r in range(R):
-        lib.mpsort_util_generate_as(comm.handle, ctypes.c_void_p(buf + r * per * E), per, E, 0, 0x5EED0001, r, R)
-    lib.mpsort_mpi_desc_impl(buf, n, E, ctypes.byref(C.RadixDesc(0, 8, 1, 0, 0)), comm.handle, 0, b"fullsize_ref")
-    assert C.last_stats(comm.handle, 1)["hybrid"] == 1
-    res = O.run_bench16(R, per, elsize=E, kind=0, reps=1, timeout=1500, outdir=str(tmp_path))
+        lib.mpsort_util_generate_as(comm.handle, ctypes.c_void_p(buf + r * per * E), per, E, kind, 0x5EED0001, r, R)
+    lib.mpsort_mpi_desc_impl(buf, n, E, ctypes.byref(C.RadixDesc(0, 8, 1, 1 if kind == 2 else 0, 0)), comm.handle, 0, b"fullsize_ref")
+    st = C.last_stats(comm.handle, 1)
+    res = O.run_bench16(R, per, elsize=E, kind=kind, reps=1, timeout=1500, outdir=str(tmp_path))
     got = np.empty((per, E), np.uint8)
     for r in range(R):
         lib.mpsort_util_memcpy(0, got.ctypes.data, ctypes.c_void_p(buf + r * per * E), per * E)
@@ -557,6 +554,25 @@ def test_full_size_config_b_bytes_equal_the_reference(tmp_path):
     lib.mpsort_util_dev_free(0, buf)
     comm.destroy()
     print("reference: %d ranks, %.1f s per sort" % (R, res["best_seconds"]))
+    return st
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref (the compiled reference) is not in this tree")
+def test_full_size_config_b_bytes_equal_the_reference(tmp_path):
+    """BASELINE.json configs[1] at FULL size, byte for byte: 2^28 uniform 16-byte records (record mode + hybrid)"""
+    st = _full_size_against_the_reference(tmp_path, 28, 16, 0)
+    assert st["hybrid"] == 1 and st["record_mode"] == 1
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref (the compiled reference) is not in this tree")
+@pytest.mark.parametrize("log2n,E,kind", [(28, 16, 1), (27, 48, 2)], ids=["mostly_sorted16", "particles48"])
+def test_full_size_configs_4_and_5_bytes_equal_the_reference(tmp_path, log2n, E, kind):
+    """BASELINE.json configs[3] and [4] on one GPU at full per-GPU size, byte for byte against the unmodified
+    reference: 2^28 mostly sorted 16-byte records (the predictor's choice of depth, runs of equal high parts fixed up
+    in place) and 2^27 48-byte particles with skewed signed ids and 5 % duplicates (index mode, range compression,
+    ties in input order, the payload gather)"""
+    st = _full_size_against_the_reference(tmp_path, log2n, E, kind)
+    assert st["record_mode"] == (1 if E == 16 else 0)
 
 
 def test_large_particles48_and_mostly_sorted_by_properties():

@@ -42,9 +42,10 @@ def test_mock_provides_every_symbol_the_host_code_uses(mock_env):
     assert os.path.exists(mock_env["MPSORT_LIB"])
 
 
-# the two full-size property tests take minutes as CPU loops; their host flow is the same as the 2^22 cases below
+# the full-size tests take minutes as CPU loops; their host flow is the same as the 2^22 cases below
 BIG = ["tests/test_gpu_parity.py::test_full_size_config_b_by_properties",
        "tests/test_gpu_parity.py::test_full_size_config_b_bytes_equal_the_reference",
+       "tests/test_gpu_parity.py::test_full_size_configs_4_and_5_bytes_equal_the_reference",
        "tests/test_gpu_parity.py::test_large_particles48_and_mostly_sorted_by_properties"]
 
 
