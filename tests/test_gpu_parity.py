@@ -659,3 +659,21 @@ def test_nccl_process_per_gpu():
                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     assert rc.returncode == 0, rc.stdout.decode()[-4000:]
     assert b"NCCL PARITY OK" in rc.stdout
+
+
+@pytest.mark.skipif(lib.mpsort_util_device_count() < 2, reason="needs >= 2 GPUs (run with gpurun --gpus 2)")
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref (the compiled reference) is not in this tree")
+@pytest.mark.parametrize("kind", [0, 1], ids=["uniform16", "mostly_sorted16"])
+def test_nccl_full_size_bytes_equal_the_reference(kind):
+    """two processes, two GPUs, 2^28 16-byte records each through the production transport (IPC-mapped DMA exchange in
+    parts, peer splitter kernel, own slice merged in place): every byte equal to the unmodified reference's output for the
+    same 2^29 records (tests/support/nccl_fullsize_worker.py)"""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29519", KIND=str(kind))
+    rc = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                         "--master-addr", "127.0.0.1", "--master-port", "29519",
+                         os.path.join(ROOT, "tests", "support", "nccl_fullsize_worker.py")], env=env, timeout=1500,
+                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    print(rc.stdout.decode()[-1500:])
+    assert rc.returncode == 0, rc.stdout.decode()[-4000:]
+    assert b"NCCL FULL SIZE OK" in rc.stdout
+
